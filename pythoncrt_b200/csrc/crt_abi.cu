@@ -1,0 +1,371 @@
+// crt_abi.cu — implementation of include/crt_b200.h: context, tables, launch logic.
+// Pure CUDA runtime; no torch, no CPU compute path.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/crt_b200.h"
+#include "crt_derive.h"
+#include "crt_kernels.cuh"
+#include "crt_fused.cuh"
+
+using namespace crt;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct HostRing {                       // crt_process_host staging
+    static constexpr int SLOTS = 3;
+    uint8_t* d_in[SLOTS] = {nullptr, nullptr, nullptr};
+    uint8_t* d_out[SLOTS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t in_ready[SLOTS] = {}, done[SLOTS] = {}, out_ready[SLOTS] = {};
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    int chunk_frames = 0;
+    bool ready = false;
+};
+
+}  // namespace
+
+struct crt_ctx {
+    int device = 0, W = 0, H = 0;
+    crt_params p{};
+    bool have_params = false;
+    void* tab[CRT_TABLE_COUNT] = {};
+    size_t tab_bytes[CRT_TABLE_COUNT] = {};
+    Lerp1 *dn_x = nullptr, *dn_y = nullptr, *up_x = nullptr, *up_y = nullptr, *nz_x = nullptr, *nz_y = nullptr;
+    int nz_grain = 0;
+    Scratch scratch{nullptr, nullptr, nullptr};
+    float* noise_buf = nullptr;
+    int32_t* glitch_buf = nullptr;
+    size_t glitch_cap = 0;
+    float* state = nullptr;             // host-API persistence state
+    int state_valid = 0;
+    HostRing ring;
+    Dev dev{};
+    bool dev_ok = false;
+    int policy = 0;
+    FusedPlan plan{};
+    std::string err;
+};
+
+namespace {
+
+int fail(crt_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, CRT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+int upload(crt_ctx* ctx, Lerp1** dst, const std::vector<Lerp1>& v) {
+    if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    CU(cudaMalloc((void**)dst, v.size() * sizeof(Lerp1)));
+    CU(cudaMemcpy(*dst, v.data(), v.size() * sizeof(Lerp1), cudaMemcpyHostToDevice));
+    return CRT_OK;
+}
+
+// Derive the device parameter block (crt_derive.h) from the context's parameters and tables.
+int build_dev(crt_ctx* ctx) {
+    const crt_params& p = ctx->p;
+    if (p.noise_strength > 0.0 && p.grain_size > 1 && ctx->nz_grain != p.grain_size) {
+        const int gh = ctx->H / p.grain_size > 1 ? ctx->H / p.grain_size : 1, gw = ctx->W / p.grain_size > 1 ? ctx->W / p.grain_size : 1;
+        int rc = upload(ctx, &ctx->nz_x, linear_coords(ctx->W, gw)); if (rc) return rc;
+        rc = upload(ctx, &ctx->nz_y, linear_coords(ctx->H, gh)); if (rc) return rc;
+        ctx->nz_grain = p.grain_size;
+    }
+    TablePtrs t{};
+    for (int i = 0; i < CRT_TABLE_COUNT; ++i) { t.tab[i] = ctx->tab[i]; t.bytes[i] = ctx->tab_bytes[i]; }
+    t.dn_x = ctx->dn_x; t.dn_y = ctx->dn_y; t.up_x = ctx->up_x; t.up_y = ctx->up_y; t.nz_x = ctx->nz_x; t.nz_y = ctx->nz_y;
+    std::string err;
+    int rc = derive_dev(p, ctx->W, ctx->H, t, &ctx->dev, &err);
+    if (rc) return fail(ctx, rc, err);
+    ctx->dev_ok = true;
+    ctx->plan = plan_fused(ctx->dev, glitch_active(p), p.glitch_amp_px);
+    return CRT_OK;
+}
+
+int ensure_scratch(crt_ctx* ctx) {
+    const Dev& d = ctx->dev;
+    const size_t px = (size_t)d.W * d.H;
+    if (d.bloom_mode == 1 && !ctx->scratch.ds) CU(cudaMalloc((void**)&ctx->scratch.ds, (size_t)d.hw * d.hh * 3 * sizeof(float)));
+    if (d.bloom_mode == 2 && !ctx->scratch.bl) CU(cudaMalloc((void**)&ctx->scratch.bl, px * 3 * sizeof(float)));
+    if (d.warp_on && !ctx->scratch.q) CU(cudaMalloc((void**)&ctx->scratch.q, px * 3 * sizeof(float)));
+    return CRT_OK;
+}
+
+int gen_glitch(crt_ctx* ctx, const crt_frame& fr, const GlitchGeom& g, int32_t* d_offs, cudaStream_t st) {
+    if (g.rows <= 0) return CRT_OK;
+    if (g.rows > 12000) return fail(ctx, CRT_ERR_UNSUPPORTED, "glitch band taller than 12000 rows");
+    k_glitch_gen<<<1, GLITCH_THREADS, (size_t)g.rows * sizeof(float), st>>>(d_offs, g.rows, g.nseg, ctx->p.variant == CRT_VARIANT_EXPORT ? 1 : 0,
+                                                                           (float)ctx->p.glitch_amp_px, ctx->p.noise_seed ^ 0x9E3779B97F4A7C15ull, fr.frame_index);
+    CU(cudaGetLastError());
+    return CRT_OK;
+}
+
+// One frame through the staged kernels.
+int run_staged(crt_ctx* ctx, const FrameDev& f, const uint8_t* d_in, uint8_t* d_out, float* d_state, int has_prev, float* d_img,
+               cudaStream_t st, int* launches) {
+    const Dev& d = ctx->dev;
+    int rc = ensure_scratch(ctx); if (rc) return rc;
+    dim3 blk(32, 8);
+    if (d.bloom_mode == 1) {
+        dim3 grd((d.hw + 31) / 32, (d.hh + 7) / 8);
+        k_bloom_down<<<grd, blk, 0, st>>>(d, d_in, ctx->scratch.ds); ++*launches;
+    } else if (d.bloom_mode == 2) {
+        const int r = d.ksize / 2;
+        size_t smem = ((size_t)(GAUSS_TH + 2 * r) * (GAUSS_TW + 2 * r) + (size_t)(GAUSS_TH + 2 * r) * GAUSS_TW) * 3 * sizeof(float);
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_bloom_gauss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grd((d.W + GAUSS_TW - 1) / GAUSS_TW, (d.H + GAUSS_TH - 1) / GAUSS_TH);
+        k_bloom_gauss<<<grd, blk, smem, st>>>(d, d_in, ctx->scratch.bl); ++*launches;
+    }
+    dim3 grd((d.W + 31) / 32, (d.H + 7) / 8);
+    if (d.warp_on) { k_pre_warp<<<grd, blk, 0, st>>>(d, f, d_in, ctx->scratch); ++*launches; }
+    k_output<<<grd, blk, 0, st>>>(d, f, d_in, ctx->scratch, has_prev, d_state, d_out, d_img); ++*launches;
+    CU(cudaGetLastError());
+    return CRT_OK;
+}
+
+int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_state, int state_valid, float* d_img,
+                 const crt_frame* frames, int n_frames, cudaStream_t st, crt_launch_info* info) {
+    if (!ctx) return CRT_ERR_INVALID;
+    if (!ctx->have_params) return fail(ctx, CRT_ERR_INVALID, "crt_set_params has not been called");
+    if (!ctx->dev_ok) { int rc = build_dev(ctx); if (rc) return rc; }
+    if (n_frames < 0 || (n_frames > 0 && (!d_in || !frames || (!d_out && !d_img)))) return fail(ctx, CRT_ERR_INVALID, "null buffer");
+    const crt_params& p = ctx->p;
+    const Dev& d = ctx->dev;
+    const bool persist = p.persistence > 0.0 && !d_img;
+    if (persist && !d_state) return fail(ctx, CRT_ERR_INVALID, "persistence > 0 needs a state buffer");
+    CU(cudaSetDevice(ctx->device));
+    const size_t frame_px = (size_t)d.W * d.H;
+    const GlitchGeom gg = glitch_geom(p, d.W, d.H);
+    int launches = 0, fused_used = 0;
+    const bool want_fused = ctx->policy != 1 && ctx->plan.ok && !d_img;
+    if (ctx->policy == 2 && !want_fused) return fail(ctx, CRT_ERR_UNSUPPORTED, std::string("fused kernel not available: ") + ctx->plan.why);
+    for (int i = 0; i < n_frames; ++i) {
+        const crt_frame& fr = frames[i];
+        FrameDev f = derive_frame(p, fr);
+        if (d.noise_on) {
+            f.noise = fr.d_noise;
+            if (!f.noise) {
+                if (p.noise_mode != 1) return fail(ctx, CRT_ERR_INVALID, "noise_strength > 0 with noise_mode 0 needs crt_frame.d_noise");
+                if (!ctx->noise_buf) CU(cudaMalloc((void**)&ctx->noise_buf, frame_px * sizeof(float)));
+                const int cells = d.gh * d.gw;
+                k_noise_gen<<<((cells + 3) / 4 + 255) / 256, 256, 0, st>>>(ctx->noise_buf, cells, p.noise_seed, fr.frame_index); ++launches;
+                f.noise = ctx->noise_buf;
+            }
+        }
+        if (gg.rows > 0) {
+            if (fr.d_glitch_offs) {
+                if (fr.glitch_rows != gg.rows || fr.glitch_y0 != gg.y0 || fr.glitch_seg_len <= 0 ||
+                    fr.glitch_segments != (d.W + fr.glitch_seg_len - 1) / fr.glitch_seg_len)
+                    return fail(ctx, CRT_ERR_INVALID, "injected glitch table geometry does not match the parameters");
+                f.goffs = fr.d_glitch_offs; f.gy0 = fr.glitch_y0; f.gseg = fr.glitch_seg_len; f.gnseg = fr.glitch_segments;
+            } else {
+                if (p.glitch_mode != 1) return fail(ctx, CRT_ERR_INVALID, "glitch on with glitch_mode 0 needs crt_frame.d_glitch_offs");
+                size_t need = (size_t)gg.rows * gg.nseg;
+                if (need > ctx->glitch_cap) {
+                    if (ctx->glitch_buf) cudaFree(ctx->glitch_buf);
+                    ctx->glitch_buf = nullptr; ctx->glitch_cap = 0;
+                    CU(cudaMalloc((void**)&ctx->glitch_buf, need * sizeof(int32_t)));
+                    ctx->glitch_cap = need;
+                }
+                int rc = gen_glitch(ctx, fr, gg, ctx->glitch_buf, st); if (rc) return rc;
+                ++launches;
+                f.goffs = ctx->glitch_buf; f.gy0 = gg.y0; f.gseg = gg.seg_len; f.gnseg = gg.nseg;
+            }
+        }
+        const int has_prev = persist && (state_valid || i > 0);
+        const uint8_t* in_i = d_in + (size_t)i * frame_px * 3;
+        uint8_t* out_i = d_out ? d_out + (size_t)i * frame_px * 3 : nullptr;
+        float* img_i = d_img ? d_img + (size_t)i * frame_px * 3 : nullptr;
+        float* state_i = (persist || (d_state && !d_img)) ? d_state : nullptr;
+        int rc;
+        if (want_fused) { rc = run_fused(ctx->plan, d, f, in_i, out_i, state_i, has_prev, st, &launches); fused_used = 1; }
+        else rc = run_staged(ctx, f, in_i, out_i, state_i, has_prev, img_i, st, &launches);
+        if (rc == CRT_ERR_CUDA) return fail(ctx, rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        if (rc) return rc;
+    }
+    if (info) { info->kernels_launched = launches; info->fused = fused_used; }
+    return CRT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int crt_abi_version(void) { return CRT_B200_ABI_VERSION; }
+
+const char* crt_last_error(const crt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int crt_create(int device, int width, int height, crt_ctx** out_ctx) {
+    crt_ctx* ctx = nullptr;   // for the CU macro
+    if (!out_ctx || width < 2 || height < 2 || width > 32768 || height > 32768) return fail(nullptr, CRT_ERR_INVALID, "bad size");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail(nullptr, CRT_ERR_NO_DEVICE, "no CUDA device: the CRT chain has no CPU path");
+    if (device < 0 || device >= n) return fail(nullptr, CRT_ERR_INVALID, "device index out of range");
+    CU(cudaSetDevice(device));
+    crt_ctx* c = new (std::nothrow) crt_ctx();
+    if (!c) return fail(nullptr, CRT_ERR_INVALID, "out of host memory");
+    c->device = device; c->W = width; c->H = height;
+    ctx = c;
+    const int hw = width / 2 > 1 ? width / 2 : 1, hh = height / 2 > 1 ? height / 2 : 1;
+    int rc = upload(c, &c->dn_x, linear_coords(hw, width));
+    if (!rc) rc = upload(c, &c->dn_y, linear_coords(hh, height));
+    if (!rc) rc = upload(c, &c->up_x, linear_coords(width, hw));
+    if (!rc) rc = upload(c, &c->up_y, linear_coords(height, hh));
+    if (rc) { g_create_error = c->err; crt_destroy(c); return rc; }
+    *out_ctx = c;
+    return CRT_OK;
+}
+
+int crt_destroy(crt_ctx* ctx) {
+    if (!ctx) return CRT_OK;
+    cudaSetDevice(ctx->device);
+    for (auto& t : ctx->tab) if (t) cudaFree(t);
+    for (Lerp1* t : {ctx->dn_x, ctx->dn_y, ctx->up_x, ctx->up_y, ctx->nz_x, ctx->nz_y}) if (t) cudaFree(t);
+    if (ctx->scratch.ds) cudaFree(ctx->scratch.ds);
+    if (ctx->scratch.bl) cudaFree(ctx->scratch.bl);
+    if (ctx->scratch.q) cudaFree(ctx->scratch.q);
+    if (ctx->noise_buf) cudaFree(ctx->noise_buf);
+    if (ctx->glitch_buf) cudaFree(ctx->glitch_buf);
+    if (ctx->state) cudaFree(ctx->state);
+    HostRing& r = ctx->ring;
+    for (int s = 0; s < HostRing::SLOTS; ++s) {
+        if (r.d_in[s]) cudaFree(r.d_in[s]);
+        if (r.d_out[s]) cudaFree(r.d_out[s]);
+        if (r.in_ready[s]) cudaEventDestroy(r.in_ready[s]);
+        if (r.done[s]) cudaEventDestroy(r.done[s]);
+        if (r.out_ready[s]) cudaEventDestroy(r.out_ready[s]);
+    }
+    if (r.s_in) cudaStreamDestroy(r.s_in);
+    if (r.s_comp) cudaStreamDestroy(r.s_comp);
+    if (r.s_out) cudaStreamDestroy(r.s_out);
+    delete ctx;
+    return CRT_OK;
+}
+
+int crt_set_params(crt_ctx* ctx, const crt_params* params) {
+    if (!ctx || !params) return CRT_ERR_INVALID;
+    if (params->pixel_size < 1 || params->grain_size < 0 || params->text_mode < 0 || params->text_mode > 2 || params->vignette_on < 0 ||
+        params->vignette_on > 2 || !(params->persistence >= 0.0 && params->persistence < 1.0))
+        return fail(ctx, CRT_ERR_INVALID, "parameter out of range");
+    ctx->p = *params;
+    ctx->have_params = true;
+    ctx->dev_ok = false;
+    return CRT_OK;
+}
+
+int crt_set_table(crt_ctx* ctx, int table, const void* h_data, size_t bytes) {
+    if (!ctx || table < 0 || table >= CRT_TABLE_COUNT) return CRT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->tab[table] && ctx->tab_bytes[table] != bytes) { CU(cudaDeviceSynchronize()); cudaFree(ctx->tab[table]); ctx->tab[table] = nullptr; ctx->tab_bytes[table] = 0; }
+    if (!h_data || bytes == 0) {
+        if (ctx->tab[table]) { CU(cudaDeviceSynchronize()); cudaFree(ctx->tab[table]); }
+        ctx->tab[table] = nullptr; ctx->tab_bytes[table] = 0; ctx->dev_ok = false;
+        return CRT_OK;
+    }
+    if (!ctx->tab[table]) CU(cudaMalloc(&ctx->tab[table], bytes));
+    CU(cudaMemcpy(ctx->tab[table], h_data, bytes, cudaMemcpyHostToDevice));
+    ctx->tab_bytes[table] = bytes;
+    ctx->dev_ok = false;
+    return CRT_OK;
+}
+
+int crt_set_policy(crt_ctx* ctx, int policy) {
+    if (!ctx || policy < 0 || policy > 2) return CRT_ERR_INVALID;
+    ctx->policy = policy;
+    return CRT_OK;
+}
+
+int crt_process(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_state, int state_valid, const crt_frame* frames, int n_frames,
+                void* stream, crt_launch_info* info) {
+    return process_impl(ctx, d_in, d_out, d_state, state_valid, nullptr, frames, n_frames, (cudaStream_t)stream, info);
+}
+
+int crt_process_static(crt_ctx* ctx, const uint8_t* d_in, float* d_img, const crt_frame* frames, int n_frames, void* stream, crt_launch_info* info) {
+    if (!d_img) return fail(ctx, CRT_ERR_INVALID, "null image buffer");
+    return process_impl(ctx, d_in, nullptr, nullptr, 0, d_img, frames, n_frames, (cudaStream_t)stream, info);
+}
+
+int crt_reset_state(crt_ctx* ctx) {
+    if (!ctx) return CRT_ERR_INVALID;
+    ctx->state_valid = 0;
+    return CRT_OK;
+}
+
+int crt_process_host(crt_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, const crt_frame* frames, int n_frames, crt_launch_info* info) {
+    if (!ctx || !h_in || !h_out || !frames || n_frames < 0) return CRT_ERR_INVALID;
+    if (!ctx->have_params) return fail(ctx, CRT_ERR_INVALID, "crt_set_params has not been called");
+    CU(cudaSetDevice(ctx->device));
+    const size_t fbytes = (size_t)ctx->W * ctx->H * 3;
+    HostRing& r = ctx->ring;
+    if (!r.ready) {
+        size_t target = 48u << 20;                                     // ~48 MB per chunk
+        r.chunk_frames = (int)(target / fbytes); if (r.chunk_frames < 1) r.chunk_frames = 1; if (r.chunk_frames > 256) r.chunk_frames = 256;
+        CU(cudaStreamCreateWithFlags(&r.s_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&r.s_comp, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&r.s_out, cudaStreamNonBlocking));
+        for (int s = 0; s < HostRing::SLOTS; ++s) {
+            CU(cudaMalloc((void**)&r.d_in[s], fbytes * r.chunk_frames));
+            CU(cudaMalloc((void**)&r.d_out[s], fbytes * r.chunk_frames));
+            CU(cudaEventCreateWithFlags(&r.in_ready[s], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&r.done[s], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&r.out_ready[s], cudaEventDisableTiming));
+        }
+        r.ready = true;
+    }
+    if (!ctx->state) CU(cudaMalloc((void**)&ctx->state, fbytes * sizeof(float)));
+    int total_launches = 0, fused = 0, chunk_idx = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += r.chunk_frames, ++chunk_idx) {
+        const int s = chunk_idx % HostRing::SLOTS;
+        const int nf = n_frames - f0 < r.chunk_frames ? n_frames - f0 : r.chunk_frames;
+        // slot reuse: the copy-out that last used this slot must have drained, and its compute too
+        if (chunk_idx >= HostRing::SLOTS) { CU(cudaStreamWaitEvent(r.s_in, r.done[s], 0)); CU(cudaStreamWaitEvent(r.s_comp, r.out_ready[s], 0)); }
+        CU(cudaMemcpyAsync(r.d_in[s], h_in + (size_t)f0 * fbytes, fbytes * nf, cudaMemcpyHostToDevice, r.s_in));
+        CU(cudaEventRecord(r.in_ready[s], r.s_in));
+        CU(cudaStreamWaitEvent(r.s_comp, r.in_ready[s], 0));
+        crt_launch_info li{};
+        int rc = process_impl(ctx, r.d_in[s], r.d_out[s], ctx->state, ctx->state_valid, nullptr, frames + f0, nf, r.s_comp, &li);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        total_launches += li.kernels_launched; fused = li.fused;
+        if (ctx->p.persistence > 0.0) ctx->state_valid = 1;
+        CU(cudaEventRecord(r.done[s], r.s_comp));
+        CU(cudaStreamWaitEvent(r.s_out, r.done[s], 0));
+        CU(cudaMemcpyAsync(h_out + (size_t)f0 * fbytes, r.d_out[s], fbytes * nf, cudaMemcpyDeviceToHost, r.s_out));
+        CU(cudaEventRecord(r.out_ready[s], r.s_out));
+    }
+    CU(cudaStreamSynchronize(r.s_out));
+    CU(cudaStreamSynchronize(r.s_comp));
+    if (info) { info->kernels_launched = total_launches; info->fused = fused; }
+    return CRT_OK;
+}
+
+int crt_generate_noise(crt_ctx* ctx, uint64_t frame_index, float* d_plane, void* stream) {
+    if (!ctx || !d_plane) return CRT_ERR_INVALID;
+    if (!ctx->have_params) return fail(ctx, CRT_ERR_INVALID, "crt_set_params has not been called");
+    if (!ctx->dev_ok) { int rc = build_dev(ctx); if (rc) return rc; }
+    CU(cudaSetDevice(ctx->device));
+    const int cells = ctx->dev.gh * ctx->dev.gw;
+    k_noise_gen<<<((cells + 3) / 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_plane, cells, ctx->p.noise_seed, frame_index);
+    CU(cudaGetLastError());
+    return CRT_OK;
+}
+
+int crt_generate_glitch(crt_ctx* ctx, const crt_frame* frame, int32_t* d_offs, void* stream) {
+    if (!ctx || !frame || !d_offs) return CRT_ERR_INVALID;
+    if (!ctx->have_params) return fail(ctx, CRT_ERR_INVALID, "crt_set_params has not been called");
+    CU(cudaSetDevice(ctx->device));
+    return gen_glitch(ctx, *frame, glitch_geom(ctx->p, ctx->W, ctx->H), d_offs, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,399 @@
+// crt_math.cuh — per-pixel arithmetic of the CRT effect chain, written once and
+// used by every kernel (staged and fused).
+//
+// Parity contract (oracle/cv_restated.py): everything that feeds
+// the triad LUT's floor indexing (crt_filter.py:250, :261) is evaluated in
+// float32 with numpy's operation order and NO fused multiply-add, except where
+// OpenCV itself uses an fma (resize lerps, gaussian taps).  All such operations
+// go through the crt_* wrappers below (__fmul_rn / __fadd_rn never contract);
+// the translation unit is additionally compiled with -fmad=false.
+//
+// The functions are __host__ __device__ so that tests/host_emu can compile the
+// very same arithmetic with g++ and compare it with the oracle on a machine
+// without a GPU.  That build is test infrastructure; the product never runs it.
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define CRT_HD __host__ __device__ __forceinline__
+#else
+#define CRT_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define CRT_DEVICE_CODE 1
+#else
+#define CRT_DEVICE_CODE 0
+#endif
+
+#if !defined(__CUDACC__)
+// plain g++ build of tests/host_emu: CUDA's sinpif/cospif do not exist in libm
+static inline float sinpif(float x) { return (float)sin(3.14159265358979323846 * (double)x); }
+static inline float cospif(float x) { return (float)cos(3.14159265358979323846 * (double)x); }
+#endif
+
+namespace crt {
+
+// ---- exact float32 primitives ------------------------------------------------
+CRT_HD float fmul(float a, float b) {
+#if CRT_DEVICE_CODE
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b; return r;
+#endif
+}
+CRT_HD float fadd(float a, float b) {
+#if CRT_DEVICE_CODE
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b; return r;
+#endif
+}
+CRT_HD float fsub(float a, float b) {
+#if CRT_DEVICE_CODE
+    return __fsub_rn(a, b);
+#else
+    volatile float r = a - b; return r;
+#endif
+}
+CRT_HD float fdiv(float a, float b) {
+#if CRT_DEVICE_CODE
+    return __fdiv_rn(a, b);
+#else
+    volatile float r = a / b; return r;
+#endif
+}
+CRT_HD float ffma(float a, float b, float c) {
+#if CRT_DEVICE_CODE
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+// np.clip(x, 0, 1)
+CRT_HD float sat(float x) {
+#if CRT_DEVICE_CODE
+    return __saturatef(x);
+#else
+    return x < 0.f ? 0.f : (x > 1.f ? 1.f : x);
+#endif
+}
+CRT_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+CRT_HD int imin(int a, int b) { return a < b ? a : b; }
+CRT_HD int imax(int a, int b) { return a > b ? a : b; }
+// a mod n for a in [-n, 2n)
+CRT_HD int wrap(int a, int n) { a = a < 0 ? a + n : a; return a >= n ? a - n : a; }
+// python-style modulo for arbitrary a
+CRT_HD int pymod(int a, int n) { int r = a % n; return r < 0 ? r + n : r; }
+
+struct F3 { float x, y, z; };
+CRT_HD F3 mk3(float a, float b, float c) { F3 r; r.x = a; r.y = b; r.z = c; return r; }
+
+// One axis of a cv2.resize(INTER_LINEAR) coordinate table (oracle/cv_restated.py linear_coords)
+struct Lerp1 { int32_t s0, s1; float w; };
+
+// ---- device-side parameter block ------------------------------------------------
+struct Dev {
+    int W, H;
+    // stage 1-2: aberration + pixelate (crt_filter.py:571-584)
+    int aberr;
+    const int32_t* pix_x;        // [W] or null
+    const int32_t* pix_y;        // [H] or null
+    // stage 3: colour (:279-305)
+    int col_sat, col_temp, col_bc, col_gamma;
+    float sat_f, gain0, gain2, contrast, brightness, inv_gamma;
+    // text layer (:588-598 / :653-663)
+    int text_mode;               // 0 none, 1 before, 2 after
+    const uint8_t* text;         // [H][W][4]
+    // stage 5: bloom (:599-612)
+    int bloom_mode;              // 0 off, 1 fast, 2 gaussian
+    float bloom_strength;
+    int thr_on; float thr, thr_den;
+    int ksize; const float* taps;
+    int hw, hh;                  // half-size plane of the fast path
+    int even_dims;               // W and H even: closed-form 2x coordinates
+    const Lerp1* dn_x; const Lerp1* dn_y;   // [hw], [hh]   (general sizes)
+    const Lerp1* up_x; const Lerp1* up_y;   // [W], [H]
+    // stage 6: triad (:238-263)
+    int triad_mode;              // 0 off, 1 plain multiply, 2 LUT, 3 LUT + preserve luma
+    const float* triad_cols;     // [W][3]
+    const float* lut_fwd; const float* lut_inv;   // [1025]
+    // stage 7: scanlines (:213-217, :308-328)
+    int scan_mode;               // 0 off, 1 per-row float32, 2 slanted/shaped plane
+    float scan_strength, scan_c32;
+    double scan_tan, scan_inv_period;
+    float scan_inv_sharp;
+    // stage 8: vignette (:266-276)
+    int vig_mode;                // 0 off, 1 analytic, 2 plane
+    float vig_strength, vig_cx, vig_cy, vig_irx, vig_iry;
+    const float* vig_plane;
+    // stage 10: noise (:635-648)
+    int noise_on; float noise_scale; int gh, gw;
+    const Lerp1* nz_x; const Lerp1* nz_y;   // [W], [H] when grain > 1, else null
+    // stage 11: warp (:331-348)
+    int warp_on; float warp_cx, warp_cy, warp_dx, warp_dy, warp_k;
+    // stage 14: persistence (:687-694 / :1086-1096)
+    float persist, persist_q;    // p and float32(1 - p)
+};
+
+struct FrameDev {
+    float phase32;               // float32(scanline_phase_px)
+    double phase;                // scanline_phase_px
+    int flicker_on; float flicker;
+    const float* noise;          // [gh][gw] N(0,1) plane or null
+    const int32_t* goffs;        // [rows][segments] or null
+    int gy0, gseg, gnseg;
+};
+
+// ---- stage 0-4: graded input ----------------------------------------------------
+// u8 -> float32 by true division (crt_filter.py:569)
+CRT_HD float unit(uint8_t v) { return fdiv((float)v, 255.0f); }
+
+// Raw source bytes of pixel (y, x) after aberration (:571-577: channel 0 rolled by
+// +a, channel 2 by -a, circular) and pixelate (:578-584).
+CRT_HD void source_bytes(const Dev& d, const uint8_t* __restrict__ in, int y, int x, uint8_t& b0, uint8_t& b1, uint8_t& b2) {
+    int sy = d.pix_y ? d.pix_y[y] : y;
+    int sx = d.pix_x ? d.pix_x[x] : x;
+    const uint8_t* row = in + (size_t)sy * d.W * 3;
+    int x0 = sx, x2 = sx;
+    if (d.aberr != 0) { x0 = pymod(sx - d.aberr, d.W); x2 = pymod(sx + d.aberr, d.W); }
+    b0 = row[x0 * 3 + 0];
+    b1 = row[sx * 3 + 1];
+    b2 = row[x2 * 3 + 2];
+}
+
+// apply_color_adjustments (:279-305), float32, numpy operation order.
+CRT_HD F3 colour(const Dev& d, F3 v) {
+    if (d.col_sat) {
+        float l = fadd(fadd(fmul(0.2126f, v.x), fmul(0.7152f, v.y)), fmul(0.0722f, v.z));
+        v.x = sat(fadd(l, fmul(fsub(v.x, l), d.sat_f)));
+        v.y = sat(fadd(l, fmul(fsub(v.y, l), d.sat_f)));
+        v.z = sat(fadd(l, fmul(fsub(v.z, l), d.sat_f)));
+    }
+    if (d.col_temp) {
+        v.x = sat(fmul(v.x, d.gain0));
+        v.z = sat(fmul(v.z, d.gain2));
+    }
+    if (d.col_bc) {
+        v.x = sat(fadd(fadd(fmul(fsub(v.x, 0.5f), d.contrast), 0.5f), d.brightness));
+        v.y = sat(fadd(fadd(fmul(fsub(v.y, 0.5f), d.contrast), 0.5f), d.brightness));
+        v.z = sat(fadd(fadd(fmul(fsub(v.z, 0.5f), d.contrast), 0.5f), d.brightness));
+    }
+    if (d.col_gamma) {
+        // numpy's float32 power (SVML) is within 1 ulp but not correctly rounded, so this
+        // stage cannot be matched bit for bit by any other implementation.
+        v.x = sat(powf(v.x, d.inv_gamma));
+        v.y = sat(powf(v.y, d.inv_gamma));
+        v.z = sat(powf(v.z, d.inv_gamma));
+    }
+    return v;
+}
+
+// Alpha blend of the rasterised text layer (:595-597)
+CRT_HD F3 text_blend(const Dev& d, F3 v, int y, int x) {
+    const uint8_t* t = d.text + ((size_t)y * d.W + x) * 4;
+    float a = unit(t[3]);
+    float ia = fsub(1.0f, a);
+    v.x = sat(fadd(fmul(v.x, ia), fmul(unit(t[0]), a)));
+    v.y = sat(fadd(fmul(v.y, ia), fmul(unit(t[1]), a)));
+    v.z = sat(fadd(fmul(v.z, ia), fmul(unit(t[2]), a)));
+    return v;
+}
+
+// Stages 0-4 at pixel (y, x): the image bloom sees.
+CRT_HD F3 graded_input(const Dev& d, const uint8_t* __restrict__ in, int y, int x) {
+    uint8_t b0, b1, b2;
+    source_bytes(d, in, y, x, b0, b1, b2);
+    F3 v = colour(d, mk3(unit(b0), unit(b1), unit(b2)));
+    if (d.text_mode == 1) v = text_blend(d, v, y, x);
+    return v;
+}
+
+// Bloom source: clip((img - thr) / max(1e-6, 1 - thr)) (:602-604)
+CRT_HD float bloom_src1(const Dev& d, float v) { return d.thr_on ? sat(fdiv(fsub(v, d.thr), d.thr_den)) : v; }
+CRT_HD F3 bloom_src(const Dev& d, F3 v) { return mk3(bloom_src1(d, v.x), bloom_src1(d, v.y), bloom_src1(d, v.z)); }
+
+// cv2.resize lerp: fma(q - p, w, p)
+CRT_HD float lerp_cv(float p, float q, float w) { return ffma(fsub(q, p), w, p); }
+
+// Coordinates of the 2x fast-bloom resizes (closed form for even sizes, else tables).
+CRT_HD Lerp1 down_coord(const Dev& d, const Lerp1* tab, int i) {
+    if (d.even_dims) { Lerp1 c; c.s0 = 2 * i; c.s1 = 2 * i + 1; c.w = 0.5f; return c; }
+    return tab[i];
+}
+CRT_HD Lerp1 up_coord(const Dev& d, const Lerp1* tab, int i, int n_half) {
+    if (d.even_dims) {
+        Lerp1 c;
+        int j = i >> 1;
+        if (i & 1) { c.s0 = j; c.w = 0.25f; } else { c.s0 = j - 1; c.w = 0.75f; }
+        if (c.s0 < 0) { c.s0 = 0; c.w = 0.f; }
+        if (c.s0 >= n_half - 1) { c.s0 = n_half - 1; c.w = 0.f; }
+        c.s1 = imin(c.s0 + 1, n_half - 1);
+        return c;
+    }
+    return tab[i];
+}
+
+// addition of bloom: clip(img + strength * blur) (:611)
+CRT_HD F3 add_bloom(const Dev& d, F3 v, F3 bl) {
+    v.x = sat(fadd(v.x, fmul(d.bloom_strength, bl.x)));
+    v.y = sat(fadd(v.y, fmul(d.bloom_strength, bl.y)));
+    v.z = sat(fadd(v.z, fmul(d.bloom_strength, bl.z)));
+    return v;
+}
+
+// ---- stage 6: triad -------------------------------------------------------------
+CRT_HD int lut_index(float v) {           // (np.clip(v,0,1) * 1024).astype(int32), clipped
+    int i = (int)fmul(sat(v), 1024.0f);
+    return i > 1024 ? 1024 : i;
+}
+CRT_HD F3 triad(const Dev& d, F3 v, int x, const float* __restrict__ fwd, const float* __restrict__ inv) {
+    const float* m = d.triad_cols + (size_t)x * 3;
+    float m0 = m[0], m1 = m[1], m2 = m[2];
+    if (d.triad_mode == 1) return mk3(sat(fmul(v.x, m0)), sat(fmul(v.y, m1)), sat(fmul(v.z, m2)));
+    float l0 = fwd[lut_index(v.x)], l1 = fwd[lut_index(v.y)], l2 = fwd[lut_index(v.z)];
+    float o0 = fmul(l0, m0), o1 = fmul(l1, m1), o2 = fmul(l2, m2);
+    if (d.triad_mode == 3) {
+        float before = fadd(fadd(fmul(0.2126f, l0), fmul(0.7152f, l1)), fmul(0.0722f, l2));
+        float after = fadd(fadd(fmul(0.2126f, o0), fmul(0.7152f, o1)), fmul(0.0722f, o2));
+        float ratio = clampf(fdiv(before, fmaxf(after, 1e-6f)), 0.5f, 2.0f);
+        o0 = fmul(o0, ratio); o1 = fmul(o1, ratio); o2 = fmul(o2, ratio);
+    }
+    return mk3(sat(inv[lut_index(o0)]), sat(inv[lut_index(o1)]), sat(inv[lut_index(o2)]));
+}
+
+// ---- stage 7: scanlines ---------------------------------------------------------
+// Per-row mask (:213-217): float32 throughout, as numpy evaluates it.
+CRT_HD float scan_row(const Dev& d, const FrameDev& f, int y) {
+    float arg = fmul(d.scan_c32, fadd((float)y, f.phase32));
+    float s = fmul(0.5f, fadd(1.0f, sinf(arg)));
+    return fsub(1.0f, fmul(d.scan_strength, s));
+}
+// Slanted / shaped mask (:308-328): the reference works in float64 and casts to
+// float32; the phase is reduced in double (exact), sin/pow run in float32.
+CRT_HD float scan_plane(const Dev& d, const FrameDev& f, int y, int x) {
+    double u = ((double)y + d.scan_tan * (double)x) + f.phase;
+    double t = u * d.scan_inv_period;
+    t -= floor(t);                                  // turns in [0, 1)
+    float s = 0.5f * (1.0f + sinpif(2.0f * (float)t));
+    s = fmaxf(s, 0.0f);
+    float shaped = (d.scan_inv_sharp == 1.0f) ? s : powf(s, d.scan_inv_sharp);
+    return 1.0f - d.scan_strength * shaped;
+}
+
+// ---- stage 8: vignette ----------------------------------------------------------
+CRT_HD float vignette(const Dev& d, int y, int x) {
+    if (d.vig_mode == 2) return d.vig_plane[(size_t)y * d.W + x];
+    float nx = ((float)x - d.vig_cx) * d.vig_irx;
+    float ny = ((float)y - d.vig_cy) * d.vig_iry;
+    return 1.0f - d.vig_strength * sat(nx * nx + ny * ny);
+}
+
+// ---- stage 10: noise ------------------------------------------------------------
+CRT_HD float noise_at(const Dev& d, const FrameDev& f, int y, int x) {
+    float n;
+    if (d.nz_x) {      // grain > 1: cv2.resize(small, (W, H), INTER_LINEAR)
+        Lerp1 cx = d.nz_x[x], cy = d.nz_y[y];
+        const float* r0 = f.noise + (size_t)cy.s0 * d.gw;
+        const float* r1 = f.noise + (size_t)cy.s1 * d.gw;
+        float a = lerp_cv(r0[cx.s0], r0[cx.s1], cx.w);
+        float b = lerp_cv(r1[cx.s0], r1[cx.s1], cx.w);
+        n = lerp_cv(a, b, cy.w);
+    } else {
+        n = f.noise[(size_t)y * d.W + x];
+    }
+    return fmul(n, d.noise_scale);
+}
+
+// Stages 6-10 at pixel (y, x) given the image after bloom.
+CRT_HD F3 after_bloom(const Dev& d, const FrameDev& f, F3 v, int y, int x,
+                      const float* __restrict__ fwd, const float* __restrict__ inv, float row_mask) {
+    if (d.triad_mode) v = triad(d, v, x, fwd, inv);
+    if (d.scan_mode) {
+        float m = d.scan_mode == 1 ? row_mask : scan_plane(d, f, y, x);
+        v.x = sat(v.x * m); v.y = sat(v.y * m); v.z = sat(v.z * m);
+    }
+    if (d.vig_mode) {
+        float m = vignette(d, y, x);
+        v.x = sat(v.x * m); v.y = sat(v.y * m); v.z = sat(v.z * m);
+    }
+    if (f.flicker_on) { v.x = sat(v.x * f.flicker); v.y = sat(v.y * f.flicker); v.z = sat(v.z * f.flicker); }
+    if (d.noise_on) {
+        float n = noise_at(d, f, y, x);
+        v.x = sat(v.x + n); v.y = sat(v.y + n); v.z = sat(v.z + n);
+    }
+    return v;
+}
+
+// ---- stage 11: warp -------------------------------------------------------------
+struct Taps { int ix, iy; float w00, w01, w10, w11; };
+// Source coordinates of apply_barrel_warp (:338-346) in numpy's float32 order,
+// then cv2.remap's 1/32-pixel quantisation (oracle/cv_restated.py remap_bilinear_const0).
+CRT_HD Taps warp_taps(const Dev& d, int y, int x) {
+    float xn = fdiv(fsub((float)x, d.warp_cx), d.warp_dx);
+    float yn = fdiv(fsub((float)y, d.warp_cy), d.warp_dy);
+    float r2 = fadd(fmul(xn, xn), fmul(yn, yn));
+    float fac = fadd(1.0f, fmul(d.warp_k, r2));
+    float mx = fadd(fmul(fmul(xn, fac), d.warp_cx), d.warp_cx);
+    float my = fadd(fmul(fmul(yn, fac), d.warp_cy), d.warp_cy);
+    // cv2 saturates the fixed-point coordinate to the int range first
+    float qx = clampf(fmul(mx, 32.0f), -1.0e9f, 1.0e9f), qy = clampf(fmul(my, 32.0f), -1.0e9f, 1.0e9f);
+    int sx = (int)rintf(qx), sy = (int)rintf(qy);
+    Taps t;
+    t.ix = sx >> 5; t.iy = sy >> 5;
+    float fx = fmul((float)(sx & 31), 0.03125f), fy = fmul((float)(sy & 31), 0.03125f);
+    float gx = fsub(1.0f, fx), gy = fsub(1.0f, fy);
+    t.w00 = fmul(gy, gx); t.w01 = fmul(gy, fx); t.w10 = fmul(fy, gx); t.w11 = fmul(fy, fx);
+    return t;
+}
+CRT_HD float gather4(float a, float b, float c, float e, const Taps& t) {
+    return fadd(fadd(fadd(fmul(a, t.w00), fmul(b, t.w01)), fmul(c, t.w10)), fmul(e, t.w11));
+}
+
+// ---- stage 13: glitch -----------------------------------------------------------
+// Source column of output (y, x) (:680-684 / :852-857); identity above the band.
+CRT_HD int glitch_src_x(const Dev& d, const FrameDev& f, int y, int x) {
+    if (!f.goffs || y < f.gy0) return x;
+    int off = f.goffs[(size_t)(y - f.gy0) * f.gnseg + x / f.gseg];
+    return pymod(x + off, d.W);
+}
+
+// ---- stage 14-15: persistence + quantise ------------------------------------------
+// Export: clip(p*prev + (1-p)*img) (:1092); GUI: addWeighted without clip (:693) —
+// identical here because both operands are already in [0, 1].
+CRT_HD float blend(float prev, float v, float p, float q) { return sat(p * prev + q * v); }
+// cv2.convertScaleAbs(alpha=255): round-half-even of |255 x|, saturated (:696, :1098)
+CRT_HD uint8_t quantise(float v) {
+    float s = fabsf(fmul(v, 255.0f));
+    int r = (int)rintf(s);
+    return (uint8_t)(r > 255 ? 255 : r);
+}
+
+// ---- counter-based RNG (Philox4x32-10) ----------------------------------------------
+struct U4 { uint32_t x, y, z, w; };
+CRT_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if CRT_DEVICE_CODE
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+CRT_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        U4 n; n.x = hi1 ^ c.y ^ k0; n.y = lo1; n.z = hi0 ^ c.w ^ k1; n.w = lo0;
+        c = n; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+// Two independent N(0,1) draws from two 32-bit words (Box-Muller).
+CRT_HD void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+    float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1)
+    float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float r = sqrtf(-2.0f * logf(u1));
+    n0 = r * cospif(2.0f * u2); n1 = r * sinpif(2.0f * u2);
+}
+}  // namespace crt

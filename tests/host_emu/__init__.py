@@ -1,0 +1,95 @@
+"""tests/host_emu — TEST INFRASTRUCTURE ONLY (never imported by pythoncrt_b200).
+
+Builds tests/host_emu/emu.cpp with g++ (the kernels' own per-pixel arithmetic
+headers compiled for the host) and drives it with the SAME parameter/table
+translation the product uses (pythoncrt_b200.config.build_config), so the
+arithmetic and the host-side tables can be checked against the oracle on a
+machine without a GPU.  What it cannot check — thread mapping, shared-memory
+tiling, the fused kernel — is covered by the `gpu` tests on the B200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from pythoncrt_b200 import cabi, tables
+from pythoncrt_b200.config import build_config
+from pythoncrt_b200.params import CrtParams
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_emu.so")
+SRC = os.path.join(HERE, "emu.cpp")
+CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "pythoncrt_b200", "csrc")
+_lib = None
+
+
+def _stale() -> bool:
+    if not os.path.isfile(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("crt_math.cuh", "crt_stages.cuh", "crt_derive.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if _stale():
+            subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", SO, SRC], check=True)
+        _lib = C.CDLL(SO)
+        _lib.emu_process.restype = C.c_int
+    return _lib
+
+
+def oracle_to_product_params(p) -> CrtParams:
+    """oracle.ChainParams -> pythoncrt_b200.CrtParams (same field names)."""
+    names = {f for f in CrtParams.__dataclass_fields__}
+    return CrtParams(**{k: v for k, v in vars(p).items() if k in names})
+
+
+def run_case(case, variant: str, static: bool = False):
+    """Run an oracle Case through the host build of the kernel arithmetic."""
+    from oracle import harness
+    from oracle.cases import case_frames, case_text_layer
+    L = lib()
+    p = oracle_to_product_params(case.params)
+    H, W = case.h, case.w
+    text = case_text_layer(case)
+    c, tabs = build_config(p, W, H, variant=variant, text_rgba=text, text_after=(case.text != "before"))
+    assert L.emu_sizeof_params() == C.sizeof(cabi.CrtParamsC) and L.emu_sizeof_frame() == C.sizeof(cabi.CrtFrameC)
+    ptrs = (C.c_void_p * 8)()
+    sizes = (C.c_size_t * 8)()
+    for k, a in tabs.items():
+        ptrs[k] = a.ctypes.data
+        sizes[k] = a.nbytes
+    frames = np.ascontiguousarray(np.stack(case_frames(case)))
+    n = frames.shape[0]
+    planes = harness.noise_planes(case)
+    recs = (cabi.CrtFrameC * n)()
+    keep = []
+    for j in range(n):
+        phase, tsec = harness.frame_scalars(case, j)
+        recs[j].phase_px, recs[j].time_sec, recs[j].frame_index = phase, tsec, case.first_index + j
+        if planes is not None:
+            pl = np.ascontiguousarray(planes[j], np.float32)
+            keep.append(pl)
+            recs[j].d_noise = pl.ctypes.data
+        t = tables.glitch_offsets(variant, H, W, int(p.glitch_amp_px), float(p.glitch_height_frac), phase)
+        if t is not None:
+            keep.append(t)
+            recs[j].d_glitch_offs = t.ctypes.data
+            recs[j].glitch_y0, recs[j].glitch_rows, recs[j].glitch_seg_len, recs[j].glitch_segments = \
+                tables.glitch_geometry(variant, H, W, p.glitch_height_frac)
+    out = np.empty_like(frames)
+    state = np.zeros((H, W, 3), np.float32)
+    img = np.empty(frames.shape, np.float32) if static else None
+    err = C.create_string_buffer(512)
+    rc = L.emu_process(C.byref(c), W, H, ptrs, sizes, frames.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                       state.ctypes.data_as(C.c_void_p), 0, img.ctypes.data_as(C.c_void_p) if static else None,
+                       recs, n, err, 512)
+    if rc != 0:
+        raise RuntimeError(f"emu_process failed ({rc}): {err.value.decode()}")
+    return (img if static else list(out)), state

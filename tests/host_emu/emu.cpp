@@ -1,0 +1,84 @@
+// tests/host_emu/emu.cpp — TEST INFRASTRUCTURE, never shipped, never imported by
+// the product.  Compiles the kernels' own per-pixel arithmetic
+// (pythoncrt_b200/csrc/crt_math.cuh, crt_stages.cuh, crt_derive.h) with g++ and
+// runs the staged pipeline as plain loops, so the arithmetic can be checked
+// against the oracle on a machine without a GPU (-ffp-contract=off; the exact
+// float32 wrappers keep numpy's operation order).  The CUDA thread mapping,
+// shared-memory tiling and the fused kernel are NOT covered here: those are
+// checked on the B200 by tests marked `gpu`.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../pythoncrt_b200/csrc/crt_derive.h"
+#include "../../pythoncrt_b200/csrc/crt_stages.cuh"
+
+using namespace crt;
+
+extern "C" int emu_sizeof_params() { return (int)sizeof(crt_params); }
+extern "C" int emu_sizeof_frame() { return (int)sizeof(crt_frame); }
+
+extern "C" int emu_process(const crt_params* p, int W, int H, const void* const* tabs, const size_t* tab_bytes,
+                           const uint8_t* in, uint8_t* out, float* state, int state_valid, float* img_out,
+                           const crt_frame* frames, int n_frames, char* err, int errlen) {
+    TablePtrs t{};
+    for (int i = 0; i < CRT_TABLE_COUNT; ++i) { t.tab[i] = tabs[i]; t.bytes[i] = tab_bytes[i]; }
+    const int hw = W / 2 > 1 ? W / 2 : 1, hh = H / 2 > 1 ? H / 2 : 1;
+    std::vector<Lerp1> dn_x = linear_coords(hw, W), dn_y = linear_coords(hh, H), up_x = linear_coords(W, hw), up_y = linear_coords(H, hh);
+    std::vector<Lerp1> nz_x, nz_y;
+    if (p->noise_strength > 0.0 && p->grain_size > 1) {
+        nz_x = linear_coords(W, W / p->grain_size > 1 ? W / p->grain_size : 1);
+        nz_y = linear_coords(H, H / p->grain_size > 1 ? H / p->grain_size : 1);
+    }
+    t.dn_x = dn_x.data(); t.dn_y = dn_y.data(); t.up_x = up_x.data(); t.up_y = up_y.data();
+    t.nz_x = nz_x.empty() ? nullptr : nz_x.data(); t.nz_y = nz_y.empty() ? nullptr : nz_y.data();
+    Dev d{};
+    std::string e;
+    int rc = derive_dev(*p, W, H, t, &d, &e);
+    if (rc) { if (err) { strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; } return rc; }
+    const size_t px = (size_t)W * H;
+    std::vector<float> ds((size_t)hw * hh * 3), bl, q, S, R;
+    Scratch s{ds.data(), nullptr, nullptr};
+    if (d.bloom_mode == 2) { bl.resize(px * 3); S.resize(px * 3); R.resize(px * 3); s.bl = bl.data(); }
+    if (d.warp_on) { q.resize(px * 3); s.q = q.data(); }
+    const GlitchGeom gg = glitch_geom(*p, W, H);
+    const bool persist = p->persistence > 0.0 && !img_out;
+    for (int n = 0; n < n_frames; ++n) {
+        const uint8_t* fin = in + (size_t)n * px * 3;
+        FrameDev f = derive_frame(*p, frames[n]);
+        f.noise = frames[n].d_noise;
+        if (gg.rows > 0 && frames[n].d_glitch_offs) {
+            f.goffs = frames[n].d_glitch_offs; f.gy0 = frames[n].glitch_y0; f.gseg = frames[n].glitch_seg_len; f.gnseg = frames[n].glitch_segments;
+        }
+        if (d.bloom_mode == 1) {
+            for (int j = 0; j < d.hh; ++j) for (int i = 0; i < d.hw; ++i) bloom_down_cell(d, fin, ds.data(), j, i);
+        } else if (d.bloom_mode == 2) {
+            const int K = d.ksize, r = K / 2;
+            for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+                F3 v = bloom_src(d, graded_input(d, fin, y, x));
+                float* o = &S[((size_t)y * W + x) * 3]; o[0] = v.x; o[1] = v.y; o[2] = v.z;
+            }
+            std::vector<float> line((size_t)(W + 2 * r) * 3), col((size_t)(H + 2 * r));
+            for (int y = 0; y < H; ++y) {
+                for (int x = -r; x < W + r; ++x) { int xx = x < 0 ? 0 : (x >= W ? W - 1 : x); memcpy(&line[(size_t)(x + r) * 3], &S[((size_t)y * W + xx) * 3], 12); }
+                for (int x = 0; x < W; ++x) for (int c = 0; c < 3; ++c) R[((size_t)y * W + x) * 3 + c] = gauss_row(&line[(size_t)x * 3 + c], 3, d.taps, K);
+            }
+            for (int x = 0; x < W; ++x) for (int c = 0; c < 3; ++c) {
+                for (int y = -r; y < H + r; ++y) { int yy = y < 0 ? 0 : (y >= H ? H - 1 : y); col[y + r] = R[((size_t)yy * W + x) * 3 + c]; }
+                for (int y = 0; y < H; ++y) bl[((size_t)y * W + x) * 3 + c] = gauss_col(&col[y + r], 1, d.taps, K);
+            }
+        }
+        if (d.warp_on)
+            for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+                F3 v = pre_warp_pixel(d, f, fin, s, y, x, d.lut_fwd, d.lut_inv);
+                float* o = &q[((size_t)y * W + x) * 3]; o[0] = v.x; o[1] = v.y; o[2] = v.z;
+            }
+        const int has_prev = persist && (state_valid || n > 0);
+        for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+            F3 v = post_pixel(d, f, fin, s, y, x, d.lut_fwd, d.lut_inv);
+            if (img_out) { float* o = img_out + ((size_t)n * px + (size_t)y * W + x) * 3; o[0] = v.x; o[1] = v.y; o[2] = v.z; }
+            else finish_pixel(d, v, has_prev, state, out + (size_t)n * px * 3, y, x);
+        }
+    }
+    return 0;
+}
