@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py — frames/s and HBM roofline of the per-frame CRT effect chain.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one clip of synthetic frames resident
+in HBM (BASELINE.json configs; default = configs[1], "1080p full chain with
+gaussian bloom + colour grading, 600 frames, 1 B200").  Prints ONE JSON line
+(contract in the task brief): value = whole-job frames/s with inputs in HBM,
+e2e = the same through the host-buffer C-ABI call (pinned host memory in and
+out, copies inside the timed region), roofline = achieved algorithmic GB/s of
+the dominant kernel against the measured HBM peak, cpu_baseline = the oracle
+port of the reference's CPU path timed on this box's host cores.
+
+Multi-GPU (torchrun, one rank per GPU): the clip is sharded temporally, every
+rank owns a chunk of `frames` frames preceded by its persistence warm-up halo
+(weak scaling); no data-path collective.  Times are CUDA events, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# BASELINE.json configs.  Parameter overrides on the CLI defaults with noise off.
+GRADE = dict(brightness=0.05, contrast=1.15, gamma=1.1, saturation=1.1, temperature=0.1)
+GAUSS = dict(fast_bloom=False, bloom_sigma=1.5, bloom_threshold=0.7, bloom_strength=0.35)
+WARP = dict(warp_strength=0.15, scanline_angle=3.0, scanline_thickness=1.2)
+LIVE = dict(noise_strength=1.5, grain_size=2, flicker_strength=0.25, flicker_hz=60.0, glitch_amp_px=16, glitch_height_frac=0.25)
+WORKLOADS = {
+    "cfg1": dict(desc="CLI default chain, noise off, 640x480", w=640, h=480, frames=64, fps=30.0, over={}, cpu_frames=64),
+    "cfg2": dict(desc="1080p full chain, gaussian bloom sigma 1.5 thr 0.7 + colour grading", w=1920, h=1080, frames=600, fps=30.0,
+                 over={**GAUSS, **GRADE}, cpu_frames=12),
+    "cfg3": dict(desc="4K, warp 0.15, scanline angle 3.0, aberration, persistence", w=3840, h=2160, frames=600, fps=30.0,
+                 over=WARP, cpu_frames=6),
+    "cfg4": dict(desc="4K60 full chain incl. noise/grain/flicker/glitch", w=3840, h=2160, frames=600, fps=60.0,
+                 over={**GAUSS, **GRADE, **WARP, **LIVE}, cpu_frames=4),
+    "cfg5": dict(desc="8K full chain, gaussian bloom sigma 4", w=7680, h=4320, frames=150, fps=30.0,
+                 over={**GRADE, **WARP, **LIVE, **dict(fast_bloom=False, bloom_sigma=4.0, bloom_strength=0.3)}, cpu_frames=2),
+}
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def alg_bytes_per_px(persistence: float) -> int:
+    """uint8 in + uint8 out (+ float32 x3 state read and write when persistence is on)."""
+    return 30 if persistence > 0.0 else 6
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def product_params(over):
+    from pythoncrt_b200 import CrtParams
+    return CrtParams(noise_strength=0.0).but(**over)
+
+
+def oracle_params(over):
+    from oracle.crt_oracle import ChainParams
+    return ChainParams(noise_strength=0.0).but(**over)
+
+
+def run_reference_arm(args, wl):
+    """--impl reference: the reference's CPU path (oracle port, same numpy/cv2 passes, export-like
+    2-worker loop) on this box's host cores; each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import cpu_bench
+    p = oracle_params(wl["over"])
+    n = wl["cpu_frames"]
+    for _ in range(max(0, args.warmup)):
+        cpu_bench.time_cpu_path(wl["h"], wl["w"], p, wl["fps"], max(1, n // 4))
+    secs, info = 0.0, None
+    for _ in range(args.steps):
+        info = cpu_bench.time_cpu_path(wl["h"], wl["w"], p, wl["fps"], n)
+        secs += info["seconds"]
+    fps = n * args.steps / secs
+    sample = f"{n} frames of {wl['w']}x{wl['h']} per step ({wl['frames']}-frame workload sampled; CPU path ~{fps:.2f} fps)"
+    line = {"impl": "reference", "metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "desc": wl["desc"], "width": wl["w"], "height": wl["h"], "frames": wl["frames"]},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": info["cpu_count"], "kind": "port", "sample": sample,
+                             "worker_threads": info["workers"], "cv2_threads": info["cv2_threads"], "numpy": info["numpy"], "cv2": info["cv2"]},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=0, help="override frames per clip (debug)")
+    ap.add_argument("--policy", default="auto", choices=["auto", "staged", "fused"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.frames:
+        wl["frames"] = args.frames
+    if args.impl == "reference":
+        return run_reference_arm(args, wl)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pythoncrt_b200 import CrtEngine, clip
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    W, H, N, fps = wl["w"], wl["h"], wl["frames"], wl["fps"]
+    p = product_params(wl["over"])
+    rng_modes = dict(noise_mode="generate", glitch_mode="generate", seed=1234)
+    eng = CrtEngine(W, H, local).configure(p, variant="export", policy=args.policy, **rng_modes)
+
+    # this rank's chunk of the global clip: frames [rank*N, (rank+1)*N) preceded by the persistence halo
+    halo = clip.halo_frames(p.persistence) if rank > 0 else 0
+    first = rank * N - halo
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    frames = torch.randint(0, 256, (N + halo, H, W, 3), dtype=torch.uint8, device=dev, generator=g)
+    out = torch.empty_like(frames)
+    state = eng.new_state()
+
+    def step():
+        eng.process(frames, out, state=state, state_valid=False, fps=fps, first_index=first)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sync_all()
+    launches0 = eng.kernels_launched
+    sampler = ClockSampler(local)
+    sampler.start()
+    eng.profile_begin(min(16384, (N + halo) * args.steps))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    kern_ms, kern_n = eng.profile_end()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    launches = eng.kernels_launched - launches0
+    fused = int(eng.last_info.fused)
+    value = world * N * args.steps / (total_ms * 1e-3)
+    bpp = alg_bytes_per_px(p.persistence)
+    peak, peak_src = hbm_peak()
+    kern_avg_ms = kern_ms / max(1, kern_n)
+    achieved = (W * H * bpp) / (kern_avg_ms * 1e-3) / 1e9 if kern_n else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(args.workload)
+    except Exception:
+        pass
+
+    # ---- e2e: host buffers through crt_process_host (pinned in, pinned out) ----
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+        need = 2 * N * H * W * 3
+        n_e2e = N if psutil.virtual_memory().available > need * 1.5 + (8 << 30) else max(8, N // 8)
+        h_in = torch.empty((n_e2e, H, W, 3), dtype=torch.uint8).pin_memory()
+        h_out = torch.empty((n_e2e, H, W, 3), dtype=torch.uint8).pin_memory()
+        h_in.copy_(frames[halo:halo + n_e2e].cpu())
+        e2e_steps = max(1, min(args.steps, 3))
+        eng.reset_state()
+        eng.process_host(h_in.numpy(), h_out.numpy(), fps=fps, first_index=rank * N)       # warm-up (allocates the ring)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.reset_state()
+            eng.process_host(h_in.numpy(), h_out.numpy(), fps=fps, first_index=rank * N)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        same = bool(torch.equal(h_out[:4].to(dev), out[halo:halo + 4])) if rank == 0 else True
+        e2e = {"value": world * n_e2e * e2e_steps / float(dt.item()), "unit": "frames/s", "h2d_bytes_per_step": n_e2e * H * W * 3,
+               "d2h_bytes_per_step": n_e2e * H * W * 3, "frames_per_step": n_e2e, "steps": e2e_steps, "api": "crt_process_host",
+               "matches_device_path": same}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import cpu_bench
+        info = cpu_bench.time_cpu_path(H, W, oracle_params(wl["over"]), fps, wl["cpu_frames"])
+        cpu = {"value": info["fps"], "unit": "frames/s", "cores": info["cpu_count"], "kind": "port",
+               "sample": f"{info['frames']} frames of {W}x{H} through the export-like 2-worker loop, {info['seconds']:.1f} s",
+               "worker_threads": info["workers"], "cv2_threads": info["cv2_threads"], "numpy": info["numpy"], "cv2": info["cv2"]}
+
+    if rank == 0:
+        line = {
+            "metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "desc": wl["desc"], "width": W, "height": H, "frames_per_gpu": N, "halo_frames": halo,
+                       "fps": fps, "parallelism": f"temporal-shards x{world}", "path": "fused" if fused else "staged",
+                       "rng": "device counter-based (noise/glitch generated)", "l2": "clip (in+out) is larger than L2; no flush needed",
+                       "alg_bytes_per_px": bpp},
+            "effective_gbs": value * W * H * bpp / 1e9,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "fused tile kernel" if fused else "k_output (staged)",
+                         "kernel_avg_ms": kern_avg_ms, "kernel_launches_timed": kern_n,
+                         "kernel_share_of_step": (kern_ms / total_ms) if total_ms else None},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -177,6 +177,12 @@ int crt_process_host(crt_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, const cr
                      crt_launch_info* info);
 int crt_reset_state(crt_ctx* ctx);
 
+/* Timing hooks for bench.py: while enabled, CUDA events are recorded (on the
+ * launch stream) around the dominant kernel of every frame, up to max_samples.
+ * crt_profile_end synchronises them and returns the summed duration and count. */
+int crt_profile_begin(crt_ctx* ctx, int max_samples);
+int crt_profile_end(crt_ctx* ctx, double* total_ms, int* samples);
+
 /* Device-side generators (counter-based RNG), used when noise_mode/glitch_mode == 1;
  * exposed so a host can pre-generate and inspect the draws. */
 int crt_generate_noise(crt_ctx* ctx, uint64_t frame_index, float* d_plane /* [gh][gw] */, void* stream);

@@ -51,6 +51,9 @@ struct crt_ctx {
     bool dev_ok = false;
     int policy = 0;
     FusedPlan plan{};
+    std::vector<cudaEvent_t> prof_ev;   // start/stop pairs (crt_profile_begin/end)
+    int prof_cap = 0, prof_n = 0;
+    bool prof_on = false;
     std::string err;
 };
 
@@ -112,6 +115,13 @@ int gen_glitch(crt_ctx* ctx, const crt_frame& fr, const GlitchGeom& g, int32_t* 
     return CRT_OK;
 }
 
+// bench.py timing hook: events around the dominant kernel of a frame
+void prof_mark(crt_ctx* ctx, cudaStream_t st, bool stop) {
+    if (!ctx->prof_on || ctx->prof_n >= ctx->prof_cap) return;
+    cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + (stop ? 1 : 0)], st);
+    if (stop) ++ctx->prof_n;
+}
+
 // One frame through the staged kernels.
 int run_staged(crt_ctx* ctx, const FrameDev& f, const uint8_t* d_in, uint8_t* d_out, float* d_state, int has_prev, float* d_img,
                cudaStream_t st, int* launches) {
@@ -130,7 +140,9 @@ int run_staged(crt_ctx* ctx, const FrameDev& f, const uint8_t* d_in, uint8_t* d_
     }
     dim3 grd((d.W + 31) / 32, (d.H + 7) / 8);
     if (d.warp_on) { k_pre_warp<<<grd, blk, 0, st>>>(d, f, d_in, ctx->scratch); ++*launches; }
+    prof_mark(ctx, st, false);
     k_output<<<grd, blk, 0, st>>>(d, f, d_in, ctx->scratch, has_prev, d_state, d_out, d_img); ++*launches;
+    prof_mark(ctx, st, true);
     CU(cudaGetLastError());
     return CRT_OK;
 }
@@ -190,7 +202,11 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         float* img_i = d_img ? d_img + (size_t)i * frame_px * 3 : nullptr;
         float* state_i = (persist || (d_state && !d_img)) ? d_state : nullptr;
         int rc;
-        if (want_fused) { rc = run_fused(ctx->plan, d, f, in_i, out_i, state_i, has_prev, st, &launches); fused_used = 1; }
+        if (want_fused) {
+            prof_mark(ctx, st, false);
+            rc = run_fused(ctx->plan, d, f, in_i, out_i, state_i, has_prev, st, &launches); fused_used = 1;
+            prof_mark(ctx, st, true);
+        }
         else rc = run_staged(ctx, f, in_i, out_i, state_i, has_prev, img_i, st, &launches);
         if (rc == CRT_ERR_CUDA) return fail(ctx, rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
         if (rc) return rc;
@@ -239,6 +255,7 @@ int crt_destroy(crt_ctx* ctx) {
     if (ctx->noise_buf) cudaFree(ctx->noise_buf);
     if (ctx->glitch_buf) cudaFree(ctx->glitch_buf);
     if (ctx->state) cudaFree(ctx->state);
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     HostRing& r = ctx->ring;
     for (int s = 0; s < HostRing::SLOTS; ++s) {
         if (r.d_in[s]) cudaFree(r.d_in[s]);
@@ -347,6 +364,32 @@ int crt_process_host(crt_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, const cr
     CU(cudaStreamSynchronize(r.s_out));
     CU(cudaStreamSynchronize(r.s_comp));
     if (info) { info->kernels_launched = total_launches; info->fused = fused; }
+    return CRT_OK;
+}
+
+int crt_profile_begin(crt_ctx* ctx, int max_samples) {
+    if (!ctx || max_samples < 1) return CRT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    while ((int)ctx->prof_ev.size() < 2 * max_samples) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        ctx->prof_ev.push_back(e);
+    }
+    ctx->prof_cap = max_samples; ctx->prof_n = 0; ctx->prof_on = true;
+    return CRT_OK;
+}
+
+int crt_profile_end(crt_ctx* ctx, double* total_ms, int* samples) {
+    if (!ctx || !total_ms || !samples) return CRT_ERR_INVALID;
+    ctx->prof_on = false;
+    double tot = 0.0;
+    for (int i = 0; i < ctx->prof_n; ++i) {
+        CU(cudaEventSynchronize(ctx->prof_ev[2 * i + 1]));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        tot += ms;
+    }
+    *total_ms = tot; *samples = ctx->prof_n;
     return CRT_OK;
 }
 

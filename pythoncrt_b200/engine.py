@@ -212,6 +212,16 @@ class CrtEngine:
         """'state_prev = None' for the host-buffer path (crt_filter.py:1765)."""
         self._check(self.lib.crt_reset_state(self.ctx), "crt_reset_state")
 
+    def profile_begin(self, max_samples: int = 8192) -> None:
+        """Start recording CUDA events around the dominant kernel of every frame (bench.py)."""
+        self._check(self.lib.crt_profile_begin(self.ctx, int(max_samples)), "crt_profile_begin")
+
+    def profile_end(self):
+        """Returns (summed kernel time in ms, number of launches timed)."""
+        ms, n = C.c_double(), C.c_int()
+        self._check(self.lib.crt_profile_end(self.ctx, C.byref(ms), C.byref(n)), "crt_profile_end")
+        return ms.value, n.value
+
     def generate_noise(self, frame_index: int):
         torch = _torch()
         gh, gw = tables.noise_plane_shape(self.height, self.width, self.params.grain_size)
