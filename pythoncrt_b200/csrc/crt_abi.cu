@@ -38,6 +38,8 @@ struct crt_ctx {
     bool have_params = false;
     void* tab[CRT_TABLE_COUNT] = {};
     size_t tab_bytes[CRT_TABLE_COUNT] = {};
+    std::vector<int32_t> h_pix_x, h_pix_y;                 // host copies (tile planning, pix_uniform)
+    std::vector<Lerp1> h_dn_x, h_dn_y, h_up_x, h_up_y;     // host copies of the fast-bloom coordinate tables
     Lerp1 *dn_x = nullptr, *dn_y = nullptr, *up_x = nullptr, *up_y = nullptr, *nz_x = nullptr, *nz_y = nullptr;
     int nz_grain = 0;
     Scratch scratch{nullptr, nullptr, nullptr};
@@ -88,12 +90,22 @@ int build_dev(crt_ctx* ctx) {
     }
     TablePtrs t{};
     for (int i = 0; i < CRT_TABLE_COUNT; ++i) { t.tab[i] = ctx->tab[i]; t.bytes[i] = ctx->tab_bytes[i]; }
+    // pixelate tables of the regular form ps * (i / ps) let the fused kernel grade each source pixel once
+    t.pix_uniform = 0;
+    if (p.pixel_size > 1 && (int)ctx->h_pix_x.size() == ctx->W && (int)ctx->h_pix_y.size() == ctx->H) {
+        bool uni = true;
+        for (int x = 0; x < ctx->W && uni; ++x) uni = ctx->h_pix_x[x] == p.pixel_size * (x / p.pixel_size);
+        for (int y = 0; y < ctx->H && uni; ++y) uni = ctx->h_pix_y[y] == p.pixel_size * (y / p.pixel_size);
+        t.pix_uniform = uni ? p.pixel_size : 0;
+    }
     t.dn_x = ctx->dn_x; t.dn_y = ctx->dn_y; t.up_x = ctx->up_x; t.up_y = ctx->up_y; t.nz_x = ctx->nz_x; t.nz_y = ctx->nz_y;
     std::string err;
     int rc = derive_dev(p, ctx->W, ctx->H, t, &ctx->dev, &err);
     if (rc) return fail(ctx, rc, err);
     ctx->dev_ok = true;
-    ctx->plan = plan_fused(ctx->dev, glitch_active(p), p.glitch_amp_px);
+    Dev hd = ctx->dev;                                   // same block with HOST coordinate tables, for planning
+    hd.dn_x = ctx->h_dn_x.data(); hd.dn_y = ctx->h_dn_y.data(); hd.up_x = ctx->h_up_x.data(); hd.up_y = ctx->h_up_y.data();
+    ctx->plan = plan_fused(hd, glitch_active(p));
     return CRT_OK;
 }
 
@@ -235,10 +247,12 @@ int crt_create(int device, int width, int height, crt_ctx** out_ctx) {
     c->device = device; c->W = width; c->H = height;
     ctx = c;
     const int hw = width / 2 > 1 ? width / 2 : 1, hh = height / 2 > 1 ? height / 2 : 1;
-    int rc = upload(c, &c->dn_x, linear_coords(hw, width));
-    if (!rc) rc = upload(c, &c->dn_y, linear_coords(hh, height));
-    if (!rc) rc = upload(c, &c->up_x, linear_coords(width, hw));
-    if (!rc) rc = upload(c, &c->up_y, linear_coords(height, hh));
+    c->h_dn_x = linear_coords(hw, width); c->h_dn_y = linear_coords(hh, height);
+    c->h_up_x = linear_coords(width, hw); c->h_up_y = linear_coords(height, hh);
+    int rc = upload(c, &c->dn_x, c->h_dn_x);
+    if (!rc) rc = upload(c, &c->dn_y, c->h_dn_y);
+    if (!rc) rc = upload(c, &c->up_x, c->h_up_x);
+    if (!rc) rc = upload(c, &c->up_y, c->h_up_y);
     if (rc) { g_create_error = c->err; crt_destroy(c); return rc; }
     *out_ctx = c;
     return CRT_OK;
@@ -294,6 +308,8 @@ int crt_set_table(crt_ctx* ctx, int table, const void* h_data, size_t bytes) {
     if (!ctx->tab[table]) CU(cudaMalloc(&ctx->tab[table], bytes));
     CU(cudaMemcpy(ctx->tab[table], h_data, bytes, cudaMemcpyHostToDevice));
     ctx->tab_bytes[table] = bytes;
+    if (table == CRT_TABLE_PIXELATE_X) ctx->h_pix_x.assign((const int32_t*)h_data, (const int32_t*)h_data + bytes / 4);
+    if (table == CRT_TABLE_PIXELATE_Y) ctx->h_pix_y.assign((const int32_t*)h_data, (const int32_t*)h_data + bytes / 4);
     ctx->dev_ok = false;
     return CRT_OK;
 }

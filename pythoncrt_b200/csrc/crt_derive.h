@@ -15,6 +15,7 @@ struct TablePtrs {
     const void* tab[CRT_TABLE_COUNT];
     size_t bytes[CRT_TABLE_COUNT];
     const Lerp1 *dn_x, *dn_y, *up_x, *up_y, *nz_x, *nz_y;
+    int pix_uniform;     // see Dev::pix_uniform (the caller inspects its host copy of the pixelate tables)
 };
 
 // cv2.resize INTER_LINEAR coordinates along one axis (oracle/cv_restated.py linear_coords)
@@ -44,11 +45,13 @@ inline int derive_dev(const crt_params& p, int W, int H, const TablePtrs& t, Dev
     Dev d{};
     d.W = W; d.H = H;
     d.aberr = p.aberration_px;
+    d.aberr_mod = ((p.aberration_px % W) + W) % W;
     if (p.pixel_size > 1) {
         if (t.bytes[CRT_TABLE_PIXELATE_X] != (size_t)W * 4 || t.bytes[CRT_TABLE_PIXELATE_Y] != (size_t)H * 4)
             { *err = "pixel_size > 1 needs CRT_TABLE_PIXELATE_X [W] and _Y [H]"; return CRT_ERR_INVALID; }
         d.pix_x = (const int32_t*)t.tab[CRT_TABLE_PIXELATE_X];
         d.pix_y = (const int32_t*)t.tab[CRT_TABLE_PIXELATE_Y];
+        d.pix_uniform = t.pix_uniform;
     }
     d.col_sat = p.saturation != 1.0; d.sat_f = (float)p.saturation;
     d.col_temp = p.temperature != 0.0;

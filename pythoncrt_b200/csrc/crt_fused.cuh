@@ -1,16 +1,489 @@
-// crt_fused.cuh — fused tile kernel (placeholder plan: staged path only for now).
+// crt_fused.cuh — the fused tile kernel: ONE launch per frame does the whole chain
+// (u8 in -> colour -> bloom -> triad -> scanlines -> vignette -> flicker -> noise ->
+// warp gather -> text -> persistence -> u8 out + float32 state).  Every byte of the
+// frame, of the state and of the output crosses HBM once; the bloom halo and the
+// warp footprint live in shared memory.
+//
+// Per CTA (256 threads, output tile 64 x TH):
+//   phase 0  [warp only] every thread computes the cv2.remap taps of its output
+//            pixels; a block-wide min/max gives the source footprint Q of the tile
+//   phase 1  stages 0-4 (graded input, thresholded bloom source) for the region
+//            P = Q grown by the bloom halo -> shared memory.  With pixelate on,
+//            each distinct source pixel is graded once and replicated.
+//   phase 2  bloom in shared memory: 2x2 down-scale cells (fast path) or the
+//            gaussian row pass
+//   phase 3  [warp only] stages 5-10 evaluated in place over Q
+//   phase 4  per output pixel: (column pass +) stages 5-10, or the 4-tap gather
+//            from Q; text; blend with the state; 16-byte state stores, packed
+//            uint8 stores
+// Everything that feeds the triad LUT uses crt_math.cuh's exact arithmetic
+// (shared with the staged kernels and checked on the host by tests/host_emu).
+// After the LUT only +-1 LSB matters, so the masks use per-tile row/column
+// tables and fast intrinsics (mask_at below) instead of double precision.
 #pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
 #include "crt_stages.cuh"
 
 namespace crt {
 
+constexpr int FT = 256;                 // threads per CTA
+constexpr int FTW = 64;                 // tile width (pixels); 4 pixels per thread per row
+constexpr int FROW_THREADS = FTW / 4;   // 16 threads cover one tile row
+constexpr int FROWS_PER_PASS = FT / FROW_THREADS;   // 16 rows per pass
+constexpr int FMAX_ROWS = 192;          // rows of per-tile row tables
+constexpr int FMAX_COLS = 256;          // columns of per-tile column tables
+
 struct FusedPlan {
     bool ok = false;
-    const char* why = "fused kernel not built yet";
+    const char* why = "not planned";
+    int bloom = 0, warp = 0;
+    int th = 16;                        // tile height
+    int cap_px = 0;                     // capacity of the P-region buffer in pixels
+    int cap_aux = 0;                    // floats of the auxiliary buffer (ds cells / row pass / T1 tile)
+    size_t smem = 0;
 };
 
-inline FusedPlan plan_fused(const Dev&, bool, int) { return FusedPlan{}; }
+struct FusedGeom { int th, cap_px, cap_aux; };
 
-inline int run_fused(const FusedPlan&, const Dev&, const FrameDev&, const uint8_t*, uint8_t*, float*, int, cudaStream_t, int*) { return 4; }
+// ---- region helpers ------------------------------------------------------------------------
+struct Box { int x0, y0, x1, y1; };     // inclusive
+CRT_HD int box_w(const Box& b) { return b.x1 - b.x0 + 1; }
+CRT_HD int box_h(const Box& b) { return b.y1 - b.y0 + 1; }
+
+// Region of graded-input pixels needed to evaluate bloom on Q (cells = ds cells of the fast path).
+CRT_HD Box grow_for_bloom(const Dev& d, const Box& q, Box* cells) {
+    Box p = q;
+    if (d.bloom_mode == 1) {
+        Box c;
+        c.x0 = up_coord(d, d.up_x, q.x0, d.hw).s0; c.x1 = up_coord(d, d.up_x, q.x1, d.hw).s1;
+        c.y0 = up_coord(d, d.up_y, q.y0, d.hh).s0; c.y1 = up_coord(d, d.up_y, q.y1, d.hh).s1;
+        *cells = c;
+        p.x0 = imin(q.x0, down_coord(d, d.dn_x, c.x0).s0); p.x1 = imax(q.x1, down_coord(d, d.dn_x, c.x1).s1);
+        p.y0 = imin(q.y0, down_coord(d, d.dn_y, c.y0).s0); p.y1 = imax(q.y1, down_coord(d, d.dn_y, c.y1).s1);
+    } else if (d.bloom_mode == 2) {
+        const int r = d.ksize >> 1;      // REPLICATE border: clamped coordinates stay inside the image
+        p.x0 = imax(q.x0 - r, 0); p.x1 = imin(q.x1 + r, d.W - 1);
+        p.y0 = imax(q.y0 - r, 0); p.y1 = imin(q.y1 + r, d.H - 1);
+    }
+    return p;
+}
+
+// Warp map with the per-row / per-column normalised coordinates hoisted (same float32
+// operations and order as warp_taps, crt_math.cuh).
+CRT_HD float warp_norm(float v, float c, float dv) { return fdiv(fsub(v, c), dv); }
+CRT_HD Taps warp_taps_n(const Dev& d, float xn, float yn) {
+    float r2 = fadd(fmul(xn, xn), fmul(yn, yn));
+    float fac = fadd(1.0f, fmul(d.warp_k, r2));
+    float mx = fadd(fmul(fmul(xn, fac), d.warp_cx), d.warp_cx);
+    float my = fadd(fmul(fmul(yn, fac), d.warp_cy), d.warp_cy);
+    float qx = clampf(fmul(mx, 32.0f), -1.0e9f, 1.0e9f), qy = clampf(fmul(my, 32.0f), -1.0e9f, 1.0e9f);
+    int sx = (int)rintf(qx), sy = (int)rintf(qy);
+    Taps t;
+    t.ix = sx >> 5; t.iy = sy >> 5;
+    float fx = fmul((float)(sx & 31), 0.03125f), fy = fmul((float)(sy & 31), 0.03125f);
+    float gx = fsub(1.0f, fx), gy = fsub(1.0f, fy);
+    t.w00 = fmul(gy, gx); t.w01 = fmul(gy, fx); t.w10 = fmul(fy, gx); t.w11 = fmul(fy, fx);
+    return t;
+}
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ void store_f3(float* p, F3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+__device__ __forceinline__ F3 load_f3(const float* p) { return mk3(p[0], p[1], p[2]); }
+// q = n / dv with magic = 2^32 / dv + 1 computed once per CTA; exact for n * dv < 2^32 (dv >= 2)
+__device__ __forceinline__ int fastdiv(int n, unsigned magic) { return magic ? (int)__umulhi((unsigned)n, magic) : n; }
+__device__ __forceinline__ unsigned make_magic(int dv) { return dv <= 1 ? 0u : 0xffffffffu / (unsigned)dv + 1u; }   // 0 = divide by 1
+
+// Per-tile tables for the masks applied after the triad LUT.
+struct MaskTabs {
+    float* row_scan;    // scan_mode 1: row mask;  scan_mode 2: phase fraction of the row
+    float* col_scan;    // scan_mode 2: phase fraction of the column
+    float* row_vig;     // ((y - cy) / ry)^2
+    float* col_vig;     // ((x - cx) / rx)^2
+};
+
+// Stages 7-8 as one multiplier (after the LUT the clip between them is a no-op: both factors are <= 1).
+__device__ __forceinline__ float mask_at(const Dev& d, const MaskTabs& m, int r, int c, int y, int x) {
+    float mk = 1.0f;
+    if (d.scan_mode == 1) mk = m.row_scan[r];
+    else if (d.scan_mode == 2) {
+        float t = m.row_scan[r] + m.col_scan[c];
+        t = t >= 1.0f ? t - 1.0f : t;                                  // turns in [0, 1)
+        float s = fmaxf(0.5f - 0.5f * __sinf(6.283185307f * (t - 0.5f)), 0.0f);   // 0.5 (1 + sin(2 pi t))
+        float shaped = (d.scan_inv_sharp == 1.0f) ? s : __powf(s, d.scan_inv_sharp);
+        mk = 1.0f - d.scan_strength * shaped;
+    }
+    if (d.vig_mode == 1) mk *= 1.0f - d.vig_strength * __saturatef(m.row_vig[r] + m.col_vig[c]);
+    else if (d.vig_mode == 2) mk *= d.vig_plane[(size_t)y * d.W + x];
+    return mk;
+}
+
+// Stages 6-10 with the mask tables (the triad LUT part is crt_math.cuh's exact code).
+__device__ __forceinline__ F3 after_bloom_fast(const Dev& d, const FrameDev& f, F3 v, int y, int x, const float* fwd, const float* inv,
+                                               const MaskTabs& m, int r, int c) {
+    if (d.triad_mode) v = triad(d, v, x, fwd, inv);
+    if (d.scan_mode | d.vig_mode) {
+        const float mk = mask_at(d, m, r, c, y, x);
+        v.x = __saturatef(v.x * mk); v.y = __saturatef(v.y * mk); v.z = __saturatef(v.z * mk);
+    }
+    if (f.flicker_on) { v.x = __saturatef(v.x * f.flicker); v.y = __saturatef(v.y * f.flicker); v.z = __saturatef(v.z * f.flicker); }
+    if (d.noise_on) {
+        const float n = noise_at(d, f, y, x);
+        v.x = __saturatef(v.x + n); v.y = __saturatef(v.y + n); v.z = __saturatef(v.z + n);
+    }
+    return v;
+}
+
+template <int BLOOM, bool WARP>
+__global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                              float* __restrict__ state, int has_prev, FusedGeom g) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ float s_fwd[1025], s_inv[1025];
+    __shared__ float s_unit[256];
+    __shared__ float s_rows[2 * FMAX_ROWS], s_cols[2 * FMAX_COLS];
+    __shared__ int s_box[4];
+    float* T = sm;                                  // [ph][pw][3] graded input (bloom source when thresholded)
+    float* A = sm + g.cap_px * 3;                   // auxiliary: ds cells | row pass (+ T1 tile)
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int ox0 = blockIdx.x * FTW, oy0 = blockIdx.y * g.th;
+    const int ox1 = imin(ox0 + FTW, d.W) - 1, oy1 = imin(oy0 + g.th, d.H) - 1;
+    const int trow = tid / FROW_THREADS, xb = ox0 + (tid % FROW_THREADS) * 4;    // this thread's pixel quad
+
+    if (d.triad_mode >= 2)
+        for (int i = tid; i < 1025; i += FT) { s_fwd[i] = d.lut_fwd[i]; s_inv[i] = d.lut_inv[i]; }
+    s_unit[tid] = __fdiv_rn((float)tid, 255.0f);    // FT == 256
+    if (WARP && tid < 4) s_box[tid] = (tid < 2) ? 0x7fffffff : -0x7fffffff;
+    __syncthreads();
+
+    // ---- phase 0: footprint of the tile in the pre-warp image ------------------------------
+    Box q;
+    float xn[4] = {0.f, 0.f, 0.f, 0.f};
+    if (WARP) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xn[k] = warp_norm((float)(xb + k), d.warp_cx, d.warp_dx);
+        int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
+        for (int y = oy0 + trow; y <= oy1; y += FROWS_PER_PASS) {
+            const float yn = warp_norm((float)y, d.warp_cy, d.warp_dy);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (xb + k <= ox1) {
+                    const Taps t = warp_taps_n(d, xn[k], yn);
+                    if (t.ix + 1 >= 0 && t.ix < d.W && t.iy + 1 >= 0 && t.iy < d.H) {      // only taps inside the image are read
+                        bx0 = imin(bx0, imax(t.ix, 0)); bx1 = imax(bx1, imin(t.ix + 1, d.W - 1));
+                        by0 = imin(by0, imax(t.iy, 0)); by1 = imax(by1, imin(t.iy + 1, d.H - 1));
+                    }
+                }
+            }
+        }
+        bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
+        bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
+        if (lane == 0) { atomicMin(&s_box[0], bx0); atomicMin(&s_box[1], by0); atomicMax(&s_box[2], bx1); atomicMax(&s_box[3], by1); }
+        __syncthreads();
+        q.x0 = s_box[0]; q.y0 = s_box[1]; q.x1 = s_box[2]; q.y1 = s_box[3];
+    } else {
+        q.x0 = ox0; q.y0 = oy0; q.x1 = ox1; q.y1 = oy1;
+    }
+    const bool q_empty = WARP && (q.x1 < q.x0 || q.y1 < q.y0);
+    Box cells{0, 0, -1, -1};
+    Box p = q;
+    if (!q_empty) p = grow_for_bloom(d, q, &cells);
+    const int pw = q_empty ? 0 : box_w(p), ph = q_empty ? 0 : box_h(p);
+    const int qw = q_empty ? 0 : box_w(q), qh = q_empty ? 0 : box_h(q);
+    // planning guarantees the region fits; a violated bound must never corrupt memory
+    if (pw * ph > g.cap_px || qh > FMAX_ROWS || qw > FMAX_COLS) {
+        if (tid == 0) printf("crt_b200: fused tile region %dx%d exceeds capacity %d\n", pw, ph, g.cap_px);
+        return;
+    }
+    MaskTabs mt{s_rows, s_cols, s_rows + FMAX_ROWS, s_cols + FMAX_COLS};
+
+    // ---- phase 1: graded input over P (each distinct source pixel once) ------------------------
+    const int cw = BLOOM == 2 ? qw : 0;             // row-pass columns
+    float* T1 = A + ph * cw * 3;                    // [th][FTW][3], only BLOOM==2 && thr_on
+    if (!q_empty) {
+        const int ps = (d.pix_uniform > 1 && d.text_mode != 1) ? d.pix_uniform : 1;
+        const int ux0 = p.x0 / ps, uy0 = p.y0 / ps;
+        const int nux = p.x1 / ps - ux0 + 1, nuy = p.y1 / ps - uy0 + 1;
+        const unsigned magic = make_magic(nux);
+        for (int u = tid; u < nux * nuy; u += FT) {
+            const int uy = fastdiv(u, magic), ux = u - uy * nux;
+            const int xa = imax((ux0 + ux) * ps, p.x0), xe = imin((ux0 + ux) * ps + ps - 1, p.x1);
+            const int ya = imax((uy0 + uy) * ps, p.y0), ye = imin((uy0 + uy) * ps + ps - 1, p.y1);
+            const F3 v1 = graded_input_lut(d, in, ya, xa, s_unit);
+            const F3 v = (BLOOM == 2 && d.thr_on) ? bloom_src(d, v1) : v1;
+            for (int y = ya; y <= ye; ++y)
+                for (int x = xa; x <= xe; ++x) {
+                    if (BLOOM == 2 && d.thr_on && y >= oy0 && y <= oy1 && x >= ox0 && x <= ox1)
+                        store_f3(T1 + ((y - oy0) * FTW + (x - ox0)) * 3, v1);
+                    store_f3(T + ((y - p.y0) * pw + (x - p.x0)) * 3, v);
+                }
+        }
+        // per-tile mask tables over Q
+        for (int r = tid; r < qh; r += FT) {
+            const int y = q.y0 + r;
+            if (d.scan_mode == 1) mt.row_scan[r] = scan_row(d, f, y);
+            else if (d.scan_mode == 2) { double t = ((double)y + f.phase) * d.scan_inv_period; mt.row_scan[r] = (float)(t - floor(t)); }
+            if (d.vig_mode == 1) { const float ny = ((float)y - d.vig_cy) * d.vig_iry; mt.row_vig[r] = ny * ny; }
+        }
+        for (int c = tid; c < qw; c += FT) {
+            const int x = q.x0 + c;
+            if (d.scan_mode == 2) { double t = (d.scan_tan * (double)x) * d.scan_inv_period; mt.col_scan[c] = (float)(t - floor(t)); }
+            if (d.vig_mode == 1) { const float nx = ((float)x - d.vig_cx) * d.vig_irx; mt.col_vig[c] = nx * nx; }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: bloom in shared memory -------------------------------------------------------
+    const int dw = box_w(cells), dh = box_h(cells);
+    if (BLOOM == 1 && !q_empty) {
+        const unsigned magic = make_magic(dw);
+        for (int u = tid; u < dw * dh; u += FT) {
+            const int r = fastdiv(u, magic), c = u - r * dw;
+            const Lerp1 cy = down_coord(d, d.dn_y, cells.y0 + r), cx = down_coord(d, d.dn_x, cells.x0 + c);
+            const float* r0 = T + (cy.s0 - p.y0) * pw * 3;
+            const float* r1 = T + (cy.s1 - p.y0) * pw * 3;
+            const int a0 = (cx.s0 - p.x0) * 3, a1 = (cx.s1 - p.x0) * 3;
+            const F3 a = bloom_src(d, load_f3(r0 + a0)), b = bloom_src(d, load_f3(r0 + a1));
+            const F3 cc = bloom_src(d, load_f3(r1 + a0)), e = bloom_src(d, load_f3(r1 + a1));
+            float* o = A + u * 3;
+            o[0] = lerp_cv(lerp_cv(a.x, b.x, cx.w), lerp_cv(cc.x, e.x, cx.w), cy.w);
+            o[1] = lerp_cv(lerp_cv(a.y, b.y, cx.w), lerp_cv(cc.y, e.y, cx.w), cy.w);
+            o[2] = lerp_cv(lerp_cv(a.z, b.z, cx.w), lerp_cv(cc.z, e.z, cx.w), cy.w);
+        }
+        __syncthreads();
+    }
+    if (BLOOM == 2) {
+        // row pass over every region row, for the tile's columns; REPLICATE = clamped column index
+        const int K = d.ksize, rad = K >> 1;
+        const int rowlen = cw * 3;
+        const unsigned magic = make_magic(rowlen);
+        for (int u = tid; u < ph * rowlen; u += FT) {
+            const int r = fastdiv(u, magic), e = u - r * rowlen;
+            const int c = fastdiv(e, 0x55555556u /* 2^32/3 + 1 */), ch = e - c * 3, x = q.x0 + c;
+            const float* row = T + r * pw * 3;
+            float acc;
+            if (x - rad >= p.x0 && x + rad <= p.x1) {
+                acc = gauss_row(row + (x - rad - p.x0) * 3 + ch, 3, d.taps, K);
+            } else {                     // image border: REPLICATE = clamped column index
+                auto tapv = [&](int i) { return row[(imin(imax(x - rad + i, 0), d.W - 1) - p.x0) * 3 + ch]; };
+                if (K == 1) acc = fmul(tapv(0), d.taps[0]);
+                else if (K == 3) acc = ffma(tapv(1), d.taps[1], fmul(fadd(tapv(0), tapv(2)), d.taps[2]));
+                else if (K == 5) acc = ffma(fadd(tapv(4), tapv(0)), d.taps[4], ffma(tapv(2), d.taps[2], fmul(fadd(tapv(1), tapv(3)), d.taps[3])));
+                else {
+                    acc = fmul(tapv(0), d.taps[0]);
+                    for (int i = 1; i < K; ++i) acc = ffma(tapv(i), d.taps[i], acc);
+                }
+            }
+            A[u] = acc;
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 3 [warp]: stages 5-10 in place over Q ----------------------------------------------
+    if (WARP && !q_empty) {
+        const unsigned magic = make_magic(qw);
+        for (int u = tid; u < qw * qh; u += FT) {
+            const int r = fastdiv(u, magic), c = u - r * qw;
+            const int y = q.y0 + r, x = q.x0 + c;
+            float* tp = T + ((y - p.y0) * pw + (x - p.x0)) * 3;
+            F3 v = load_f3(tp);
+            if (BLOOM == 1) v = add_bloom(d, v, bloom_up_at(d, A, dw * 3, cells.y0, cells.x0, y, x));
+            v = after_bloom_fast(d, f, v, y, x, s_fwd, s_inv, mt, r, c);
+            store_f3(tp, v);
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 4: output pixels ---------------------------------------------------------------------
+    const float pp = d.persist, pq = d.persist_q;
+    const bool vec = (d.W & 3) == 0;
+    if (xb > ox1) return;
+    for (int y = oy0 + trow; y <= oy1; y += FROWS_PER_PASS) {
+        const int o = (y * d.W + xb) * 3;           // < 2^31 (checked by plan_fused)
+        const int npx = imin(4, ox1 - xb + 1);
+        float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa, pc = pa;       // previous state of the 4 pixels
+        if (has_prev) {
+            if (vec) {
+                const float4* sp = reinterpret_cast<const float4*>(state + o);
+                pa = sp[0]; pb = sp[1]; pc = sp[2];
+            } else {
+                float t[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) t[k] = (k < npx * 3) ? state[o + k] : 0.f;
+                pa = make_float4(t[0], t[1], t[2], t[3]); pb = make_float4(t[4], t[5], t[6], t[7]); pc = make_float4(t[8], t[9], t[10], t[11]);
+            }
+        }
+        const float prev[12] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, pc.x, pc.y, pc.z, pc.w};
+        float res[12];
+        float yn = 0.f;
+        if (WARP) yn = warp_norm((float)y, d.warp_cy, d.warp_dy);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int x = xb + k;
+            F3 v = mk3(0.f, 0.f, 0.f);
+            if (k < npx) {
+                if (WARP) {
+                    if (!q_empty) {
+                        const Taps t = warp_taps_n(d, xn[k], yn);
+                        F3 a[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int ty = t.iy + (j >> 1), tx = t.ix + (j & 1);
+                            const bool ok = ty >= 0 && ty < d.H && tx >= 0 && tx < d.W;
+                            const float* qp = T + (((ok ? ty : q.y0) - p.y0) * pw + ((ok ? tx : q.x0) - p.x0)) * 3;
+                            a[j] = ok ? load_f3(qp) : mk3(0.f, 0.f, 0.f);
+                        }
+                        v = mk3(gather4(a[0].x, a[1].x, a[2].x, a[3].x, t), gather4(a[0].y, a[1].y, a[2].y, a[3].y, t),
+                                gather4(a[0].z, a[1].z, a[2].z, a[3].z, t));
+                    }
+                } else {
+                    const float* tp = T + ((y - p.y0) * pw + (x - p.x0)) * 3;
+                    v = (BLOOM == 2 && d.thr_on) ? load_f3(T1 + ((y - oy0) * FTW + (x - ox0)) * 3) : load_f3(tp);
+                    if (BLOOM == 1) v = add_bloom(d, v, bloom_up_at(d, A, dw * 3, cells.y0, cells.x0, y, x));
+                    if (BLOOM == 2) {
+                        const int K = d.ksize, rad = K >> 1, c = x - q.x0;
+                        float bl[3];
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            if (y - rad >= p.y0 && y + rad <= p.y1) {
+                                bl[ch] = gauss_col(A + ((y - p.y0) * cw + c) * 3 + ch, cw * 3, d.taps, K);
+                            } else {     // image border: REPLICATE = clamped row index
+                                const float* col = A + c * 3 + ch;
+                                float acc = fmul(col[(y - p.y0) * cw * 3], d.taps[rad]);
+                                for (int i = 1; i <= rad; ++i) {
+                                    const int yu = imin(y + i, d.H - 1) - p.y0, yd = imax(y - i, 0) - p.y0;
+                                    acc = ffma(fadd(col[yu * cw * 3], col[yd * cw * 3]), d.taps[rad + i], acc);
+                                }
+                                bl[ch] = acc;
+                            }
+                        }
+                        v = add_bloom(d, v, mk3(bl[0], bl[1], bl[2]));
+                    }
+                    v = after_bloom_fast(d, f, v, y, x, s_fwd, s_inv, mt, y - q.y0, x - q.x0);
+                }
+                if (d.text_mode == 2) v = text_blend(d, v, y, x);
+                if (has_prev) { v.x = blend(prev[k * 3], v.x, pp, pq); v.y = blend(prev[k * 3 + 1], v.y, pp, pq); v.z = blend(prev[k * 3 + 2], v.z, pp, pq); }
+            }
+            res[k * 3] = v.x; res[k * 3 + 1] = v.y; res[k * 3 + 2] = v.z;
+        }
+        if (vec) {
+            if (state) {
+                float4* sp = reinterpret_cast<float4*>(state + o);
+                sp[0] = make_float4(res[0], res[1], res[2], res[3]);
+                sp[1] = make_float4(res[4], res[5], res[6], res[7]);
+                sp[2] = make_float4(res[8], res[9], res[10], res[11]);
+            }
+            uint32_t w[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                w[j] = (uint32_t)quantise(res[j * 4]) | ((uint32_t)quantise(res[j * 4 + 1]) << 8) | ((uint32_t)quantise(res[j * 4 + 2]) << 16) |
+                       ((uint32_t)quantise(res[j * 4 + 3]) << 24);
+            uint32_t* op = reinterpret_cast<uint32_t*>(out + o);
+            op[0] = w[0]; op[1] = w[1]; op[2] = w[2];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+                if (k < npx * 3) {
+                    if (state) state[o + k] = res[k];
+                    out[o + k] = quantise(res[k]);
+                }
+        }
+    }
+}
+
+#endif  // __CUDACC__
+
+// ---- planning (host) --------------------------------------------------------------------------
+// `hd` is a copy of the device parameter block whose coordinate tables point at HOST copies.
+// The worst-case region over all tiles is exact: it is evaluated with the same float32 warp map
+// the kernel uses.  Tall tiles amortise the bloom/warp halo, so the tallest tile that leaves room
+// for two CTAs per SM is chosen.
+inline FusedPlan plan_fused(const Dev& hd, bool glitch_on) {
+    const Dev& d = hd;
+    FusedPlan pl;
+    pl.bloom = d.bloom_mode; pl.warp = d.warp_on;
+    if (glitch_on) { pl.why = "glitch gather is handled by the staged kernels"; return pl; }
+    if (d.warp_on && d.bloom_mode == 2) { pl.why = "warp + gaussian bloom is handled by the staged kernels"; return pl; }
+    if ((size_t)d.W * d.H * 3 >= ((size_t)1 << 31)) { pl.why = "frame too large for 32-bit indexing"; return pl; }
+    // warp: per-row / per-column normalised coordinates, as the kernel computes them
+    std::vector<float> xn(d.warp_on ? d.W : 0), yn(d.warp_on ? d.H : 0);
+    for (int x = 0; x < (int)xn.size(); ++x) xn[x] = warp_norm((float)x, d.warp_cx, d.warp_dx);
+    for (int y = 0; y < (int)yn.size(); ++y) yn[y] = warp_norm((float)y, d.warp_cy, d.warp_dy);
+    FusedPlan best;
+    best.why = "tile footprint does not fit in shared memory";
+    for (int th : {64, 32, 16}) {
+        size_t best_px = 0, best_aux = 0;
+        int max_qh = 0, max_qw = 0;
+        const int tiles_x = (d.W + FTW - 1) / FTW, tiles_y = (d.H + th - 1) / th;
+        for (int ty = 0; ty < tiles_y; ++ty)
+            for (int tx = 0; tx < tiles_x; ++tx) {
+                Box o{tx * FTW, ty * th, imin((tx + 1) * FTW, d.W) - 1, imin((ty + 1) * th, d.H) - 1};
+                Box q = o;
+                if (d.warp_on) {
+                    q = Box{0x7fffffff, 0x7fffffff, -0x7fffffff, -0x7fffffff};
+                    for (int y = o.y0; y <= o.y1; ++y)
+                        for (int x = o.x0; x <= o.x1; ++x) {
+                            Taps t = warp_taps_n(d, xn[x], yn[y]);
+                            if (t.ix + 1 >= 0 && t.ix < d.W && t.iy + 1 >= 0 && t.iy < d.H) {
+                                q.x0 = imin(q.x0, imax(t.ix, 0)); q.x1 = imax(q.x1, imin(t.ix + 1, d.W - 1));
+                                q.y0 = imin(q.y0, imax(t.iy, 0)); q.y1 = imax(q.y1, imin(t.iy + 1, d.H - 1));
+                            }
+                        }
+                    if (q.x1 < q.x0 || q.y1 < q.y0) continue;
+                }
+                Box cells{0, 0, -1, -1};
+                Box p = grow_for_bloom(d, q, &cells);
+                size_t px = (size_t)box_w(p) * box_h(p);
+                size_t aux = 0;
+                if (d.bloom_mode == 1) aux = (size_t)box_w(cells) * box_h(cells) * 3;
+                if (d.bloom_mode == 2) aux = (size_t)box_h(p) * box_w(q) * 3 + (d.thr_on ? (size_t)th * FTW * 3 : 0);
+                if (px > best_px) best_px = px;
+                if (aux > best_aux) best_aux = aux;
+                if (box_h(q) > max_qh) max_qh = box_h(q);
+                if (box_w(q) > max_qw) max_qw = box_w(q);
+            }
+        const size_t smem = (best_px * 3 + best_aux) * sizeof(float);
+        const bool fits = smem <= 200 * 1024 && max_qh <= FMAX_ROWS && max_qw <= FMAX_COLS && best_px < 21000;
+        if (!fits) continue;
+        FusedPlan c;
+        c.ok = true; c.why = ""; c.bloom = d.bloom_mode; c.warp = d.warp_on;
+        c.th = th; c.cap_px = (int)best_px; c.cap_aux = (int)best_aux; c.smem = smem;
+        if (!best.ok) best = c;                          // tallest tile that fits at all
+        if (smem + 14 * 1024 <= 112 * 1024) return c;    // tallest tile that still allows 2 CTAs per SM
+    }
+    return best;
+}
+
+#if defined(__CUDACC__)
+template <int BLOOM, bool WARP>
+inline int launch_fused_t(const FusedPlan& pl, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state,
+                          int has_prev, cudaStream_t st) {
+    static size_t configured[64] = {};      // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (pl.smem > configured[dev & 63]) {
+        if (cudaFuncSetAttribute(k_fused<BLOOM, WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) return 2;
+        configured[dev & 63] = pl.smem;
+    }
+    dim3 grid((d.W + FTW - 1) / FTW, (d.H + pl.th - 1) / pl.th);
+    FusedGeom g{pl.th, pl.cap_px, pl.cap_aux};
+    k_fused<BLOOM, WARP><<<grid, FT, pl.smem, st>>>(d, f, in, out, state, has_prev, g);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
+inline int run_fused(const FusedPlan& pl, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, int has_prev,
+                     cudaStream_t st, int* launches) {
+    int rc;
+    if (d.warp_on) rc = d.bloom_mode == 1 ? launch_fused_t<1, true>(pl, d, f, in, out, state, has_prev, st)
+                                          : launch_fused_t<0, true>(pl, d, f, in, out, state, has_prev, st);
+    else rc = d.bloom_mode == 2 ? launch_fused_t<2, false>(pl, d, f, in, out, state, has_prev, st)
+            : d.bloom_mode == 1 ? launch_fused_t<1, false>(pl, d, f, in, out, state, has_prev, st)
+                                : launch_fused_t<0, false>(pl, d, f, in, out, state, has_prev, st);
+    ++*launches;
+    return rc;
+}
+#endif
 
 }  // namespace crt

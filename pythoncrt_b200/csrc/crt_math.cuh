@@ -98,7 +98,9 @@ struct Lerp1 { int32_t s0, s1; float w; };
 struct Dev {
     int W, H;
     // stage 1-2: aberration + pixelate (crt_filter.py:571-584)
-    int aberr;
+    int aberr;                   // aberration_px
+    int aberr_mod;               // aberration_px mod W, in [0, W): lets the kernels wrap with one compare
+    int pix_uniform;             // pixel_size when pix_x[x] == ps*(x/ps) and pix_y likewise (lets tiles de-duplicate), else 0
     const int32_t* pix_x;        // [W] or null
     const int32_t* pix_y;        // [H] or null
     // stage 3: colour (:279-305)
@@ -158,7 +160,7 @@ CRT_HD void source_bytes(const Dev& d, const uint8_t* __restrict__ in, int y, in
     int sx = d.pix_x ? d.pix_x[x] : x;
     const uint8_t* row = in + (size_t)sy * d.W * 3;
     int x0 = sx, x2 = sx;
-    if (d.aberr != 0) { x0 = pymod(sx - d.aberr, d.W); x2 = pymod(sx + d.aberr, d.W); }
+    if (d.aberr != 0) { x0 = wrap(sx - d.aberr_mod, d.W); x2 = wrap(sx + d.aberr_mod, d.W); }
     b0 = row[x0 * 3 + 0];
     b1 = row[sx * 3 + 1];
     b2 = row[x2 * 3 + 2];
@@ -207,6 +209,16 @@ CRT_HD F3 graded_input(const Dev& d, const uint8_t* __restrict__ in, int y, int 
     uint8_t b0, b1, b2;
     source_bytes(d, in, y, x, b0, b1, b2);
     F3 v = colour(d, mk3(unit(b0), unit(b1), unit(b2)));
+    if (d.text_mode == 1) v = text_blend(d, v, y, x);
+    return v;
+}
+
+// Same, with the u8 -> float32 conversion read from a 256-entry table of unit() values
+// (identical results; saves three IEEE divisions per pixel in the fused kernel).
+CRT_HD F3 graded_input_lut(const Dev& d, const uint8_t* __restrict__ in, int y, int x, const float* __restrict__ unit_lut) {
+    uint8_t b0, b1, b2;
+    source_bytes(d, in, y, x, b0, b1, b2);
+    F3 v = colour(d, mk3(unit_lut[b0], unit_lut[b1], unit_lut[b2]));
     if (d.text_mode == 1) v = text_blend(d, v, y, x);
     return v;
 }

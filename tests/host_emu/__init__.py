@@ -30,7 +30,7 @@ def _stale() -> bool:
     if not os.path.isfile(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("crt_math.cuh", "crt_stages.cuh", "crt_derive.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("crt_math.cuh", "crt_stages.cuh", "crt_derive.h", "crt_fused.cuh")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -38,7 +38,8 @@ def lib():
     global _lib
     if _lib is None:
         if _stale():
-            subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", SO, SRC], check=True)
+            subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I/usr/local/cuda/include",
+                            "-o", SO, SRC], check=True)
         _lib = C.CDLL(SO)
         _lib.emu_process.restype = C.c_int
     return _lib
@@ -93,3 +94,26 @@ def run_case(case, variant: str, static: bool = False):
     if rc != 0:
         raise RuntimeError(f"emu_process failed ({rc}): {err.value.decode()}")
     return (img if static else list(out)), state
+
+
+def plan(params: CrtParams, W: int, H: int, variant: str = "export"):
+    """Tile plan the library would choose for the fused kernel: dict(ok, th, cap_px, cap_aux, smem, why)."""
+    L = lib()
+    c, tabs = build_config(params, W, H, variant=variant)
+    ptrs = (C.c_void_p * 8)()
+    sizes = (C.c_size_t * 8)()
+    for k, a in tabs.items():
+        ptrs[k] = a.ctypes.data
+        sizes[k] = a.nbytes
+    ps = int(params.pixel_size)
+    uni = 0
+    if ps > 1:
+        xs, ys = tabs[cabi.TABLE_PIXELATE_X], tabs[cabi.TABLE_PIXELATE_Y]
+        if np.array_equal(xs, ps * (np.arange(W) // ps)) and np.array_equal(ys, ps * (np.arange(H) // ps)):
+            uni = ps
+    out = (C.c_longlong * 5)()
+    why = C.create_string_buffer(256)
+    rc = L.emu_plan(C.byref(c), W, H, ptrs, sizes, uni, out, why, 256)
+    if rc:
+        raise RuntimeError(why.value.decode())
+    return dict(ok=bool(out[0]), th=out[1], cap_px=out[2], cap_aux=out[3], smem=out[4], why=why.value.decode())

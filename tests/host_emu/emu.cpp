@@ -12,6 +12,7 @@
 
 #include "../../pythoncrt_b200/csrc/crt_derive.h"
 #include "../../pythoncrt_b200/csrc/crt_stages.cuh"
+#include "../../pythoncrt_b200/csrc/crt_fused.cuh"   // host-side tile planner only
 
 using namespace crt;
 
@@ -80,5 +81,25 @@ extern "C" int emu_process(const crt_params* p, int W, int H, const void* const*
             else finish_pixel(d, v, has_prev, state, out + (size_t)n * px * 3, y, x);
         }
     }
+    return 0;
+}
+
+// Host-side tile planner of the fused kernel (plan_fused): out = {ok, th, cap_px, cap_aux, smem bytes}
+extern "C" int emu_plan(const crt_params* p, int W, int H, const void* const* tabs, const size_t* tab_bytes, int pix_uniform,
+                        long long* out, char* why, int whylen) {
+    TablePtrs t{};
+    for (int i = 0; i < CRT_TABLE_COUNT; ++i) { t.tab[i] = tabs[i]; t.bytes[i] = tab_bytes[i]; }
+    const int hw = W / 2 > 1 ? W / 2 : 1, hh = H / 2 > 1 ? H / 2 : 1;
+    std::vector<Lerp1> dn_x = linear_coords(hw, W), dn_y = linear_coords(hh, H), up_x = linear_coords(W, hw), up_y = linear_coords(H, hh);
+    std::vector<Lerp1> nz(1);
+    t.dn_x = dn_x.data(); t.dn_y = dn_y.data(); t.up_x = up_x.data(); t.up_y = up_y.data(); t.nz_x = nz.data(); t.nz_y = nz.data();
+    t.pix_uniform = pix_uniform;
+    Dev d{};
+    std::string e;
+    int rc = derive_dev(*p, W, H, t, &d, &e);
+    if (rc) { strncpy(why, e.c_str(), whylen - 1); why[whylen - 1] = 0; return rc; }
+    FusedPlan pl = plan_fused(d, glitch_active(*p));
+    out[0] = pl.ok; out[1] = pl.th; out[2] = pl.cap_px; out[3] = pl.cap_aux; out[4] = (long long)pl.smem;
+    strncpy(why, pl.why, whylen - 1); why[whylen - 1] = 0;
     return 0;
 }

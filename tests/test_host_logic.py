@@ -154,3 +154,21 @@ def test_no_cpu_fallback_without_a_gpu():
     lib = cabi.load_library()
     h = C.c_void_p()
     assert lib.crt_create(0, 64, 48, C.byref(h)) == 3         # CRT_ERR_NO_DEVICE
+
+
+# ------------------------------------------------------------ tile planner --
+def test_fused_tile_planner_on_every_case():
+    """Host-side planner of the fused kernel (csrc/crt_fused.cuh plan_fused): must never touch
+    device memory, must fit shared memory, and must hand glitch / warp+gaussian to the staged path."""
+    import host_emu
+    from oracle.cases import CASES
+    for case in CASES:
+        p = host_emu.oracle_to_product_params(case.params)
+        pl = host_emu.plan(p, case.w, case.h)
+        glitch = p.glitch_amp_px > 0 and p.glitch_height_frac > 0
+        warp_gauss = p.warp_strength != 0 and not p.fast_bloom and p.bloom_strength > 0 and p.bloom_sigma > 0
+        assert pl["ok"] == (not glitch and not warp_gauss), (case.name, pl)
+        if pl["ok"]:
+            assert pl["smem"] <= 200 * 1024 and pl["th"] in (16, 32, 64) and pl["cap_px"] >= min(64, case.w) * min(pl["th"], case.h)
+    big = host_emu.plan(CrtParams(noise_strength=0.0, warp_strength=0.15, scanline_angle=3.0), 3840, 2160)
+    assert big["ok"] and big["smem"] <= 110 * 1024          # BASELINE configs[2] keeps two CTAs per SM
