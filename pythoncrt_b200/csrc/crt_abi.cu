@@ -13,6 +13,7 @@
 #include "crt_derive.h"
 #include "crt_kernels.cuh"
 #include "crt_fused.cuh"
+#include "crt_fused_gauss.cuh"
 
 using namespace crt;
 
@@ -216,7 +217,9 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         int rc;
         if (want_fused) {
             prof_mark(ctx, st, false);
-            rc = run_fused(ctx->plan, d, f, in_i, out_i, state_i, has_prev, st, &launches); fused_used = 1;
+            rc = ctx->plan.gauss_k ? run_fused_gauss(ctx->plan.th, d, f, in_i, out_i, state_i, has_prev, st, &launches)
+                                   : run_fused(ctx->plan, d, f, in_i, out_i, state_i, has_prev, st, &launches);
+            fused_used = 1;
             prof_mark(ctx, st, true);
         }
         else rc = run_staged(ctx, f, in_i, out_i, state_i, has_prev, img_i, st, &launches);

@@ -43,8 +43,17 @@ struct FusedPlan {
     int th = 16;                        // tile height
     int cap_px = 0;                     // capacity of the P-region buffer in pixels
     int cap_aux = 0;                    // floats of the auxiliary buffer (ds cells / row pass / T1 tile)
+    int gauss_k = 0;                    // != 0: the packed-FP32 gaussian kernel (crt_fused_gauss.cuh) with this tap count
     size_t smem = 0;
 };
+
+// Shared-memory footprint / availability of k_fused_gauss<K> (crt_fused_gauss.cuh)
+inline size_t fused_gauss_smem(int K, int th) {
+    const int R = K / 2, PW = FTW + 2 * R, PH = th + 2 * R;
+    return ((size_t)3 * PW * PH + (size_t)3 * PH * FTW + (size_t)th * FTW * 3) * sizeof(float);
+}
+inline bool fused_gauss_supported(int K) { return K == 5 || K == 7 || K == 9 || K == 11 || K == 13 || K == 25; }
+
 
 struct FusedGeom { int th, cap_px, cap_aux; };
 
@@ -135,6 +144,63 @@ __device__ __forceinline__ F3 after_bloom_fast(const Dev& d, const FrameDev& f, 
         v.x = __saturatef(v.x + n); v.y = __saturatef(v.y + n); v.z = __saturatef(v.z + n);
     }
     return v;
+}
+
+// Blend four horizontally adjacent pixels with the persistence state, write state (16-byte
+// stores) and packed uint8 output.  `pixel(y, x, k)` returns the float image value
+// (what apply_static_effects returns) of pixel k of the quad.
+template <typename PixelFn>
+__device__ __forceinline__ void finish_quad(const Dev& d, float* __restrict__ state, uint8_t* __restrict__ out, int has_prev,
+                                            int y, int xb, int npx, PixelFn&& pixel) {
+    const float pp = d.persist, pq = d.persist_q;
+    const bool vec = (d.W & 3) == 0;
+    const int o = (y * d.W + xb) * 3;               // < 2^31 (checked by plan_fused)
+    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa, pc = pa;       // previous state of the 4 pixels
+    if (has_prev) {
+        if (vec) {
+            const float4* sp = reinterpret_cast<const float4*>(state + o);
+            pa = sp[0]; pb = sp[1]; pc = sp[2];
+        } else {
+            float t[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) t[k] = (k < npx * 3) ? state[o + k] : 0.f;
+            pa = make_float4(t[0], t[1], t[2], t[3]); pb = make_float4(t[4], t[5], t[6], t[7]); pc = make_float4(t[8], t[9], t[10], t[11]);
+        }
+    }
+    const float prev[12] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, pc.x, pc.y, pc.z, pc.w};
+    float res[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        F3 v = mk3(0.f, 0.f, 0.f);
+        if (k < npx) {
+            v = pixel(y, xb + k, k);
+            if (d.text_mode == 2) v = text_blend(d, v, y, xb + k);
+            if (has_prev) { v.x = blend(prev[k * 3], v.x, pp, pq); v.y = blend(prev[k * 3 + 1], v.y, pp, pq); v.z = blend(prev[k * 3 + 2], v.z, pp, pq); }
+        }
+        res[k * 3] = v.x; res[k * 3 + 1] = v.y; res[k * 3 + 2] = v.z;
+    }
+    if (vec) {
+        if (state) {
+            float4* sp = reinterpret_cast<float4*>(state + o);
+            sp[0] = make_float4(res[0], res[1], res[2], res[3]);
+            sp[1] = make_float4(res[4], res[5], res[6], res[7]);
+            sp[2] = make_float4(res[8], res[9], res[10], res[11]);
+        }
+        uint32_t w[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            w[j] = (uint32_t)quantise(res[j * 4]) | ((uint32_t)quantise(res[j * 4 + 1]) << 8) | ((uint32_t)quantise(res[j * 4 + 2]) << 16) |
+                   ((uint32_t)quantise(res[j * 4 + 3]) << 24);
+        uint32_t* op = reinterpret_cast<uint32_t*>(out + o);
+        op[0] = w[0]; op[1] = w[1]; op[2] = w[2];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k)
+            if (k < npx * 3) {
+                if (state) state[o + k] = res[k];
+                out[o + k] = quantise(res[k]);
+            }
+    }
 }
 
 template <int BLOOM, bool WARP>
@@ -297,99 +363,58 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
     }
 
     // ---- phase 4: output pixels ---------------------------------------------------------------------
-    const float pp = d.persist, pq = d.persist_q;
-    const bool vec = (d.W & 3) == 0;
     if (xb > ox1) return;
-    for (int y = oy0 + trow; y <= oy1; y += FROWS_PER_PASS) {
-        const int o = (y * d.W + xb) * 3;           // < 2^31 (checked by plan_fused)
-        const int npx = imin(4, ox1 - xb + 1);
-        float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa, pc = pa;       // previous state of the 4 pixels
-        if (has_prev) {
-            if (vec) {
-                const float4* sp = reinterpret_cast<const float4*>(state + o);
-                pa = sp[0]; pb = sp[1]; pc = sp[2];
-            } else {
-                float t[12];
-#pragma unroll
-                for (int k = 0; k < 12; ++k) t[k] = (k < npx * 3) ? state[o + k] : 0.f;
-                pa = make_float4(t[0], t[1], t[2], t[3]); pb = make_float4(t[4], t[5], t[6], t[7]); pc = make_float4(t[8], t[9], t[10], t[11]);
-            }
-        }
-        const float prev[12] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, pc.x, pc.y, pc.z, pc.w};
-        float res[12];
-        float yn = 0.f;
-        if (WARP) yn = warp_norm((float)y, d.warp_cy, d.warp_dy);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int x = xb + k;
-            F3 v = mk3(0.f, 0.f, 0.f);
-            if (k < npx) {
-                if (WARP) {
-                    if (!q_empty) {
-                        const Taps t = warp_taps_n(d, xn[k], yn);
-                        F3 a[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int ty = t.iy + (j >> 1), tx = t.ix + (j & 1);
-                            const bool ok = ty >= 0 && ty < d.H && tx >= 0 && tx < d.W;
-                            const float* qp = T + (((ok ? ty : q.y0) - p.y0) * pw + ((ok ? tx : q.x0) - p.x0)) * 3;
-                            a[j] = ok ? load_f3(qp) : mk3(0.f, 0.f, 0.f);
-                        }
-                        v = mk3(gather4(a[0].x, a[1].x, a[2].x, a[3].x, t), gather4(a[0].y, a[1].y, a[2].y, a[3].y, t),
-                                gather4(a[0].z, a[1].z, a[2].z, a[3].z, t));
-                    }
+    float yn = 0.f;
+    auto pixel = [&](int y, int x, int k) -> F3 {
+        F3 v = mk3(0.f, 0.f, 0.f);
+        if (WARP) {
+            if (!q_empty) {
+                const Taps t = warp_taps_n(d, xn[k], yn);
+                const float* base = T + ((t.iy - p.y0) * pw + (t.ix - p.x0)) * 3;
+                F3 a[4];
+                if (t.ix >= q.x0 && t.ix < q.x1 && t.iy >= q.y0 && t.iy < q.y1) {       // all four taps inside Q (hence inside the image)
+                    a[0] = load_f3(base); a[1] = load_f3(base + 3); a[2] = load_f3(base + pw * 3); a[3] = load_f3(base + pw * 3 + 3);
                 } else {
-                    const float* tp = T + ((y - p.y0) * pw + (x - p.x0)) * 3;
-                    v = (BLOOM == 2 && d.thr_on) ? load_f3(T1 + ((y - oy0) * FTW + (x - ox0)) * 3) : load_f3(tp);
-                    if (BLOOM == 1) v = add_bloom(d, v, bloom_up_at(d, A, dw * 3, cells.y0, cells.x0, y, x));
-                    if (BLOOM == 2) {
-                        const int K = d.ksize, rad = K >> 1, c = x - q.x0;
-                        float bl[3];
 #pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) {
-                            if (y - rad >= p.y0 && y + rad <= p.y1) {
-                                bl[ch] = gauss_col(A + ((y - p.y0) * cw + c) * 3 + ch, cw * 3, d.taps, K);
-                            } else {     // image border: REPLICATE = clamped row index
-                                const float* col = A + c * 3 + ch;
-                                float acc = fmul(col[(y - p.y0) * cw * 3], d.taps[rad]);
-                                for (int i = 1; i <= rad; ++i) {
-                                    const int yu = imin(y + i, d.H - 1) - p.y0, yd = imax(y - i, 0) - p.y0;
-                                    acc = ffma(fadd(col[yu * cw * 3], col[yd * cw * 3]), d.taps[rad + i], acc);
-                                }
-                                bl[ch] = acc;
-                            }
-                        }
-                        v = add_bloom(d, v, mk3(bl[0], bl[1], bl[2]));
+                    for (int j = 0; j < 4; ++j) {
+                        const int ty = t.iy + (j >> 1), tx = t.ix + (j & 1);
+                        const bool ok = ty >= 0 && ty < d.H && tx >= 0 && tx < d.W;
+                        a[j] = ok ? load_f3(T + ((ty - p.y0) * pw + (tx - p.x0)) * 3) : mk3(0.f, 0.f, 0.f);
                     }
-                    v = after_bloom_fast(d, f, v, y, x, s_fwd, s_inv, mt, y - q.y0, x - q.x0);
                 }
-                if (d.text_mode == 2) v = text_blend(d, v, y, x);
-                if (has_prev) { v.x = blend(prev[k * 3], v.x, pp, pq); v.y = blend(prev[k * 3 + 1], v.y, pp, pq); v.z = blend(prev[k * 3 + 2], v.z, pp, pq); }
+                v = mk3(gather4(a[0].x, a[1].x, a[2].x, a[3].x, t), gather4(a[0].y, a[1].y, a[2].y, a[3].y, t),
+                        gather4(a[0].z, a[1].z, a[2].z, a[3].z, t));
             }
-            res[k * 3] = v.x; res[k * 3 + 1] = v.y; res[k * 3 + 2] = v.z;
-        }
-        if (vec) {
-            if (state) {
-                float4* sp = reinterpret_cast<float4*>(state + o);
-                sp[0] = make_float4(res[0], res[1], res[2], res[3]);
-                sp[1] = make_float4(res[4], res[5], res[6], res[7]);
-                sp[2] = make_float4(res[8], res[9], res[10], res[11]);
-            }
-            uint32_t w[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-                w[j] = (uint32_t)quantise(res[j * 4]) | ((uint32_t)quantise(res[j * 4 + 1]) << 8) | ((uint32_t)quantise(res[j * 4 + 2]) << 16) |
-                       ((uint32_t)quantise(res[j * 4 + 3]) << 24);
-            uint32_t* op = reinterpret_cast<uint32_t*>(out + o);
-            op[0] = w[0]; op[1] = w[1]; op[2] = w[2];
         } else {
+            const float* tp = T + ((y - p.y0) * pw + (x - p.x0)) * 3;
+            v = (BLOOM == 2 && d.thr_on) ? load_f3(T1 + ((y - oy0) * FTW + (x - ox0)) * 3) : load_f3(tp);
+            if (BLOOM == 1) v = add_bloom(d, v, bloom_up_at(d, A, dw * 3, cells.y0, cells.x0, y, x));
+            if (BLOOM == 2) {
+                const int K = d.ksize, rad = K >> 1, c = x - q.x0;
+                float bl[3];
 #pragma unroll
-            for (int k = 0; k < 12; ++k)
-                if (k < npx * 3) {
-                    if (state) state[o + k] = res[k];
-                    out[o + k] = quantise(res[k]);
+                for (int ch = 0; ch < 3; ++ch) {
+                    if (y - rad >= p.y0 && y + rad <= p.y1) {
+                        bl[ch] = gauss_col(A + ((y - p.y0) * cw + c) * 3 + ch, cw * 3, d.taps, K);
+                    } else {     // image border: REPLICATE = clamped row index
+                        const float* col = A + c * 3 + ch;
+                        float acc = fmul(col[(y - p.y0) * cw * 3], d.taps[rad]);
+                        for (int i = 1; i <= rad; ++i) {
+                            const int yu = imin(y + i, d.H - 1) - p.y0, yd = imax(y - i, 0) - p.y0;
+                            acc = ffma(fadd(col[yu * cw * 3], col[yd * cw * 3]), d.taps[rad + i], acc);
+                        }
+                        bl[ch] = acc;
+                    }
                 }
+                v = add_bloom(d, v, mk3(bl[0], bl[1], bl[2]));
+            }
+            v = after_bloom_fast(d, f, v, y, x, s_fwd, s_inv, mt, y - q.y0, x - q.x0);
         }
+        return v;
+    };
+    for (int y = oy0 + trow; y <= oy1; y += FROWS_PER_PASS) {
+        if (WARP) yn = warp_norm((float)y, d.warp_cy, d.warp_dy);
+        finish_quad(d, state, out, has_prev, y, xb, imin(4, ox1 - xb + 1), pixel);
     }
 }
 
@@ -407,11 +432,25 @@ inline FusedPlan plan_fused(const Dev& hd, bool glitch_on) {
     if (glitch_on) { pl.why = "glitch gather is handled by the staged kernels"; return pl; }
     if (d.warp_on && d.bloom_mode == 2) { pl.why = "warp + gaussian bloom is handled by the staged kernels"; return pl; }
     if ((size_t)d.W * d.H * 3 >= ((size_t)1 << 31)) { pl.why = "frame too large for 32-bit indexing"; return pl; }
+    // grid sizing: at least two waves of CTAs over the 148 SMs when the frame allows it
+    auto enough_tiles = [&](int th) { return (long long)((d.W + FTW - 1) / FTW) * ((d.H + th - 1) / th) >= 2 * 148; };
+    if (d.bloom_mode == 2 && !d.warp_on && fused_gauss_supported(d.ksize) && d.W >= 4 && d.H >= 4) {
+        FusedPlan cand;
+        for (int th : {32, 16}) {
+            const size_t smem = fused_gauss_smem(d.ksize, th);
+            const bool two_ctas = smem + 14 * 1024 <= 112 * 1024;
+            if (two_ctas || (th == 16 && smem <= 200 * 1024)) {
+                cand.ok = true; cand.why = ""; cand.bloom = 2; cand.th = th; cand.smem = smem; cand.gauss_k = d.ksize;
+                if (enough_tiles(th)) return cand;
+            }
+        }
+        if (cand.ok) return cand;        // smallest tile that fits: most CTAs
+    }
     // warp: per-row / per-column normalised coordinates, as the kernel computes them
     std::vector<float> xn(d.warp_on ? d.W : 0), yn(d.warp_on ? d.H : 0);
     for (int x = 0; x < (int)xn.size(); ++x) xn[x] = warp_norm((float)x, d.warp_cx, d.warp_dx);
     for (int y = 0; y < (int)yn.size(); ++y) yn[y] = warp_norm((float)y, d.warp_cy, d.warp_dy);
-    FusedPlan best;
+    FusedPlan best, small;
     best.why = "tile footprint does not fit in shared memory";
     for (int th : {64, 32, 16}) {
         size_t best_px = 0, best_aux = 0;
@@ -451,9 +490,12 @@ inline FusedPlan plan_fused(const Dev& hd, bool glitch_on) {
         c.ok = true; c.why = ""; c.bloom = d.bloom_mode; c.warp = d.warp_on;
         c.th = th; c.cap_px = (int)best_px; c.cap_aux = (int)best_aux; c.smem = smem;
         if (!best.ok) best = c;                          // tallest tile that fits at all
-        if (smem + 14 * 1024 <= 112 * 1024) return c;    // tallest tile that still allows 2 CTAs per SM
+        if (smem + 14 * 1024 <= 112 * 1024) {            // two CTAs per SM
+            if (enough_tiles(th)) return c;              // tallest such tile that still fills the GPU twice over
+            small = c;
+        }
     }
-    return best;
+    return small.ok ? small : best;
 }
 
 #if defined(__CUDACC__)

@@ -1,0 +1,199 @@
+// crt_fused_gauss.cuh — fused tile kernel for the gaussian-bloom chain without warp
+// (BASELINE.json configs[1]): same single-launch structure as k_fused, with the
+// separable blur written for Blackwell's packed FP32 pipe.
+//
+//   * cv2.GaussianBlur's float32 arithmetic is kept bit for bit (row pass
+//     s = x0*k0; s = fma(x_i, k_i, s); column pass s = c*k0; s = fma(x_+i + x_-i, k_i, s)),
+//     but two outputs are computed per instruction with FMUL2 / FFMA2 / FADD2
+//     (__fmul2_rn, __ffma2_rn, __fadd2_rn: per-component IEEE round-to-nearest, sm_100+).
+//   * The thresholded source is stored TRANSPOSED and planar, St[ch][x][y], so the row
+//     pass reads aligned (y, y+1) pairs with LDS.64 while blocking four outputs along x;
+//     the row-pass result is row-major planar, Rp[ch][y][x], so the column pass reads
+//     aligned (x, x+1) pairs while blocking four outputs along y.  Each pass costs
+//     (K + 3) LDS.64 + 4 K packed FMAs per 8 outputs.
+//   * The REPLICATE border is materialised while filling St (clamped coordinates), so
+//     neither pass has border logic.
+#pragma once
+#include "crt_fused.cuh"
+
+namespace crt {
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+// cv2 row pass for one pair of outputs: in[0..K-1] are the K taps (each a pair of rows)
+template <int K>
+__device__ __forceinline__ float2 gauss_row2(const float2* in, const float* k) {
+    if (K == 3) return __ffma2_rn(in[1], splat2(k[1]), __fmul2_rn(__fadd2_rn(in[0], in[2]), splat2(k[2])));
+    if (K == 5) {
+        const float2 inner = __ffma2_rn(in[2], splat2(k[2]), __fmul2_rn(__fadd2_rn(in[1], in[3]), splat2(k[3])));
+        return __ffma2_rn(__fadd2_rn(in[4], in[0]), splat2(k[4]), inner);
+    }
+    float2 s = __fmul2_rn(in[0], splat2(k[0]));
+#pragma unroll
+    for (int i = 1; i < K; ++i) s = __ffma2_rn(in[i], splat2(k[i]), s);
+    return s;
+}
+// cv2 column pass for one pair of outputs: c points at the centre tap
+template <int K>
+__device__ __forceinline__ float2 gauss_col2(const float2* c, const float* k) {
+    constexpr int R = K / 2;
+    float2 s = __fmul2_rn(c[0], splat2(k[R]));
+#pragma unroll
+    for (int i = 1; i <= R; ++i) s = __ffma2_rn(__fadd2_rn(c[i], c[-i]), splat2(k[R + i]), s);
+    return s;
+}
+
+template <int K>
+__global__ void __launch_bounds__(FT) k_fused_gauss(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                    float* __restrict__ state, int has_prev, int th) {
+    constexpr int R = K / 2, PW = FTW + 2 * R;
+    extern __shared__ __align__(16) float sm[];
+    __shared__ float s_fwd[1025], s_inv[1025];
+    __shared__ float s_unit[256];
+    __shared__ float s_rows[2 * 64], s_cols[2 * FTW];
+    const int PH = th + 2 * R;                      // padded rows; th is even, so PH is even
+    const int pitch = PH;                           // floats between consecutive x in St
+    float* St = sm;                                 // [3][PW][pitch]  thresholded source, transposed
+    float* Rp = St + 3 * PW * pitch;                // [3][PH][FTW]    row-pass result
+    float* T1 = Rp + 3 * PH * FTW;                  // [th][FTW][3]    graded tile (bloom is added to this)
+    float* Bl = St;                                 // [3][th][FTW]    blurred tile (St is dead after the row pass)
+    const int tid = threadIdx.x;
+    const int ox0 = blockIdx.x * FTW, oy0 = blockIdx.y * th;
+    const int ox1 = imin(ox0 + FTW, d.W) - 1, oy1 = imin(oy0 + th, d.H) - 1;
+    const int trow = tid / FROW_THREADS, xb = ox0 + (tid % FROW_THREADS) * 4;
+
+    if (d.triad_mode >= 2)
+        for (int i = tid; i < 1025; i += FT) { s_fwd[i] = d.lut_fwd[i]; s_inv[i] = d.lut_inv[i]; }
+    s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
+    float taps[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) taps[i] = d.taps[i];
+    __syncthreads();
+    MaskTabs mt{s_rows, s_cols, s_rows + 64, s_cols + FTW};
+
+    // ---- phase 1: graded input over the in-image part of tile + halo; REPLICATE border materialised ----
+    const int px0 = ox0 - R, py0 = oy0 - R;                         // padded origin (may be negative)
+    const int PWe = ox1 - ox0 + 1 + 2 * R, PHe = oy1 - oy0 + 1 + 2 * R;
+    const int ix0 = imax(px0, 0), ix1 = imin(ox1 + R, d.W - 1), iy0 = imax(py0, 0), iy1 = imin(oy1 + R, d.H - 1);
+    {
+        const int ps = (d.pix_uniform > 1 && d.text_mode != 1) ? d.pix_uniform : 1;
+        const int ux0 = ix0 / ps, uy0 = iy0 / ps;
+        const int nux = ix1 / ps - ux0 + 1, nuy = iy1 / ps - uy0 + 1;
+        const unsigned magic = make_magic(nux);
+        for (int u = tid; u < nux * nuy; u += FT) {
+            const int uy = fastdiv(u, magic), ux = u - uy * nux;
+            const int xa = imax((ux0 + ux) * ps, ix0), xe = imin((ux0 + ux) * ps + ps - 1, ix1);
+            const int ya = imax((uy0 + uy) * ps, iy0), ye = imin((uy0 + uy) * ps + ps - 1, iy1);
+            const F3 v1 = graded_input_lut(d, in, ya, xa, s_unit);
+            const F3 v = bloom_src(d, v1);
+            // padded positions that replicate this block (image borders extend outwards)
+            const int xx0 = (xa == 0) ? 0 : xa - px0, xx1 = (xe == d.W - 1) ? PWe - 1 : xe - px0;
+            const int yy0 = (ya == 0) ? 0 : ya - py0, yy1 = (ye == d.H - 1) ? PHe - 1 : ye - py0;
+            for (int xx = xx0; xx <= xx1; ++xx) {
+                float* c0 = St + xx * pitch;
+                for (int yy = yy0; yy <= yy1; ++yy) { c0[yy] = v.x; c0[PW * pitch + yy] = v.y; c0[2 * PW * pitch + yy] = v.z; }
+            }
+            for (int y = imax(ya, oy0); y <= imin(ye, oy1); ++y)
+                for (int x = imax(xa, ox0); x <= imin(xe, ox1); ++x) store_f3(T1 + ((y - oy0) * FTW + (x - ox0)) * 3, v1);
+        }
+        for (int r = tid; r <= oy1 - oy0; r += FT) {
+            const int y = oy0 + r;
+            if (d.scan_mode == 1) mt.row_scan[r] = scan_row(d, f, y);
+            else if (d.scan_mode == 2) { double t = ((double)y + f.phase) * d.scan_inv_period; mt.row_scan[r] = (float)(t - floor(t)); }
+            if (d.vig_mode == 1) { const float ny = ((float)y - d.vig_cy) * d.vig_iry; mt.row_vig[r] = ny * ny; }
+        }
+        for (int c = tid; c <= ox1 - ox0; c += FT) {
+            const int x = ox0 + c;
+            if (d.scan_mode == 2) { double t = (d.scan_tan * (double)x) * d.scan_inv_period; mt.col_scan[c] = (float)(t - floor(t)); }
+            if (d.vig_mode == 1) { const float nx = ((float)x - d.vig_cx) * d.vig_irx; mt.col_vig[c] = nx * nx; }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2a: row pass, 4 outputs along x for a pair of rows per task ------------------------------
+    {
+        const int nyp = PH >> 1;
+        const unsigned magic = make_magic(nyp);
+        const int hp = pitch >> 1;                                  // float2 stride between consecutive x
+        for (int u = tid; u < 3 * (FTW / 4) * nyp; u += FT) {
+            const int t = fastdiv(u, magic), yp = u - t * nyp;
+            const int xblk = t & (FTW / 4 - 1), ch = t >> 4;        // FTW / 4 == 16
+            const float2* src = reinterpret_cast<const float2*>(St + (ch * PW + xblk * 4) * pitch) + yp;
+            float2 v[K + 3];
+#pragma unroll
+            for (int i = 0; i < K + 3; ++i) v[i] = src[i * hp];
+            float* o0 = Rp + (ch * PH + 2 * yp) * FTW + xblk * 4;
+            float2 r0 = gauss_row2<K>(v + 0, taps), r1 = gauss_row2<K>(v + 1, taps), r2 = gauss_row2<K>(v + 2, taps), r3 = gauss_row2<K>(v + 3, taps);
+            *reinterpret_cast<float4*>(o0) = make_float4(r0.x, r1.x, r2.x, r3.x);
+            *reinterpret_cast<float4*>(o0 + FTW) = make_float4(r0.y, r1.y, r2.y, r3.y);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2b: column pass, 4 outputs along y for a pair of columns per task ----------------------------
+    {
+        const int nyb = th >> 2;
+        const unsigned magic = make_magic(nyb);
+        for (int u = tid; u < 3 * nyb * (FTW / 2); u += FT) {
+            const int xp = u & (FTW / 2 - 1), t = u >> 5;           // FTW / 2 == 32
+            const int ch = fastdiv(t, magic), yblk = t - ch * nyb;
+            const float2* src = reinterpret_cast<const float2*>(Rp + (ch * PH + yblk * 4) * FTW) + xp;
+            float2 v[K + 3];
+#pragma unroll
+            for (int i = 0; i < K + 3; ++i) v[i] = src[i * (FTW / 2)];
+            float2* o0 = reinterpret_cast<float2*>(Bl + (ch * th + yblk * 4) * FTW) + xp;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o0[j * (FTW / 2)] = gauss_col2<K>(v + R + j, taps);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 4: output pixels ---------------------------------------------------------------------------------
+    if (xb > ox1) return;
+    auto pixel = [&](int y, int x, int k) -> F3 {
+        const int ly = y - oy0, lx = x - ox0;
+        F3 v = load_f3(T1 + (ly * FTW + lx) * 3);
+        const float* b = Bl + ly * FTW + lx;
+        v = add_bloom(d, v, mk3(b[0], b[th * FTW], b[2 * th * FTW]));
+        return after_bloom_fast(d, f, v, y, x, s_fwd, s_inv, mt, ly, lx);
+    };
+    for (int y = oy0 + trow; y <= oy1; y += FROWS_PER_PASS) finish_quad(d, state, out, has_prev, y, xb, imin(4, ox1 - xb + 1), pixel);
+}
+
+template <int K>
+inline int launch_fused_gauss_t(int th, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, int has_prev,
+                                cudaStream_t st) {
+    static size_t configured[64] = {};
+    const size_t smem = fused_gauss_smem(K, th);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
+        if (cudaFuncSetAttribute(k_fused_gauss<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+        configured[dev & 63] = smem;
+    }
+    dim3 grid((d.W + FTW - 1) / FTW, (d.H + th - 1) / th);
+    k_fused_gauss<K><<<grid, FT, smem, st>>>(d, f, in, out, state, has_prev, th);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
+inline int run_fused_gauss(int th, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, int has_prev,
+                           cudaStream_t st, int* launches) {
+    int rc = 4;
+    switch (d.ksize) {
+        case 5: rc = launch_fused_gauss_t<5>(th, d, f, in, out, state, has_prev, st); break;
+        case 7: rc = launch_fused_gauss_t<7>(th, d, f, in, out, state, has_prev, st); break;
+        case 9: rc = launch_fused_gauss_t<9>(th, d, f, in, out, state, has_prev, st); break;
+        case 11: rc = launch_fused_gauss_t<11>(th, d, f, in, out, state, has_prev, st); break;
+        case 13: rc = launch_fused_gauss_t<13>(th, d, f, in, out, state, has_prev, st); break;
+        case 25: rc = launch_fused_gauss_t<25>(th, d, f, in, out, state, has_prev, st); break;
+        default: break;
+    }
+    ++*launches;
+    return rc;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace crt
