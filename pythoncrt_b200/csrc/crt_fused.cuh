@@ -106,6 +106,15 @@ __device__ __forceinline__ F3 load_f3(const float* p) { return mk3(p[0], p[1], p
 __device__ __forceinline__ int fastdiv(int n, unsigned magic) { return magic ? (int)__umulhi((unsigned)n, magic) : n; }
 __device__ __forceinline__ unsigned make_magic(int dv) { return dv <= 1 ? 0u : 0xffffffffu / (unsigned)dv + 1u; }   // 0 = divide by 1
 
+// After the triad LUT only the final +-1 LSB matters: these use fused multiply-adds where the
+// reference's float64 / OpenCV code uses separate operations.
+__device__ __forceinline__ float gather4_fast(float a, float b, float c, float e, const Taps& t) {
+    return __fmaf_rn(e, t.w11, __fmaf_rn(c, t.w10, __fmaf_rn(b, t.w01, a * t.w00)));
+}
+__device__ __forceinline__ float blend_fast(float prev, float v, float p, float q) { return __saturatef(__fmaf_rn(p, prev, q * v)); }
+// values are already clipped to [0, 1] (or exceed 1 by an ulp after the gather): |.| and the upper clamp are no-ops
+__device__ __forceinline__ uint32_t quantise_fast(float v) { return (uint32_t)__float2int_rn(fminf(v * 255.0f, 255.0f)); }
+
 // Per-tile tables for the masks applied after the triad LUT.
 struct MaskTabs {
     float* row_scan;    // scan_mode 1: row mask;  scan_mode 2: phase fraction of the row
@@ -121,11 +130,11 @@ __device__ __forceinline__ float mask_at(const Dev& d, const MaskTabs& m, int r,
     else if (d.scan_mode == 2) {
         float t = m.row_scan[r] + m.col_scan[c];
         t = t >= 1.0f ? t - 1.0f : t;                                  // turns in [0, 1)
-        float s = fmaxf(0.5f - 0.5f * __sinf(6.283185307f * (t - 0.5f)), 0.0f);   // 0.5 (1 + sin(2 pi t))
+        float s = fmaxf(__fmaf_rn(-0.5f, __sinf(__fmaf_rn(6.283185307f, t, -3.14159265f)), 0.5f), 0.0f);   // 0.5 (1 + sin(2 pi t))
         float shaped = (d.scan_inv_sharp == 1.0f) ? s : __powf(s, d.scan_inv_sharp);
-        mk = 1.0f - d.scan_strength * shaped;
+        mk = __fmaf_rn(-d.scan_strength, shaped, 1.0f);
     }
-    if (d.vig_mode == 1) mk *= 1.0f - d.vig_strength * __saturatef(m.row_vig[r] + m.col_vig[c]);
+    if (d.vig_mode == 1) mk *= __fmaf_rn(-d.vig_strength, __saturatef(m.row_vig[r] + m.col_vig[c]), 1.0f);
     else if (d.vig_mode == 2) mk *= d.vig_plane[(size_t)y * d.W + x];
     return mk;
 }
@@ -175,7 +184,7 @@ __device__ __forceinline__ void finish_quad(const Dev& d, float* __restrict__ st
         if (k < npx) {
             v = pixel(y, xb + k, k);
             if (d.text_mode == 2) v = text_blend(d, v, y, xb + k);
-            if (has_prev) { v.x = blend(prev[k * 3], v.x, pp, pq); v.y = blend(prev[k * 3 + 1], v.y, pp, pq); v.z = blend(prev[k * 3 + 2], v.z, pp, pq); }
+            if (has_prev) { v.x = blend_fast(prev[k * 3], v.x, pp, pq); v.y = blend_fast(prev[k * 3 + 1], v.y, pp, pq); v.z = blend_fast(prev[k * 3 + 2], v.z, pp, pq); }
         }
         res[k * 3] = v.x; res[k * 3 + 1] = v.y; res[k * 3 + 2] = v.z;
     }
@@ -189,8 +198,8 @@ __device__ __forceinline__ void finish_quad(const Dev& d, float* __restrict__ st
         uint32_t w[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j)
-            w[j] = (uint32_t)quantise(res[j * 4]) | ((uint32_t)quantise(res[j * 4 + 1]) << 8) | ((uint32_t)quantise(res[j * 4 + 2]) << 16) |
-                   ((uint32_t)quantise(res[j * 4 + 3]) << 24);
+            w[j] = quantise_fast(res[j * 4]) | (quantise_fast(res[j * 4 + 1]) << 8) | (quantise_fast(res[j * 4 + 2]) << 16) |
+                   (quantise_fast(res[j * 4 + 3]) << 24);
         uint32_t* op = reinterpret_cast<uint32_t*>(out + o);
         op[0] = w[0]; op[1] = w[1]; op[2] = w[2];
     } else {
@@ -210,6 +219,8 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
     __shared__ float s_fwd[1025], s_inv[1025];
     __shared__ float s_unit[256];
     __shared__ float s_rows[2 * FMAX_ROWS], s_cols[2 * FMAX_COLS];
+    __shared__ int s_ci[2 * FMAX_COLS], s_ri[2 * FMAX_ROWS];       // fast bloom: up-scale tap offsets per Q column / row
+    __shared__ float s_cw[FMAX_COLS], s_rw[FMAX_ROWS];              // ... and weights (cv2.resize coordinates)
     __shared__ int s_box[4];
     float* T = sm;                                  // [ph][pw][3] graded input (bloom source when thresholded)
     float* A = sm + g.cap_px * 3;                   // auxiliary: ds cells | row pass (+ T1 tile)
@@ -277,7 +288,7 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
             const int uy = fastdiv(u, magic), ux = u - uy * nux;
             const int xa = imax((ux0 + ux) * ps, p.x0), xe = imin((ux0 + ux) * ps + ps - 1, p.x1);
             const int ya = imax((uy0 + uy) * ps, p.y0), ye = imin((uy0 + uy) * ps + ps - 1, p.y1);
-            const F3 v1 = graded_input_lut(d, in, ya, xa, s_unit);
+            const F3 v1 = ps > 1 ? graded_source_lut(d, in, (uy0 + uy) * ps, (ux0 + ux) * ps, ya, xa, s_unit) : graded_input_lut(d, in, ya, xa, s_unit);
             const F3 v = (BLOOM == 2 && d.thr_on) ? bloom_src(d, v1) : v1;
             for (int y = ya; y <= ye; ++y)
                 for (int x = xa; x <= xe; ++x) {
@@ -298,11 +309,29 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
             if (d.scan_mode == 2) { double t = (d.scan_tan * (double)x) * d.scan_inv_period; mt.col_scan[c] = (float)(t - floor(t)); }
             if (d.vig_mode == 1) { const float nx = ((float)x - d.vig_cx) * d.vig_irx; mt.col_vig[c] = nx * nx; }
         }
+        if (BLOOM == 1) {
+            for (int c = tid; c < qw; c += FT) {
+                const Lerp1 cx = up_coord(d, d.up_x, q.x0 + c, d.hw);
+                s_ci[c] = (cx.s0 - cells.x0) * 3; s_ci[FMAX_COLS + c] = (cx.s1 - cells.x0) * 3; s_cw[c] = cx.w;
+            }
+            for (int r = tid; r < qh; r += FT) {
+                const Lerp1 cy = up_coord(d, d.up_y, q.y0 + r, d.hh);
+                s_ri[r] = (cy.s0 - cells.y0) * qw * 3; s_ri[FMAX_ROWS + r] = (cy.s1 - cells.y0) * qw * 3; s_rw[r] = cy.w;
+            }
+        }
     }
     __syncthreads();
 
     // ---- phase 2: bloom in shared memory -------------------------------------------------------
     const int dw = box_w(cells), dh = box_h(cells);
+    float* HP = A + dw * dh * 3;                    // [dh][qw][3] fast bloom: cells up-scaled along x
+    // vertical half of the up-scale at Q pixel (r, c)
+    auto bloom_fast_at = [&](int r, int c) -> F3 {
+        const float* h0 = HP + s_ri[r] + c * 3;
+        const float* h1 = HP + s_ri[FMAX_ROWS + r] + c * 3;
+        const float w = s_rw[r];
+        return mk3(lerp_cv(h0[0], h1[0], w), lerp_cv(h0[1], h1[1], w), lerp_cv(h0[2], h1[2], w));
+    };
     if (BLOOM == 1 && !q_empty) {
         const unsigned magic = make_magic(dw);
         for (int u = tid; u < dw * dh; u += FT) {
@@ -317,6 +346,17 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
             o[0] = lerp_cv(lerp_cv(a.x, b.x, cx.w), lerp_cv(cc.x, e.x, cx.w), cy.w);
             o[1] = lerp_cv(lerp_cv(a.y, b.y, cx.w), lerp_cv(cc.y, e.y, cx.w), cy.w);
             o[2] = lerp_cv(lerp_cv(a.z, b.z, cx.w), lerp_cv(cc.z, e.z, cx.w), cy.w);
+        }
+        __syncthreads();
+        // horizontal half of the 2x up-scale (cv2.resize works rows first), once per (cell row, Q column)
+        const unsigned magic_q = make_magic(qw);
+        for (int u = tid; u < dh * qw; u += FT) {
+            const int j = fastdiv(u, magic_q), c = u - j * qw;
+            const float* dr = A + j * dw * 3;
+            const int a0 = s_ci[c], a1 = s_ci[FMAX_COLS + c];
+            const float w = s_cw[c];
+            float* o = HP + u * 3;
+            o[0] = lerp_cv(dr[a0], dr[a1], w); o[1] = lerp_cv(dr[a0 + 1], dr[a1 + 1], w); o[2] = lerp_cv(dr[a0 + 2], dr[a1 + 2], w);
         }
         __syncthreads();
     }
@@ -355,7 +395,7 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
             const int y = q.y0 + r, x = q.x0 + c;
             float* tp = T + ((y - p.y0) * pw + (x - p.x0)) * 3;
             F3 v = load_f3(tp);
-            if (BLOOM == 1) v = add_bloom(d, v, bloom_up_at(d, A, dw * 3, cells.y0, cells.x0, y, x));
+            if (BLOOM == 1) v = add_bloom(d, v, bloom_fast_at(r, c));
             v = after_bloom_fast(d, f, v, y, x, s_fwd, s_inv, mt, r, c);
             store_f3(tp, v);
         }
@@ -382,13 +422,13 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
                         a[j] = ok ? load_f3(T + ((ty - p.y0) * pw + (tx - p.x0)) * 3) : mk3(0.f, 0.f, 0.f);
                     }
                 }
-                v = mk3(gather4(a[0].x, a[1].x, a[2].x, a[3].x, t), gather4(a[0].y, a[1].y, a[2].y, a[3].y, t),
-                        gather4(a[0].z, a[1].z, a[2].z, a[3].z, t));
+                v = mk3(gather4_fast(a[0].x, a[1].x, a[2].x, a[3].x, t), gather4_fast(a[0].y, a[1].y, a[2].y, a[3].y, t),
+                        gather4_fast(a[0].z, a[1].z, a[2].z, a[3].z, t));
             }
         } else {
             const float* tp = T + ((y - p.y0) * pw + (x - p.x0)) * 3;
             v = (BLOOM == 2 && d.thr_on) ? load_f3(T1 + ((y - oy0) * FTW + (x - ox0)) * 3) : load_f3(tp);
-            if (BLOOM == 1) v = add_bloom(d, v, bloom_up_at(d, A, dw * 3, cells.y0, cells.x0, y, x));
+            if (BLOOM == 1) v = add_bloom(d, v, bloom_fast_at(y - q.y0, x - q.x0));
             if (BLOOM == 2) {
                 const int K = d.ksize, rad = K >> 1, c = x - q.x0;
                 float bl[3];
@@ -438,7 +478,7 @@ inline FusedPlan plan_fused(const Dev& hd, bool glitch_on) {
         FusedPlan cand;
         for (int th : {32, 16}) {
             const size_t smem = fused_gauss_smem(d.ksize, th);
-            const bool two_ctas = smem + 14 * 1024 <= 112 * 1024;
+            const bool two_ctas = smem + 12 * 1024 <= 113 * 1024;   // + static shared memory and the per-CTA reserve
             if (two_ctas || (th == 16 && smem <= 200 * 1024)) {
                 cand.ok = true; cand.why = ""; cand.bloom = 2; cand.th = th; cand.smem = smem; cand.gauss_k = d.ksize;
                 if (enough_tiles(th)) return cand;
@@ -476,7 +516,7 @@ inline FusedPlan plan_fused(const Dev& hd, bool glitch_on) {
                 Box p = grow_for_bloom(d, q, &cells);
                 size_t px = (size_t)box_w(p) * box_h(p);
                 size_t aux = 0;
-                if (d.bloom_mode == 1) aux = (size_t)box_w(cells) * box_h(cells) * 3;
+                if (d.bloom_mode == 1) aux = ((size_t)box_w(cells) + box_w(q)) * box_h(cells) * 3;   // ds cells + x-up-scaled cells
                 if (d.bloom_mode == 2) aux = (size_t)box_h(p) * box_w(q) * 3 + (d.thr_on ? (size_t)th * FTW * 3 : 0);
                 if (px > best_px) best_px = px;
                 if (aux > best_aux) best_aux = aux;
@@ -490,7 +530,7 @@ inline FusedPlan plan_fused(const Dev& hd, bool glitch_on) {
         c.ok = true; c.why = ""; c.bloom = d.bloom_mode; c.warp = d.warp_on;
         c.th = th; c.cap_px = (int)best_px; c.cap_aux = (int)best_aux; c.smem = smem;
         if (!best.ok) best = c;                          // tallest tile that fits at all
-        if (smem + 14 * 1024 <= 112 * 1024) {            // two CTAs per SM
+        if (smem + 20 * 1024 <= 113 * 1024) {            // two CTAs per SM (+ ~19 KB static shared memory and reserve)
             if (enough_tiles(th)) return c;              // tallest such tile that still fills the GPU twice over
             small = c;
         }

@@ -45,8 +45,8 @@ __device__ __forceinline__ float2 gauss_col2(const float2* c, const float* k) {
     return s;
 }
 
-template <int K>
-__global__ void __launch_bounds__(FT) k_fused_gauss(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+template <int K, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                     float* __restrict__ state, int has_prev, int th) {
     constexpr int R = K / 2, PW = FTW + 2 * R;
     extern __shared__ __align__(16) float sm[];
@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(FT) k_fused_gauss(Dev d, FrameDev f, const uin
     const int trow = tid / FROW_THREADS, xb = ox0 + (tid % FROW_THREADS) * 4;
 
     if (d.triad_mode >= 2)
-        for (int i = tid; i < 1025; i += FT) { s_fwd[i] = d.lut_fwd[i]; s_inv[i] = d.lut_inv[i]; }
-    s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
+        for (int i = tid; i < 1025; i += NT) { s_fwd[i] = d.lut_fwd[i]; s_inv[i] = d.lut_inv[i]; }
+    if (tid < 256) s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
     float taps[K];
 #pragma unroll
     for (int i = 0; i < K; ++i) taps[i] = d.taps[i];
@@ -82,11 +82,11 @@ __global__ void __launch_bounds__(FT) k_fused_gauss(Dev d, FrameDev f, const uin
         const int ux0 = ix0 / ps, uy0 = iy0 / ps;
         const int nux = ix1 / ps - ux0 + 1, nuy = iy1 / ps - uy0 + 1;
         const unsigned magic = make_magic(nux);
-        for (int u = tid; u < nux * nuy; u += FT) {
+        for (int u = tid; u < nux * nuy; u += NT) {
             const int uy = fastdiv(u, magic), ux = u - uy * nux;
             const int xa = imax((ux0 + ux) * ps, ix0), xe = imin((ux0 + ux) * ps + ps - 1, ix1);
             const int ya = imax((uy0 + uy) * ps, iy0), ye = imin((uy0 + uy) * ps + ps - 1, iy1);
-            const F3 v1 = graded_input_lut(d, in, ya, xa, s_unit);
+            const F3 v1 = ps > 1 ? graded_source_lut(d, in, (uy0 + uy) * ps, (ux0 + ux) * ps, ya, xa, s_unit) : graded_input_lut(d, in, ya, xa, s_unit);
             const F3 v = bloom_src(d, v1);
             // padded positions that replicate this block (image borders extend outwards)
             const int xx0 = (xa == 0) ? 0 : xa - px0, xx1 = (xe == d.W - 1) ? PWe - 1 : xe - px0;
@@ -98,13 +98,13 @@ __global__ void __launch_bounds__(FT) k_fused_gauss(Dev d, FrameDev f, const uin
             for (int y = imax(ya, oy0); y <= imin(ye, oy1); ++y)
                 for (int x = imax(xa, ox0); x <= imin(xe, ox1); ++x) store_f3(T1 + ((y - oy0) * FTW + (x - ox0)) * 3, v1);
         }
-        for (int r = tid; r <= oy1 - oy0; r += FT) {
+        for (int r = tid; r <= oy1 - oy0; r += NT) {
             const int y = oy0 + r;
             if (d.scan_mode == 1) mt.row_scan[r] = scan_row(d, f, y);
             else if (d.scan_mode == 2) { double t = ((double)y + f.phase) * d.scan_inv_period; mt.row_scan[r] = (float)(t - floor(t)); }
             if (d.vig_mode == 1) { const float ny = ((float)y - d.vig_cy) * d.vig_iry; mt.row_vig[r] = ny * ny; }
         }
-        for (int c = tid; c <= ox1 - ox0; c += FT) {
+        for (int c = tid; c <= ox1 - ox0; c += NT) {
             const int x = ox0 + c;
             if (d.scan_mode == 2) { double t = (d.scan_tan * (double)x) * d.scan_inv_period; mt.col_scan[c] = (float)(t - floor(t)); }
             if (d.vig_mode == 1) { const float nx = ((float)x - d.vig_cx) * d.vig_irx; mt.col_vig[c] = nx * nx; }
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(FT) k_fused_gauss(Dev d, FrameDev f, const uin
         const int nyp = PH >> 1;
         const unsigned magic = make_magic(nyp);
         const int hp = pitch >> 1;                                  // float2 stride between consecutive x
-        for (int u = tid; u < 3 * (FTW / 4) * nyp; u += FT) {
+        for (int u = tid; u < 3 * (FTW / 4) * nyp; u += NT) {
             const int t = fastdiv(u, magic), yp = u - t * nyp;
             const int xblk = t & (FTW / 4 - 1), ch = t >> 4;        // FTW / 4 == 16
             const float2* src = reinterpret_cast<const float2*>(St + (ch * PW + xblk * 4) * pitch) + yp;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(FT) k_fused_gauss(Dev d, FrameDev f, const uin
     {
         const int nyb = th >> 2;
         const unsigned magic = make_magic(nyb);
-        for (int u = tid; u < 3 * nyb * (FTW / 2); u += FT) {
+        for (int u = tid; u < 3 * nyb * (FTW / 2); u += NT) {
             const int xp = u & (FTW / 2 - 1), t = u >> 5;           // FTW / 2 == 32
             const int ch = fastdiv(t, magic), yblk = t - ch * nyb;
             const float2* src = reinterpret_cast<const float2*>(Rp + (ch * PH + yblk * 4) * FTW) + xp;
@@ -159,8 +159,10 @@ __global__ void __launch_bounds__(FT) k_fused_gauss(Dev d, FrameDev f, const uin
         v = add_bloom(d, v, mk3(b[0], b[th * FTW], b[2 * th * FTW]));
         return after_bloom_fast(d, f, v, y, x, s_fwd, s_inv, mt, ly, lx);
     };
-    for (int y = oy0 + trow; y <= oy1; y += FROWS_PER_PASS) finish_quad(d, state, out, has_prev, y, xb, imin(4, ox1 - xb + 1), pixel);
+    for (int y = oy0 + trow; y <= oy1; y += NT / FROW_THREADS) finish_quad(d, state, out, has_prev, y, xb, imin(4, ox1 - xb + 1), pixel);
 }
+
+constexpr int GAUSS_NT = 512;           // 16 warps per CTA: two CTAs per SM give 32 resident warps
 
 template <int K>
 inline int launch_fused_gauss_t(int th, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, int has_prev,
@@ -170,11 +172,11 @@ inline int launch_fused_gauss_t(int th, const Dev& d, const FrameDev& f, const u
     int dev = 0;
     cudaGetDevice(&dev);
     if (smem > configured[dev & 63]) {
-        if (cudaFuncSetAttribute(k_fused_gauss<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+        if (cudaFuncSetAttribute(k_fused_gauss<K, GAUSS_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
         configured[dev & 63] = smem;
     }
     dim3 grid((d.W + FTW - 1) / FTW, (d.H + th - 1) / th);
-    k_fused_gauss<K><<<grid, FT, smem, st>>>(d, f, in, out, state, has_prev, th);
+    k_fused_gauss<K, GAUSS_NT><<<grid, GAUSS_NT, smem, st>>>(d, f, in, out, state, has_prev, th);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 

@@ -223,6 +223,17 @@ CRT_HD F3 graded_input_lut(const Dev& d, const uint8_t* __restrict__ in, int y, 
     return v;
 }
 
+// Same for a pixel whose pixelate source (sy, sx) is already known (regular pixelate tables:
+// the block origin), skipping the index-table loads.
+CRT_HD F3 graded_source_lut(const Dev& d, const uint8_t* __restrict__ in, int sy, int sx, int y, int x, const float* __restrict__ unit_lut) {
+    const uint8_t* row = in + (size_t)sy * d.W * 3;
+    int x0 = sx, x2 = sx;
+    if (d.aberr != 0) { x0 = wrap(sx - d.aberr_mod, d.W); x2 = wrap(sx + d.aberr_mod, d.W); }
+    F3 v = colour(d, mk3(unit_lut[row[x0 * 3 + 0]], unit_lut[row[sx * 3 + 1]], unit_lut[row[x2 * 3 + 2]]));
+    if (d.text_mode == 1) v = text_blend(d, v, y, x);
+    return v;
+}
+
 // Bloom source: clip((img - thr) / max(1e-6, 1 - thr)) (:602-604)
 CRT_HD float bloom_src1(const Dev& d, float v) { return d.thr_on ? sat(fdiv(fsub(v, d.thr), d.thr_den)) : v; }
 CRT_HD F3 bloom_src(const Dev& d, F3 v) { return mk3(bloom_src1(d, v.x), bloom_src1(d, v.y), bloom_src1(d, v.z)); }
