@@ -40,6 +40,8 @@ struct crt_ctx {
     void* tab[CRT_TABLE_COUNT] = {};
     size_t tab_bytes[CRT_TABLE_COUNT] = {};
     std::vector<int32_t> h_pix_x, h_pix_y;                 // host copies (tile planning, pix_uniform)
+    std::vector<float> h_cols, h_fwd, h_inv;               // host copies of the triad tables (composite LUT)
+    float* comp_lut = nullptr;                             // device [2][1028] (16-byte aligned tables of 1025)
     std::vector<Lerp1> h_dn_x, h_dn_y, h_up_x, h_up_y;     // host copies of the fast-bloom coordinate tables
     Lerp1 *dn_x = nullptr, *dn_y = nullptr, *up_x = nullptr, *up_y = nullptr, *nz_x = nullptr, *nz_y = nullptr;
     int nz_grain = 0;
@@ -103,6 +105,19 @@ int build_dev(crt_ctx* ctx) {
     std::string err;
     int rc = derive_dev(p, ctx->W, ctx->H, t, &ctx->dev, &err);
     if (rc) return fail(ctx, rc, err);
+    // composite triad tables for the fused kernels
+    ctx->dev.triad_comp = nullptr;
+    if (ctx->dev.triad_mode == 2 && (int)ctx->h_cols.size() == ctx->W * 3 && ctx->h_fwd.size() == 1025 && ctx->h_inv.size() == 1025) {
+        std::vector<float> comp;
+        int x0 = 0, x1 = -1;
+        if (build_triad_comp(ctx->h_cols.data(), ctx->W, ctx->h_fwd.data(), ctx->h_inv.data(), &comp, &x0, &x1)) {
+            // device layout [2][1028] so that both tables start on a 16-byte boundary
+            if (!ctx->comp_lut) CU(cudaMalloc((void**)&ctx->comp_lut, 2 * 1028 * sizeof(float)));
+            CU(cudaMemcpy(ctx->comp_lut, comp.data(), 1025 * sizeof(float), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(ctx->comp_lut + 1028, comp.data() + 1025, 1025 * sizeof(float), cudaMemcpyHostToDevice));
+            ctx->dev.triad_comp = ctx->comp_lut; ctx->dev.comp_x0 = x0; ctx->dev.comp_x1 = x1;
+        }
+    }
     ctx->dev_ok = true;
     Dev hd = ctx->dev;                                   // same block with HOST coordinate tables, for planning
     hd.dn_x = ctx->h_dn_x.data(); hd.dn_y = ctx->h_dn_y.data(); hd.up_x = ctx->h_up_x.data(); hd.up_y = ctx->h_up_y.data();
@@ -217,7 +232,7 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         int rc;
         if (want_fused) {
             prof_mark(ctx, st, false);
-            rc = ctx->plan.gauss_k ? run_fused_gauss(ctx->plan.th, d, f, in_i, out_i, state_i, has_prev, st, &launches)
+            rc = ctx->plan.gauss_k ? run_fused_gauss(ctx->plan.th, ctx->plan.nt, d, f, in_i, out_i, state_i, has_prev, st, &launches)
                                    : run_fused(ctx->plan, d, f, in_i, out_i, state_i, has_prev, st, &launches);
             fused_used = 1;
             prof_mark(ctx, st, true);
@@ -272,6 +287,7 @@ int crt_destroy(crt_ctx* ctx) {
     if (ctx->noise_buf) cudaFree(ctx->noise_buf);
     if (ctx->glitch_buf) cudaFree(ctx->glitch_buf);
     if (ctx->state) cudaFree(ctx->state);
+    if (ctx->comp_lut) cudaFree(ctx->comp_lut);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     HostRing& r = ctx->ring;
     for (int s = 0; s < HostRing::SLOTS; ++s) {
@@ -311,6 +327,9 @@ int crt_set_table(crt_ctx* ctx, int table, const void* h_data, size_t bytes) {
     if (!ctx->tab[table]) CU(cudaMalloc(&ctx->tab[table], bytes));
     CU(cudaMemcpy(ctx->tab[table], h_data, bytes, cudaMemcpyHostToDevice));
     ctx->tab_bytes[table] = bytes;
+    if (table == CRT_TABLE_TRIAD_COLS) ctx->h_cols.assign((const float*)h_data, (const float*)h_data + bytes / 4);
+    if (table == CRT_TABLE_LUT_FWD) ctx->h_fwd.assign((const float*)h_data, (const float*)h_data + bytes / 4);
+    if (table == CRT_TABLE_LUT_INV) ctx->h_inv.assign((const float*)h_data, (const float*)h_data + bytes / 4);
     if (table == CRT_TABLE_PIXELATE_X) ctx->h_pix_x.assign((const int32_t*)h_data, (const int32_t*)h_data + bytes / 4);
     if (table == CRT_TABLE_PIXELATE_Y) ctx->h_pix_y.assign((const int32_t*)h_data, (const int32_t*)h_data + bytes / 4);
     ctx->dev_ok = false;

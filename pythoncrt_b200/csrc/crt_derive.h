@@ -157,6 +157,31 @@ inline GlitchGeom glitch_geom(const crt_params& p, int W, int H) {
     return g;
 }
 
+// Composite triad tables (Dev::triad_comp): detects the regular interior pattern of the mask
+// (bright on x % 3 == channel, dim elsewhere, identical on every interior column) and
+// pre-applies mask multiply + inverse LUT to every forward-LUT entry with the kernels' own
+// float32 operations.  Returns false when the mask is not of that form.
+inline bool build_triad_comp(const float* cols, int W, const float* fwd, const float* inv, std::vector<float>* comp, int* x0, int* x1) {
+    if (W < 12) return false;
+    const int xm = W / 2;
+    const float bright = cols[xm * 3 + xm % 3], dim = cols[xm * 3 + (xm + 1) % 3];
+    auto regular = [&](int x) {
+        for (int c = 0; c < 3; ++c) if (cols[x * 3 + c] != (x % 3 == c ? bright : dim)) return false;
+        return true;
+    };
+    int a = xm, b = xm;
+    while (a > 0 && regular(a - 1)) --a;
+    while (b < W - 1 && regular(b + 1)) ++b;
+    if (!regular(xm) || b - a + 1 < W / 2) return false;
+    comp->resize(2 * 1025);
+    for (int t = 0; t < 2; ++t) {
+        const float m = t == 0 ? bright : dim;
+        for (int i = 0; i < 1025; ++i) (*comp)[t * 1025 + i] = sat(inv[lut_index(fmul(fwd[i], m))]);
+    }
+    *x0 = a; *x1 = b;
+    return true;
+}
+
 // Per-frame scalars (flicker factor: crt_filter.py:632, evaluated in double).
 inline FrameDev derive_frame(const crt_params& p, const crt_frame& fr) {
     FrameDev f{};

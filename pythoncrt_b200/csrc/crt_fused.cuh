@@ -23,6 +23,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "crt_stages.cuh"
@@ -41,6 +42,7 @@ struct FusedPlan {
     const char* why = "not planned";
     int bloom = 0, warp = 0;
     int th = 16;                        // tile height
+    int nt = 256;                       // threads per CTA (512 for tall tiles: same shared memory, twice the resident warps)
     int cap_px = 0;                     // capacity of the P-region buffer in pixels
     int cap_aux = 0;                    // floats of the auxiliary buffer (ds cells / row pass / T1 tile)
     int gauss_k = 0;                    // != 0: the packed-FP32 gaussian kernel (crt_fused_gauss.cuh) with this tap count
@@ -56,6 +58,8 @@ inline bool fused_gauss_supported(int K) { return K == 5 || K == 7 || K == 9 || 
 
 
 struct FusedGeom { int th, cap_px, cap_aux; };
+
+inline int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 
 // ---- region helpers ------------------------------------------------------------------------
 struct Box { int x0, y0, x1, y1; };     // inclusive
@@ -142,7 +146,20 @@ __device__ __forceinline__ float mask_at(const Dev& d, const MaskTabs& m, int r,
 // Stages 6-10 with the mask tables (the triad LUT part is crt_math.cuh's exact code).
 __device__ __forceinline__ F3 after_bloom_fast(const Dev& d, const FrameDev& f, F3 v, int y, int x, const float* fwd, const float* inv,
                                                const MaskTabs& m, int r, int c) {
-    if (d.triad_mode) v = triad(d, v, x, fwd, inv);
+    if (d.triad_mode) {
+        if (d.triad_comp) {
+            if (x >= d.comp_x0 && x <= d.comp_x1) {               // regular column: one composite look-up per channel
+                const int ph = x - 3 * (int)__umulhi((unsigned)x, 0x55555556u);     // x % 3
+                v.x = (ph == 0 ? fwd : inv)[lut_index(v.x)];
+                v.y = (ph == 1 ? fwd : inv)[lut_index(v.y)];
+                v.z = (ph == 2 ? fwd : inv)[lut_index(v.z)];
+            } else {
+                v = triad(d, v, x, d.lut_fwd, d.lut_inv);         // mask edge columns: full path from global memory
+            }
+        } else {
+            v = triad(d, v, x, fwd, inv);
+        }
+    }
     if (d.scan_mode | d.vig_mode) {
         const float mk = mask_at(d, m, r, c, y, x);
         v.x = __saturatef(v.x * mk); v.y = __saturatef(v.y * mk); v.z = __saturatef(v.z * mk);
@@ -212,11 +229,11 @@ __device__ __forceinline__ void finish_quad(const Dev& d, float* __restrict__ st
     }
 }
 
-template <int BLOOM, bool WARP>
-__global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+template <int BLOOM, bool WARP, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                               float* __restrict__ state, int has_prev, FusedGeom g) {
     extern __shared__ __align__(16) float sm[];
-    __shared__ float s_fwd[1025], s_inv[1025];
+    __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
     __shared__ float s_unit[256];
     __shared__ float s_rows[2 * FMAX_ROWS], s_cols[2 * FMAX_COLS];
     __shared__ int s_ci[2 * FMAX_COLS], s_ri[2 * FMAX_ROWS];       // fast bloom: up-scale tap offsets per Q column / row
@@ -229,9 +246,17 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
     const int ox1 = imin(ox0 + FTW, d.W) - 1, oy1 = imin(oy0 + g.th, d.H) - 1;
     const int trow = tid / FROW_THREADS, xb = ox0 + (tid % FROW_THREADS) * 4;    // this thread's pixel quad
 
-    if (d.triad_mode >= 2)
-        for (int i = tid; i < 1025; i += FT) { s_fwd[i] = d.lut_fwd[i]; s_inv[i] = d.lut_inv[i]; }
-    s_unit[tid] = __fdiv_rn((float)tid, 255.0f);    // FT == 256
+    // triad tables in shared memory: the composite (bright, dim) pair when the mask is regular, else (forward, inverse)
+    const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
+    const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
+    if (d.triad_mode >= 2) {                        // 2 x 1025 floats, 16-byte loads
+        for (int i = tid; i < 256; i += NT) {
+            reinterpret_cast<float4*>(s_fwd)[i] = reinterpret_cast<const float4*>(lut_a)[i];
+            reinterpret_cast<float4*>(s_inv)[i] = reinterpret_cast<const float4*>(lut_b)[i];
+        }
+        if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
+    }
+    if (tid < 256) s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
     if (WARP && tid < 4) s_box[tid] = (tid < 2) ? 0x7fffffff : -0x7fffffff;
     __syncthreads();
 
@@ -242,7 +267,7 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
 #pragma unroll
         for (int k = 0; k < 4; ++k) xn[k] = warp_norm((float)(xb + k), d.warp_cx, d.warp_dx);
         int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
-        for (int y = oy0 + trow; y <= oy1; y += FROWS_PER_PASS) {
+        for (int y = oy0 + trow; y <= oy1; y += NT / FROW_THREADS) {
             const float yn = warp_norm((float)y, d.warp_cy, d.warp_dy);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -284,7 +309,7 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
         const int ux0 = p.x0 / ps, uy0 = p.y0 / ps;
         const int nux = p.x1 / ps - ux0 + 1, nuy = p.y1 / ps - uy0 + 1;
         const unsigned magic = make_magic(nux);
-        for (int u = tid; u < nux * nuy; u += FT) {
+        for (int u = tid; u < nux * nuy; u += NT) {
             const int uy = fastdiv(u, magic), ux = u - uy * nux;
             const int xa = imax((ux0 + ux) * ps, p.x0), xe = imin((ux0 + ux) * ps + ps - 1, p.x1);
             const int ya = imax((uy0 + uy) * ps, p.y0), ye = imin((uy0 + uy) * ps + ps - 1, p.y1);
@@ -298,23 +323,23 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
                 }
         }
         // per-tile mask tables over Q
-        for (int r = tid; r < qh; r += FT) {
+        for (int r = tid; r < qh; r += NT) {
             const int y = q.y0 + r;
             if (d.scan_mode == 1) mt.row_scan[r] = scan_row(d, f, y);
             else if (d.scan_mode == 2) { double t = ((double)y + f.phase) * d.scan_inv_period; mt.row_scan[r] = (float)(t - floor(t)); }
             if (d.vig_mode == 1) { const float ny = ((float)y - d.vig_cy) * d.vig_iry; mt.row_vig[r] = ny * ny; }
         }
-        for (int c = tid; c < qw; c += FT) {
+        for (int c = tid; c < qw; c += NT) {
             const int x = q.x0 + c;
             if (d.scan_mode == 2) { double t = (d.scan_tan * (double)x) * d.scan_inv_period; mt.col_scan[c] = (float)(t - floor(t)); }
             if (d.vig_mode == 1) { const float nx = ((float)x - d.vig_cx) * d.vig_irx; mt.col_vig[c] = nx * nx; }
         }
         if (BLOOM == 1) {
-            for (int c = tid; c < qw; c += FT) {
+            for (int c = tid; c < qw; c += NT) {
                 const Lerp1 cx = up_coord(d, d.up_x, q.x0 + c, d.hw);
                 s_ci[c] = (cx.s0 - cells.x0) * 3; s_ci[FMAX_COLS + c] = (cx.s1 - cells.x0) * 3; s_cw[c] = cx.w;
             }
-            for (int r = tid; r < qh; r += FT) {
+            for (int r = tid; r < qh; r += NT) {
                 const Lerp1 cy = up_coord(d, d.up_y, q.y0 + r, d.hh);
                 s_ri[r] = (cy.s0 - cells.y0) * qw * 3; s_ri[FMAX_ROWS + r] = (cy.s1 - cells.y0) * qw * 3; s_rw[r] = cy.w;
             }
@@ -334,7 +359,7 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
     };
     if (BLOOM == 1 && !q_empty) {
         const unsigned magic = make_magic(dw);
-        for (int u = tid; u < dw * dh; u += FT) {
+        for (int u = tid; u < dw * dh; u += NT) {
             const int r = fastdiv(u, magic), c = u - r * dw;
             const Lerp1 cy = down_coord(d, d.dn_y, cells.y0 + r), cx = down_coord(d, d.dn_x, cells.x0 + c);
             const float* r0 = T + (cy.s0 - p.y0) * pw * 3;
@@ -350,7 +375,7 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
         __syncthreads();
         // horizontal half of the 2x up-scale (cv2.resize works rows first), once per (cell row, Q column)
         const unsigned magic_q = make_magic(qw);
-        for (int u = tid; u < dh * qw; u += FT) {
+        for (int u = tid; u < dh * qw; u += NT) {
             const int j = fastdiv(u, magic_q), c = u - j * qw;
             const float* dr = A + j * dw * 3;
             const int a0 = s_ci[c], a1 = s_ci[FMAX_COLS + c];
@@ -365,7 +390,7 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
         const int K = d.ksize, rad = K >> 1;
         const int rowlen = cw * 3;
         const unsigned magic = make_magic(rowlen);
-        for (int u = tid; u < ph * rowlen; u += FT) {
+        for (int u = tid; u < ph * rowlen; u += NT) {
             const int r = fastdiv(u, magic), e = u - r * rowlen;
             const int c = fastdiv(e, 0x55555556u /* 2^32/3 + 1 */), ch = e - c * 3, x = q.x0 + c;
             const float* row = T + r * pw * 3;
@@ -390,7 +415,7 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
     // ---- phase 3 [warp]: stages 5-10 in place over Q ----------------------------------------------
     if (WARP && !q_empty) {
         const unsigned magic = make_magic(qw);
-        for (int u = tid; u < qw * qh; u += FT) {
+        for (int u = tid; u < qw * qh; u += NT) {
             const int r = fastdiv(u, magic), c = u - r * qw;
             const int y = q.y0 + r, x = q.x0 + c;
             float* tp = T + ((y - p.y0) * pw + (x - p.x0)) * 3;
@@ -452,7 +477,7 @@ __global__ void __launch_bounds__(FT) k_fused(Dev d, FrameDev f, const uint8_t* 
         }
         return v;
     };
-    for (int y = oy0 + trow; y <= oy1; y += FROWS_PER_PASS) {
+    for (int y = oy0 + trow; y <= oy1; y += NT / FROW_THREADS) {
         if (WARP) yn = warp_norm((float)y, d.warp_cy, d.warp_dy);
         finish_quad(d, state, out, has_prev, y, xb, imin(4, ox1 - xb + 1), pixel);
     }
@@ -476,11 +501,14 @@ inline FusedPlan plan_fused(const Dev& hd, bool glitch_on) {
     auto enough_tiles = [&](int th) { return (long long)((d.W + FTW - 1) / FTW) * ((d.H + th - 1) / th) >= 2 * 148; };
     if (d.bloom_mode == 2 && !d.warp_on && fused_gauss_supported(d.ksize) && d.W >= 4 && d.H >= 4) {
         FusedPlan cand;
+        const int force_th = env_int("CRT_GAUSS_TH", 0);      // tuning knobs (tile height / threads per CTA)
         for (int th : {32, 16}) {
+            if (force_th && th != force_th) continue;
             const size_t smem = fused_gauss_smem(d.ksize, th);
             const bool two_ctas = smem + 12 * 1024 <= 113 * 1024;   // + static shared memory and the per-CTA reserve
             if (two_ctas || (th == 16 && smem <= 200 * 1024)) {
                 cand.ok = true; cand.why = ""; cand.bloom = 2; cand.th = th; cand.smem = smem; cand.gauss_k = d.ksize;
+                cand.nt = env_int("CRT_GAUSS_NT", th >= 32 ? 512 : 256);
                 if (enough_tiles(th)) return cand;
             }
         }
@@ -492,7 +520,9 @@ inline FusedPlan plan_fused(const Dev& hd, bool glitch_on) {
     for (int y = 0; y < (int)yn.size(); ++y) yn[y] = warp_norm((float)y, d.warp_cy, d.warp_dy);
     FusedPlan best, small;
     best.why = "tile footprint does not fit in shared memory";
+    const int force_th = env_int("CRT_FUSED_TH", 0);
     for (int th : {64, 32, 16}) {
+        if (force_th && th != force_th) continue;
         size_t best_px = 0, best_aux = 0;
         int max_qh = 0, max_qw = 0;
         const int tiles_x = (d.W + FTW - 1) / FTW, tiles_y = (d.H + th - 1) / th;
@@ -529,6 +559,7 @@ inline FusedPlan plan_fused(const Dev& hd, bool glitch_on) {
         FusedPlan c;
         c.ok = true; c.why = ""; c.bloom = d.bloom_mode; c.warp = d.warp_on;
         c.th = th; c.cap_px = (int)best_px; c.cap_aux = (int)best_aux; c.smem = smem;
+        c.nt = env_int("CRT_FUSED_NT", th >= 32 ? 512 : 256);
         if (!best.ok) best = c;                          // tallest tile that fits at all
         if (smem + 20 * 1024 <= 113 * 1024) {            // two CTAs per SM (+ ~19 KB static shared memory and reserve)
             if (enough_tiles(th)) return c;              // tallest such tile that still fills the GPU twice over
@@ -539,30 +570,30 @@ inline FusedPlan plan_fused(const Dev& hd, bool glitch_on) {
 }
 
 #if defined(__CUDACC__)
-template <int BLOOM, bool WARP>
+template <int BLOOM, bool WARP, int NT>
 inline int launch_fused_t(const FusedPlan& pl, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state,
                           int has_prev, cudaStream_t st) {
     static size_t configured[64] = {};      // per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (pl.smem > configured[dev & 63]) {
-        if (cudaFuncSetAttribute(k_fused<BLOOM, WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) return 2;
+        if (cudaFuncSetAttribute(k_fused<BLOOM, WARP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) return 2;
         configured[dev & 63] = pl.smem;
     }
     dim3 grid((d.W + FTW - 1) / FTW, (d.H + pl.th - 1) / pl.th);
     FusedGeom g{pl.th, pl.cap_px, pl.cap_aux};
-    k_fused<BLOOM, WARP><<<grid, FT, pl.smem, st>>>(d, f, in, out, state, has_prev, g);
+    k_fused<BLOOM, WARP, NT><<<grid, NT, pl.smem, st>>>(d, f, in, out, state, has_prev, g);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
 inline int run_fused(const FusedPlan& pl, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, int has_prev,
                      cudaStream_t st, int* launches) {
     int rc;
-    if (d.warp_on) rc = d.bloom_mode == 1 ? launch_fused_t<1, true>(pl, d, f, in, out, state, has_prev, st)
-                                          : launch_fused_t<0, true>(pl, d, f, in, out, state, has_prev, st);
-    else rc = d.bloom_mode == 2 ? launch_fused_t<2, false>(pl, d, f, in, out, state, has_prev, st)
-            : d.bloom_mode == 1 ? launch_fused_t<1, false>(pl, d, f, in, out, state, has_prev, st)
-                                : launch_fused_t<0, false>(pl, d, f, in, out, state, has_prev, st);
+#define CRT_LAUNCH(B, W) (pl.nt == 512 ? launch_fused_t<B, W, 512>(pl, d, f, in, out, state, has_prev, st) \
+                                       : launch_fused_t<B, W, 256>(pl, d, f, in, out, state, has_prev, st))
+    if (d.warp_on) rc = d.bloom_mode == 1 ? CRT_LAUNCH(1, true) : CRT_LAUNCH(0, true);
+    else rc = d.bloom_mode == 2 ? CRT_LAUNCH(2, false) : d.bloom_mode == 1 ? CRT_LAUNCH(1, false) : CRT_LAUNCH(0, false);
+#undef CRT_LAUNCH
     ++*launches;
     return rc;
 }

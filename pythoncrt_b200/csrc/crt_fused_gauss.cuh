@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
                                                     float* __restrict__ state, int has_prev, int th) {
     constexpr int R = K / 2, PW = FTW + 2 * R;
     extern __shared__ __align__(16) float sm[];
-    __shared__ float s_fwd[1025], s_inv[1025];
+    __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
     __shared__ float s_unit[256];
     __shared__ float s_rows[2 * 64], s_cols[2 * FTW];
     const int PH = th + 2 * R;                      // padded rows; th is even, so PH is even
@@ -64,8 +64,16 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
     const int ox1 = imin(ox0 + FTW, d.W) - 1, oy1 = imin(oy0 + th, d.H) - 1;
     const int trow = tid / FROW_THREADS, xb = ox0 + (tid % FROW_THREADS) * 4;
 
-    if (d.triad_mode >= 2)
-        for (int i = tid; i < 1025; i += NT) { s_fwd[i] = d.lut_fwd[i]; s_inv[i] = d.lut_inv[i]; }
+    // triad tables in shared memory: the composite (bright, dim) pair when the mask is regular, else (forward, inverse)
+    const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
+    const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
+    if (d.triad_mode >= 2) {                        // 2 x 1025 floats, 16-byte loads
+        for (int i = tid; i < 256; i += NT) {
+            reinterpret_cast<float4*>(s_fwd)[i] = reinterpret_cast<const float4*>(lut_a)[i];
+            reinterpret_cast<float4*>(s_inv)[i] = reinterpret_cast<const float4*>(lut_b)[i];
+        }
+        if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
+    }
     if (tid < 256) s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
     float taps[K];
 #pragma unroll
@@ -162,9 +170,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
     for (int y = oy0 + trow; y <= oy1; y += NT / FROW_THREADS) finish_quad(d, state, out, has_prev, y, xb, imin(4, ox1 - xb + 1), pixel);
 }
 
-constexpr int GAUSS_NT = 512;           // 16 warps per CTA: two CTAs per SM give 32 resident warps
-
-template <int K>
+template <int K, int GAUSS_NT>
 inline int launch_fused_gauss_t(int th, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, int has_prev,
                                 cudaStream_t st) {
     static size_t configured[64] = {};
@@ -180,16 +186,16 @@ inline int launch_fused_gauss_t(int th, const Dev& d, const FrameDev& f, const u
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
-inline int run_fused_gauss(int th, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, int has_prev,
+inline int run_fused_gauss(int th, int nt, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, int has_prev,
                            cudaStream_t st, int* launches) {
     int rc = 4;
     switch (d.ksize) {
-        case 5: rc = launch_fused_gauss_t<5>(th, d, f, in, out, state, has_prev, st); break;
-        case 7: rc = launch_fused_gauss_t<7>(th, d, f, in, out, state, has_prev, st); break;
-        case 9: rc = launch_fused_gauss_t<9>(th, d, f, in, out, state, has_prev, st); break;
-        case 11: rc = launch_fused_gauss_t<11>(th, d, f, in, out, state, has_prev, st); break;
-        case 13: rc = launch_fused_gauss_t<13>(th, d, f, in, out, state, has_prev, st); break;
-        case 25: rc = launch_fused_gauss_t<25>(th, d, f, in, out, state, has_prev, st); break;
+        case 5: rc = nt == 512 ? launch_fused_gauss_t<5, 512>(th, d, f, in, out, state, has_prev, st) : launch_fused_gauss_t<5, 256>(th, d, f, in, out, state, has_prev, st); break;
+        case 7: rc = nt == 512 ? launch_fused_gauss_t<7, 512>(th, d, f, in, out, state, has_prev, st) : launch_fused_gauss_t<7, 256>(th, d, f, in, out, state, has_prev, st); break;
+        case 9: rc = nt == 512 ? launch_fused_gauss_t<9, 512>(th, d, f, in, out, state, has_prev, st) : launch_fused_gauss_t<9, 256>(th, d, f, in, out, state, has_prev, st); break;
+        case 11: rc = nt == 512 ? launch_fused_gauss_t<11, 512>(th, d, f, in, out, state, has_prev, st) : launch_fused_gauss_t<11, 256>(th, d, f, in, out, state, has_prev, st); break;
+        case 13: rc = nt == 512 ? launch_fused_gauss_t<13, 512>(th, d, f, in, out, state, has_prev, st) : launch_fused_gauss_t<13, 256>(th, d, f, in, out, state, has_prev, st); break;
+        case 25: rc = nt == 512 ? launch_fused_gauss_t<25, 512>(th, d, f, in, out, state, has_prev, st) : launch_fused_gauss_t<25, 256>(th, d, f, in, out, state, has_prev, st); break;
         default: break;
     }
     ++*launches;

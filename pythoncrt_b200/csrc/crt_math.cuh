@@ -122,6 +122,11 @@ struct Dev {
     int triad_mode;              // 0 off, 1 plain multiply, 2 LUT, 3 LUT + preserve luma
     const float* triad_cols;     // [W][3]
     const float* lut_fwd; const float* lut_inv;   // [1025]
+    // Composite tables for the interior columns of a regular triad mask (triad_mode 2 only):
+    // comp[0][i] = inv[idx(fwd[i] * bright)], comp[1][i] = inv[idx(fwd[i] * dim)] — the same
+    // float32 operations, evaluated once per table entry instead of once per pixel.
+    const float* triad_comp;     // [2][1025] or null
+    int comp_x0, comp_x1;        // columns [comp_x0, comp_x1] follow the (x % 3 == channel ? bright : dim) pattern
     // stage 7: scanlines (:213-217, :308-328)
     int scan_mode;               // 0 off, 1 per-row float32, 2 slanted/shaped plane
     float scan_strength, scan_c32;
