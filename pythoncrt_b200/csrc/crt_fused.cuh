@@ -315,12 +315,17 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
             const int ya = imax((uy0 + uy) * ps, p.y0), ye = imin((uy0 + uy) * ps + ps - 1, p.y1);
             const F3 v1 = ps > 1 ? graded_source_lut(d, in, (uy0 + uy) * ps, (ux0 + ux) * ps, ya, xa, s_unit) : graded_input_lut(d, in, ya, xa, s_unit);
             const F3 v = (BLOOM == 2 && d.thr_on) ? bloom_src(d, v1) : v1;
-            for (int y = ya; y <= ye; ++y)
-                for (int x = xa; x <= xe; ++x) {
-                    if (BLOOM == 2 && d.thr_on && y >= oy0 && y <= oy1 && x >= ox0 && x <= ox1)
-                        store_f3(T1 + ((y - oy0) * FTW + (x - ox0)) * 3, v1);
-                    store_f3(T + ((y - p.y0) * pw + (x - p.x0)) * 3, v);
-                }
+            float* t0 = T + ((ya - p.y0) * pw + (xa - p.x0)) * 3;
+            if (ps == 2 && xe == xa + 1 && ye == ya + 1 && !(BLOOM == 2 && d.thr_on)) {      // whole 2x2 block inside the region
+                store_f3(t0, v); store_f3(t0 + 3, v); store_f3(t0 + pw * 3, v); store_f3(t0 + pw * 3 + 3, v);
+            } else {
+                for (int y = ya; y <= ye; ++y)
+                    for (int x = xa; x <= xe; ++x) {
+                        if (BLOOM == 2 && d.thr_on && y >= oy0 && y <= oy1 && x >= ox0 && x <= ox1)
+                            store_f3(T1 + ((y - oy0) * FTW + (x - ox0)) * 3, v1);
+                        store_f3(t0 + ((y - ya) * pw + (x - xa)) * 3, v);
+                    }
+            }
         }
         // per-tile mask tables over Q
         for (int r = tid; r < qh; r += NT) {

@@ -99,12 +99,26 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
             // padded positions that replicate this block (image borders extend outwards)
             const int xx0 = (xa == 0) ? 0 : xa - px0, xx1 = (xe == d.W - 1) ? PWe - 1 : xe - px0;
             const int yy0 = (ya == 0) ? 0 : ya - py0, yy1 = (ye == d.H - 1) ? PHe - 1 : ye - py0;
-            for (int xx = xx0; xx <= xx1; ++xx) {
-                float* c0 = St + xx * pitch;
-                for (int yy = yy0; yy <= yy1; ++yy) { c0[yy] = v.x; c0[PW * pitch + yy] = v.y; c0[2 * PW * pitch + yy] = v.z; }
+            float* c0 = St + xx0 * pitch + yy0;
+            if (xx1 == xx0 + 1 && yy1 == yy0 + 1) {            // interior 2x2 block (pixel_size 2): straight-line stores
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float val = ch == 0 ? v.x : (ch == 1 ? v.y : v.z);
+                    float* cc = c0 + ch * PW * pitch;
+                    cc[0] = val; cc[1] = val; cc[pitch] = val; cc[pitch + 1] = val;
+                }
+            } else {
+                for (int xx = xx0; xx <= xx1; ++xx, c0 += pitch)
+                    for (int yy = 0; yy <= yy1 - yy0; ++yy) { c0[yy] = v.x; c0[PW * pitch + yy] = v.y; c0[2 * PW * pitch + yy] = v.z; }
             }
-            for (int y = imax(ya, oy0); y <= imin(ye, oy1); ++y)
-                for (int x = imax(xa, ox0); x <= imin(xe, ox1); ++x) store_f3(T1 + ((y - oy0) * FTW + (x - ox0)) * 3, v1);
+            const int tx0 = imax(xa, ox0), tx1 = imin(xe, ox1), ty0 = imax(ya, oy0), ty1 = imin(ye, oy1);
+            float* t1 = T1 + ((ty0 - oy0) * FTW + (tx0 - ox0)) * 3;
+            if (tx1 == tx0 + 1 && ty1 == ty0 + 1) {
+                store_f3(t1, v1); store_f3(t1 + 3, v1); store_f3(t1 + FTW * 3, v1); store_f3(t1 + FTW * 3 + 3, v1);
+            } else {
+                for (int y = ty0; y <= ty1; ++y)
+                    for (int x = tx0; x <= tx1; ++x) store_f3(T1 + ((y - oy0) * FTW + (x - ox0)) * 3, v1);
+            }
         }
         for (int r = tid; r <= oy1 - oy0; r += NT) {
             const int y = oy0 + r;
