@@ -255,12 +255,12 @@ def main() -> int:
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": args.workload, "desc": wl["desc"], "width": W, "height": H, "frames_per_gpu": N, "halo_frames": halo,
-                       "fps": fps, "parallelism": f"temporal-shards x{world}", "path": "fused" if fused else "staged",
+                       "fps": fps, "parallelism": f"temporal-shards x{world}", "path": {0: "staged", 1: "fused", 2: "two-pass"}.get(fused, str(fused)),
                        "rng": "device counter-based (noise/glitch generated)", "l2": "clip (in+out) is larger than L2; no flush needed",
                        "alg_bytes_per_px": bpp},
             "effective_gbs": value * W * H * bpp / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "fused tile kernel" if fused else "k_output (staged)",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": {0: "k_output (staged)", 1: "fused tile kernel", 2: "fused first pass (two-pass path)"}.get(fused),
                          "kernel_avg_ms": kern_avg_ms, "kernel_launches_timed": kern_n,
                          "kernel_share_of_step": (kern_ms / total_ms) if total_ms else None},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

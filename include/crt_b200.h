@@ -123,7 +123,7 @@ typedef struct crt_frame {
 
 typedef struct crt_launch_info {
     int32_t kernels_launched;       /* kernels of this library launched by the call */
-    int32_t fused;                  /* 1 if the single fused tile kernel ran, 0 if the staged path ran */
+    int32_t fused;                  /* 1 = single fused tile kernel, 2 = two-pass (fused first pass + gather), 0 = staged kernels */
     int32_t reserved[6];
 } crt_launch_info;
 

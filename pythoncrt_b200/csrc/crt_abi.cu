@@ -55,7 +55,9 @@ struct crt_ctx {
     Dev dev{};
     bool dev_ok = false;
     int policy = 0;
-    FusedPlan plan{};
+    FusedPlan plan{};                   // single-pass fused kernel
+    FusedPlan plan_q{};                 // two-pass: fused first pass without warp/glitch/text-after, then k_gather
+    Dev dev_q{};                        // parameter block of that first pass
     std::vector<cudaEvent_t> prof_ev;   // start/stop pairs (crt_profile_begin/end)
     int prof_cap = 0, prof_n = 0;
     bool prof_on = false;
@@ -122,6 +124,15 @@ int build_dev(crt_ctx* ctx) {
     Dev hd = ctx->dev;                                   // same block with HOST coordinate tables, for planning
     hd.dn_x = ctx->h_dn_x.data(); hd.dn_y = ctx->h_dn_y.data(); hd.up_x = ctx->h_up_x.data(); hd.up_y = ctx->h_up_y.data();
     ctx->plan = plan_fused(hd, glitch_active(p));
+    ctx->plan_q = FusedPlan{};
+    if (!ctx->plan.ok || env_int("CRT_TWO_PASS", 0)) {
+        Dev hq = hd;
+        hq.warp_on = 0; hq.text_mode = hd.text_mode == 1 ? 1 : 0;
+        ctx->plan_q = plan_fused(hq, false);
+        ctx->dev_q = ctx->dev;
+        ctx->dev_q.warp_on = 0; ctx->dev_q.text_mode = hq.text_mode;
+        if (env_int("CRT_TWO_PASS", 0) && ctx->plan_q.ok) ctx->plan.ok = false;      // tuning knob: prefer the two-pass path
+    }
     return CRT_OK;
 }
 
@@ -190,7 +201,10 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
     const GlitchGeom gg = glitch_geom(p, d.W, d.H);
     int launches = 0, fused_used = 0;
     const bool want_fused = ctx->policy != 1 && ctx->plan.ok && !d_img;
-    if (ctx->policy == 2 && !want_fused) return fail(ctx, CRT_ERR_UNSUPPORTED, std::string("fused kernel not available: ") + ctx->plan.why);
+    const bool want_two_pass = ctx->policy != 1 && !want_fused && ctx->plan_q.ok && !d_img;
+    if (ctx->policy == 2 && !want_fused && !want_two_pass)
+        return fail(ctx, CRT_ERR_UNSUPPORTED, std::string("fused kernel not available: ") + ctx->plan.why);
+    if (want_two_pass && !ctx->scratch.q) CU(cudaMalloc((void**)&ctx->scratch.q, frame_px * 3 * sizeof(float)));
     for (int i = 0; i < n_frames; ++i) {
         const crt_frame& fr = frames[i];
         FrameDev f = derive_frame(p, fr);
@@ -232,10 +246,18 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         int rc;
         if (want_fused) {
             prof_mark(ctx, st, false);
-            rc = ctx->plan.gauss_k ? run_fused_gauss(ctx->plan.th, ctx->plan.nt, d, f, in_i, out_i, state_i, has_prev, st, &launches)
-                                   : run_fused(ctx->plan, d, f, in_i, out_i, state_i, has_prev, st, &launches);
+            rc = ctx->plan.gauss_k ? run_fused_gauss(ctx->plan.th, ctx->plan.nt, d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches)
+                                   : run_fused(ctx->plan, d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches);
             fused_used = 1;
             prof_mark(ctx, st, true);
+        } else if (want_two_pass) {
+            const FusedPlan& pq = ctx->plan_q;
+            prof_mark(ctx, st, false);
+            rc = pq.gauss_k ? run_fused_gauss(pq.th, pq.nt, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
+                            : run_fused(pq, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches);
+            prof_mark(ctx, st, true);
+            if (!rc) rc = run_gather(d, f, ctx->scratch.q, out_i, state_i, has_prev, st, &launches);
+            fused_used = 2;
         }
         else rc = run_staged(ctx, f, in_i, out_i, state_i, has_prev, img_i, st, &launches);
         if (rc == CRT_ERR_CUDA) return fail(ctx, rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));

@@ -174,14 +174,16 @@ __device__ __forceinline__ F3 after_bloom_fast(const Dev& d, const FrameDev& f, 
 
 // Blend four horizontally adjacent pixels with the persistence state, write state (16-byte
 // stores) and packed uint8 output.  `pixel(y, x, k)` returns the float image value
-// (what apply_static_effects returns) of pixel k of the quad.
+// (what apply_static_effects returns) of pixel k of the quad.  With `q_out` set the float
+// values are stored there instead (first pass of the two-pass path, crt_abi.cu).
 template <typename PixelFn>
-__device__ __forceinline__ void finish_quad(const Dev& d, float* __restrict__ state, uint8_t* __restrict__ out, int has_prev,
-                                            int y, int xb, int npx, PixelFn&& pixel) {
+__device__ __forceinline__ void finish_quad(const Dev& d, float* __restrict__ state, uint8_t* __restrict__ out, float* __restrict__ q_out,
+                                            int has_prev, int y, int xb, int npx, PixelFn&& pixel) {
     const float pp = d.persist, pq = d.persist_q;
     const bool vec = (d.W & 3) == 0;
     const int o = (y * d.W + xb) * 3;               // < 2^31 (checked by plan_fused)
     float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa, pc = pa;       // previous state of the 4 pixels
+    if (q_out) { has_prev = 0; state = q_out; }
     if (has_prev) {
         if (vec) {
             const float4* sp = reinterpret_cast<const float4*>(state + o);
@@ -200,7 +202,6 @@ __device__ __forceinline__ void finish_quad(const Dev& d, float* __restrict__ st
         F3 v = mk3(0.f, 0.f, 0.f);
         if (k < npx) {
             v = pixel(y, xb + k, k);
-            if (d.text_mode == 2) v = text_blend(d, v, y, xb + k);
             if (has_prev) { v.x = blend_fast(prev[k * 3], v.x, pp, pq); v.y = blend_fast(prev[k * 3 + 1], v.y, pp, pq); v.z = blend_fast(prev[k * 3 + 2], v.z, pp, pq); }
         }
         res[k * 3] = v.x; res[k * 3 + 1] = v.y; res[k * 3 + 2] = v.z;
@@ -212,6 +213,7 @@ __device__ __forceinline__ void finish_quad(const Dev& d, float* __restrict__ st
             sp[1] = make_float4(res[4], res[5], res[6], res[7]);
             sp[2] = make_float4(res[8], res[9], res[10], res[11]);
         }
+        if (q_out) return;
         uint32_t w[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j)
@@ -224,14 +226,14 @@ __device__ __forceinline__ void finish_quad(const Dev& d, float* __restrict__ st
         for (int k = 0; k < 12; ++k)
             if (k < npx * 3) {
                 if (state) state[o + k] = res[k];
-                out[o + k] = quantise(res[k]);
+                if (!q_out) out[o + k] = quantise(res[k]);
             }
     }
 }
 
 template <int BLOOM, bool WARP, int NT>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
-                                              float* __restrict__ state, int has_prev, FusedGeom g) {
+                                              float* __restrict__ state, float* __restrict__ q_out, int has_prev, FusedGeom g) {
     extern __shared__ __align__(16) float sm[];
     __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
     __shared__ float s_unit[256];
@@ -480,12 +482,55 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
             }
             v = after_bloom_fast(d, f, v, y, x, s_fwd, s_inv, mt, y - q.y0, x - q.x0);
         }
+        if (d.text_mode == 2) v = text_blend(d, v, y, x);
         return v;
     };
     for (int y = oy0 + trow; y <= oy1; y += NT / FROW_THREADS) {
         if (WARP) yn = warp_norm((float)y, d.warp_cy, d.warp_dy);
-        finish_quad(d, state, out, has_prev, y, xb, imin(4, ox1 - xb + 1), pixel);
+        finish_quad(d, state, out, q_out, has_prev, y, xb, imin(4, ox1 - xb + 1), pixel);
     }
+}
+
+// Second pass of the two-pass path: glitch shift, 4-tap warp gather from the pre-warp image
+// written by the first pass (global memory, L2-resident for the most part), text layer,
+// persistence, quantise.  Handles every gather the single-pass kernel declines.
+constexpr int GATHER_TH = 16;
+template <bool WARP>
+__global__ void __launch_bounds__(256) k_gather(Dev d, FrameDev f, const float* __restrict__ qimg, uint8_t* __restrict__ out,
+                                                float* __restrict__ state, int has_prev) {
+    const int tid = threadIdx.x;
+    const int y = blockIdx.y * GATHER_TH + tid / FROW_THREADS, xb = blockIdx.x * FTW + (tid % FROW_THREADS) * 4;
+    if (y >= d.H || xb >= d.W) return;
+    const float yn = WARP ? warp_norm((float)y, d.warp_cy, d.warp_dy) : 0.f;
+    auto pixel = [&](int yy, int x, int k) -> F3 {
+        const int gx = glitch_src_x(d, f, yy, x);
+        F3 v = mk3(0.f, 0.f, 0.f);
+        if (WARP) {
+            const Taps t = warp_taps_n(d, warp_norm((float)gx, d.warp_cx, d.warp_dx), yn);
+            F3 a[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ty = t.iy + (j >> 1), tx = t.ix + (j & 1);
+                const bool ok = ty >= 0 && ty < d.H && tx >= 0 && tx < d.W;
+                a[j] = ok ? load_f3(qimg + ((size_t)ty * d.W + tx) * 3) : mk3(0.f, 0.f, 0.f);
+            }
+            v = mk3(gather4_fast(a[0].x, a[1].x, a[2].x, a[3].x, t), gather4_fast(a[0].y, a[1].y, a[2].y, a[3].y, t),
+                    gather4_fast(a[0].z, a[1].z, a[2].z, a[3].z, t));
+        } else {
+            v = load_f3(qimg + ((size_t)yy * d.W + gx) * 3);
+        }
+        if (d.text_mode == 2) v = text_blend(d, v, yy, gx);
+        return v;
+    };
+    finish_quad(d, state, out, nullptr, has_prev, y, xb, imin(4, d.W - xb), pixel);
+}
+
+inline int run_gather(const Dev& d, const FrameDev& f, const float* qimg, uint8_t* out, float* state, int has_prev, cudaStream_t st, int* launches) {
+    dim3 grid((d.W + FTW - 1) / FTW, (d.H + GATHER_TH - 1) / GATHER_TH);
+    if (d.warp_on) k_gather<true><<<grid, 256, 0, st>>>(d, f, qimg, out, state, has_prev);
+    else k_gather<false><<<grid, 256, 0, st>>>(d, f, qimg, out, state, has_prev);
+    ++*launches;
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
 #endif  // __CUDACC__
@@ -577,7 +622,7 @@ inline FusedPlan plan_fused(const Dev& hd, bool glitch_on) {
 #if defined(__CUDACC__)
 template <int BLOOM, bool WARP, int NT>
 inline int launch_fused_t(const FusedPlan& pl, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state,
-                          int has_prev, cudaStream_t st) {
+                          float* q_out, int has_prev, cudaStream_t st) {
     static size_t configured[64] = {};      // per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -587,15 +632,15 @@ inline int launch_fused_t(const FusedPlan& pl, const Dev& d, const FrameDev& f, 
     }
     dim3 grid((d.W + FTW - 1) / FTW, (d.H + pl.th - 1) / pl.th);
     FusedGeom g{pl.th, pl.cap_px, pl.cap_aux};
-    k_fused<BLOOM, WARP, NT><<<grid, NT, pl.smem, st>>>(d, f, in, out, state, has_prev, g);
+    k_fused<BLOOM, WARP, NT><<<grid, NT, pl.smem, st>>>(d, f, in, out, state, q_out, has_prev, g);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
-inline int run_fused(const FusedPlan& pl, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, int has_prev,
-                     cudaStream_t st, int* launches) {
+inline int run_fused(const FusedPlan& pl, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
+                     int has_prev, cudaStream_t st, int* launches) {
     int rc;
-#define CRT_LAUNCH(B, W) (pl.nt == 512 ? launch_fused_t<B, W, 512>(pl, d, f, in, out, state, has_prev, st) \
-                                       : launch_fused_t<B, W, 256>(pl, d, f, in, out, state, has_prev, st))
+#define CRT_LAUNCH(B, W) (pl.nt == 512 ? launch_fused_t<B, W, 512>(pl, d, f, in, out, state, q_out, has_prev, st) \
+                                       : launch_fused_t<B, W, 256>(pl, d, f, in, out, state, q_out, has_prev, st))
     if (d.warp_on) rc = d.bloom_mode == 1 ? CRT_LAUNCH(1, true) : CRT_LAUNCH(0, true);
     else rc = d.bloom_mode == 2 ? CRT_LAUNCH(2, false) : d.bloom_mode == 1 ? CRT_LAUNCH(1, false) : CRT_LAUNCH(0, false);
 #undef CRT_LAUNCH

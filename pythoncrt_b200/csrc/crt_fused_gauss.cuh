@@ -47,7 +47,7 @@ __device__ __forceinline__ float2 gauss_col2(const float2* c, const float* k) {
 
 template <int K, int NT>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
-                                                    float* __restrict__ state, int has_prev, int th) {
+                                                    float* __restrict__ state, float* __restrict__ q_out, int has_prev, int th) {
     constexpr int R = K / 2, PW = FTW + 2 * R;
     extern __shared__ __align__(16) float sm[];
     __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
@@ -179,14 +179,16 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
         F3 v = load_f3(T1 + (ly * FTW + lx) * 3);
         const float* b = Bl + ly * FTW + lx;
         v = add_bloom(d, v, mk3(b[0], b[th * FTW], b[2 * th * FTW]));
-        return after_bloom_fast(d, f, v, y, x, s_fwd, s_inv, mt, ly, lx);
+        v = after_bloom_fast(d, f, v, y, x, s_fwd, s_inv, mt, ly, lx);
+        if (d.text_mode == 2) v = text_blend(d, v, y, x);
+        return v;
     };
-    for (int y = oy0 + trow; y <= oy1; y += NT / FROW_THREADS) finish_quad(d, state, out, has_prev, y, xb, imin(4, ox1 - xb + 1), pixel);
+    for (int y = oy0 + trow; y <= oy1; y += NT / FROW_THREADS) finish_quad(d, state, out, q_out, has_prev, y, xb, imin(4, ox1 - xb + 1), pixel);
 }
 
 template <int K, int GAUSS_NT>
-inline int launch_fused_gauss_t(int th, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, int has_prev,
-                                cudaStream_t st) {
+inline int launch_fused_gauss_t(int th, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
+                                int has_prev, cudaStream_t st) {
     static size_t configured[64] = {};
     const size_t smem = fused_gauss_smem(K, th);
     int dev = 0;
@@ -196,20 +198,20 @@ inline int launch_fused_gauss_t(int th, const Dev& d, const FrameDev& f, const u
         configured[dev & 63] = smem;
     }
     dim3 grid((d.W + FTW - 1) / FTW, (d.H + th - 1) / th);
-    k_fused_gauss<K, GAUSS_NT><<<grid, GAUSS_NT, smem, st>>>(d, f, in, out, state, has_prev, th);
+    k_fused_gauss<K, GAUSS_NT><<<grid, GAUSS_NT, smem, st>>>(d, f, in, out, state, q_out, has_prev, th);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
-inline int run_fused_gauss(int th, int nt, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, int has_prev,
-                           cudaStream_t st, int* launches) {
+inline int run_fused_gauss(int th, int nt, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
+                           int has_prev, cudaStream_t st, int* launches) {
     int rc = 4;
     switch (d.ksize) {
-        case 5: rc = nt == 512 ? launch_fused_gauss_t<5, 512>(th, d, f, in, out, state, has_prev, st) : launch_fused_gauss_t<5, 256>(th, d, f, in, out, state, has_prev, st); break;
-        case 7: rc = nt == 512 ? launch_fused_gauss_t<7, 512>(th, d, f, in, out, state, has_prev, st) : launch_fused_gauss_t<7, 256>(th, d, f, in, out, state, has_prev, st); break;
-        case 9: rc = nt == 512 ? launch_fused_gauss_t<9, 512>(th, d, f, in, out, state, has_prev, st) : launch_fused_gauss_t<9, 256>(th, d, f, in, out, state, has_prev, st); break;
-        case 11: rc = nt == 512 ? launch_fused_gauss_t<11, 512>(th, d, f, in, out, state, has_prev, st) : launch_fused_gauss_t<11, 256>(th, d, f, in, out, state, has_prev, st); break;
-        case 13: rc = nt == 512 ? launch_fused_gauss_t<13, 512>(th, d, f, in, out, state, has_prev, st) : launch_fused_gauss_t<13, 256>(th, d, f, in, out, state, has_prev, st); break;
-        case 25: rc = nt == 512 ? launch_fused_gauss_t<25, 512>(th, d, f, in, out, state, has_prev, st) : launch_fused_gauss_t<25, 256>(th, d, f, in, out, state, has_prev, st); break;
+        case 5: rc = nt == 512 ? launch_fused_gauss_t<5, 512>(th, d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_t<5, 256>(th, d, f, in, out, state, q_out, has_prev, st); break;
+        case 7: rc = nt == 512 ? launch_fused_gauss_t<7, 512>(th, d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_t<7, 256>(th, d, f, in, out, state, q_out, has_prev, st); break;
+        case 9: rc = nt == 512 ? launch_fused_gauss_t<9, 512>(th, d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_t<9, 256>(th, d, f, in, out, state, q_out, has_prev, st); break;
+        case 11: rc = nt == 512 ? launch_fused_gauss_t<11, 512>(th, d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_t<11, 256>(th, d, f, in, out, state, q_out, has_prev, st); break;
+        case 13: rc = nt == 512 ? launch_fused_gauss_t<13, 512>(th, d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_t<13, 256>(th, d, f, in, out, state, q_out, has_prev, st); break;
+        case 25: rc = nt == 512 ? launch_fused_gauss_t<25, 512>(th, d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_t<25, 256>(th, d, f, in, out, state, q_out, has_prev, st); break;
         default: break;
     }
     ++*launches;
