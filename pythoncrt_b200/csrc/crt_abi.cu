@@ -41,6 +41,7 @@ struct crt_ctx {
     size_t tab_bytes[CRT_TABLE_COUNT] = {};
     std::vector<int32_t> h_pix_x, h_pix_y;                 // host copies (tile planning, pix_uniform)
     std::vector<float> h_cols, h_fwd, h_inv;               // host copies of the triad tables (composite LUT)
+    double* pow_tab = nullptr;                             // device tables of pow_unit
     float* comp_lut = nullptr;                             // device [2][1028] (16-byte aligned tables of 1025)
     std::vector<Lerp1> h_dn_x, h_dn_y, h_up_x, h_up_y;     // host copies of the fast-bloom coordinate tables
     Lerp1 *dn_x = nullptr, *dn_y = nullptr, *up_x = nullptr, *up_y = nullptr, *nz_x = nullptr, *nz_y = nullptr;
@@ -103,6 +104,7 @@ int build_dev(crt_ctx* ctx) {
         for (int y = 0; y < ctx->H && uni; ++y) uni = ctx->h_pix_y[y] == p.pixel_size * (y / p.pixel_size);
         t.pix_uniform = uni ? p.pixel_size : 0;
     }
+    t.pow_tab = ctx->pow_tab;
     t.dn_x = ctx->dn_x; t.dn_y = ctx->dn_y; t.up_x = ctx->up_x; t.up_y = ctx->up_y; t.nz_x = ctx->nz_x; t.nz_y = ctx->nz_y;
     std::string err;
     int rc = derive_dev(p, ctx->W, ctx->H, t, &ctx->dev, &err);
@@ -293,6 +295,12 @@ int crt_create(int device, int width, int height, crt_ctx** out_ctx) {
     if (!rc) rc = upload(c, &c->dn_y, c->h_dn_y);
     if (!rc) rc = upload(c, &c->up_x, c->h_up_x);
     if (!rc) rc = upload(c, &c->up_y, c->h_up_y);
+    if (!rc) {
+        double tab[POW_TAB_DOUBLES];
+        fill_pow_table(tab);
+        if (cudaMalloc((void**)&c->pow_tab, sizeof(tab)) != cudaSuccess || cudaMemcpy(c->pow_tab, tab, sizeof(tab), cudaMemcpyHostToDevice) != cudaSuccess)
+            rc = fail(c, CRT_ERR_CUDA, "pow table upload failed");
+    }
     if (rc) { g_create_error = c->err; crt_destroy(c); return rc; }
     *out_ctx = c;
     return CRT_OK;
@@ -310,6 +318,7 @@ int crt_destroy(crt_ctx* ctx) {
     if (ctx->glitch_buf) cudaFree(ctx->glitch_buf);
     if (ctx->state) cudaFree(ctx->state);
     if (ctx->comp_lut) cudaFree(ctx->comp_lut);
+    if (ctx->pow_tab) cudaFree(ctx->pow_tab);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     HostRing& r = ctx->ring;
     for (int s = 0; s < HostRing::SLOTS; ++s) {

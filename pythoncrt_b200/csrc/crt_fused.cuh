@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
     extern __shared__ __align__(16) float sm[];
     __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
     __shared__ float s_unit[256];
+    __shared__ double s_pow[POW_TAB_DOUBLES];
     __shared__ float s_rows[2 * FMAX_ROWS], s_cols[2 * FMAX_COLS];
     __shared__ int s_ci[2 * FMAX_COLS], s_ri[2 * FMAX_ROWS];       // fast bloom: up-scale tap offsets per Q column / row
     __shared__ float s_cw[FMAX_COLS], s_rw[FMAX_ROWS];              // ... and weights (cv2.resize coordinates)
@@ -259,6 +260,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
         if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
     }
     if (tid < 256) s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
+    if (d.col_gamma && tid < POW_TAB_DOUBLES) s_pow[tid] = d.pow_tab[tid];
     if (WARP && tid < 4) s_box[tid] = (tid < 2) ? 0x7fffffff : -0x7fffffff;
     __syncthreads();
 
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
             const int uy = fastdiv(u, magic), ux = u - uy * nux;
             const int xa = imax((ux0 + ux) * ps, p.x0), xe = imin((ux0 + ux) * ps + ps - 1, p.x1);
             const int ya = imax((uy0 + uy) * ps, p.y0), ye = imin((uy0 + uy) * ps + ps - 1, p.y1);
-            const F3 v1 = ps > 1 ? graded_source_lut(d, in, (uy0 + uy) * ps, (ux0 + ux) * ps, ya, xa, s_unit) : graded_input_lut(d, in, ya, xa, s_unit);
+            const F3 v1 = ps > 1 ? graded_source_lut(d, in, (uy0 + uy) * ps, (ux0 + ux) * ps, ya, xa, s_unit, s_pow) : graded_input_lut(d, in, ya, xa, s_unit, s_pow);
             const F3 v = (BLOOM == 2 && d.thr_on) ? bloom_src(d, v1) : v1;
             float* t0 = T + ((ya - p.y0) * pw + (xa - p.x0)) * 3;
             if (ps == 2 && xe == xa + 1 && ye == ya + 1 && !(BLOOM == 2 && d.thr_on)) {      // whole 2x2 block inside the region

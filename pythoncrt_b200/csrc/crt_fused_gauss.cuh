@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
     extern __shared__ __align__(16) float sm[];
     __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
     __shared__ float s_unit[256];
+    __shared__ double s_pow[POW_TAB_DOUBLES];
     __shared__ float s_rows[2 * 64], s_cols[2 * FTW];
     const int PH = th + 2 * R;                      // padded rows; th is even, so PH is even
     const int pitch = PH;                           // floats between consecutive x in St
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
         if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
     }
     if (tid < 256) s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
+    if (d.col_gamma && tid < POW_TAB_DOUBLES) s_pow[tid] = d.pow_tab[tid];
     float taps[K];
 #pragma unroll
     for (int i = 0; i < K; ++i) taps[i] = d.taps[i];
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
             const int uy = fastdiv(u, magic), ux = u - uy * nux;
             const int xa = imax((ux0 + ux) * ps, ix0), xe = imin((ux0 + ux) * ps + ps - 1, ix1);
             const int ya = imax((uy0 + uy) * ps, iy0), ye = imin((uy0 + uy) * ps + ps - 1, iy1);
-            const F3 v1 = ps > 1 ? graded_source_lut(d, in, (uy0 + uy) * ps, (ux0 + ux) * ps, ya, xa, s_unit) : graded_input_lut(d, in, ya, xa, s_unit);
+            const F3 v1 = ps > 1 ? graded_source_lut(d, in, (uy0 + uy) * ps, (ux0 + ux) * ps, ya, xa, s_unit, s_pow) : graded_input_lut(d, in, ya, xa, s_unit, s_pow);
             const F3 v = bloom_src(d, v1);
             // padded positions that replicate this block (image borders extend outwards)
             const int xx0 = (xa == 0) ? 0 : xa - px0, xx1 = (xe == d.W - 1) ? PWe - 1 : xe - px0;

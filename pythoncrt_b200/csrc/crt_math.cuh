@@ -15,6 +15,7 @@
 
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define CRT_HD __host__ __device__ __forceinline__
@@ -35,6 +36,15 @@ static inline float cospif(float x) { return (float)cos(3.14159265358979323846 *
 #endif
 
 namespace crt {
+
+#define CRT_POW_TABLE static const
+#include "crt_pow_tables.h"     // host copies; kernels read the same values through Dev::pow_tab / shared memory
+#undef CRT_POW_TABLE
+constexpr int POW_TAB_DOUBLES = 64;     // [invc 16 | logc 16 | 2^(j/32) 32]
+inline void fill_pow_table(double* t) {
+    for (int i = 0; i < 16; ++i) { t[i] = kPowInvC[i]; t[16 + i] = kPowLogC[i]; }
+    for (int j = 0; j < 32; ++j) t[32 + j] = kPowExp2[j];
+}
 
 // ---- exact float32 primitives ------------------------------------------------
 CRT_HD float fmul(float a, float b) {
@@ -106,6 +116,8 @@ struct Dev {
     // stage 3: colour (:279-305)
     int col_sat, col_temp, col_bc, col_gamma;
     float sat_f, gain0, gain2, contrast, brightness, inv_gamma;
+    double inv_gamma32;          // 32 * float32(1 / gamma), for pow_unit
+    const double* pow_tab;       // [POW_TAB_DOUBLES] tables of pow_unit
     // text layer (:588-598 / :653-663)
     int text_mode;               // 0 none, 1 before, 2 after
     const uint8_t* text;         // [H][W][4]
@@ -171,8 +183,70 @@ CRT_HD void source_bytes(const Dev& d, const uint8_t* __restrict__ in, int y, in
     b2 = row[x2 * 3 + 2];
 }
 
+// ---- x^y for the colour gamma (:304) ------------------------------------------------------------
+// numpy evaluates np.power(img, 1/gamma, dtype=float32) with SVML: within 1 ulp, not correctly
+// rounded, not reproducible elsewhere.  pow_unit is the table-driven scheme of glibc's powf
+// (16-entry log2 table + degree-6 polynomial, 32-entry exp2 table + degree-4 polynomial) in
+// double, rounded once: correctly rounded for all but ~1e-4 of inputs, max 1 ulp, ~40
+// instructions of which half run on the otherwise idle FP64 pipe (CUDA's powf: ~110).
+// Domain: x in [0, 1] (the stage input is clipped), y > 0, y32 = 32 * y.
+CRT_HD uint32_t f2u(float f) {
+#if CRT_DEVICE_CODE
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+CRT_HD float u2f(uint32_t u) {
+#if CRT_DEVICE_CODE
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+CRT_HD int64_t d2i(double v) {
+#if CRT_DEVICE_CODE
+    return __double_as_longlong(v);
+#else
+    int64_t u; memcpy(&u, &v, 8); return u;
+#endif
+}
+CRT_HD double i2d(int64_t u) {
+#if CRT_DEVICE_CODE
+    return __longlong_as_double(u);
+#else
+    double v; memcpy(&v, &u, 8); return v;
+#endif
+}
+CRT_HD float pow_unit(float x, double y32, const double* __restrict__ T) {
+    if (!(x >= 1.17549435e-38f)) return 0.0f;             // 0 (and sub-normals, which the chain never produces) -> 0
+    const uint32_t ix = f2u(x), tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> 19) & 15u);
+    const uint32_t top = tmp & 0xff800000u;
+    const double z = (double)u2f(ix - top);
+    const double k = (double)((int32_t)top >> 23);
+    const double r = fma(z, T[i], -1.0);
+    double p = 0x1.27cd35133559fp-2 + r * -0x1.ed17545dcd181p-3;      // kPowLogPoly[4], [5]
+    p = fma(p, r, -0x1.71546af33f6cfp-2);
+    p = fma(p, r, 0x1.ec7093a7cb7a1p-2);
+    p = fma(p, r, -0x1.71547652f0ec0p-1);
+    p = fma(p, r, 0x1.71547652cb19ap+0);
+    const double lg = fma(p, r, T[16 + i] + k);                          // log2(x)
+    const double e = lg * y32;                                           // 32 * log2(x^y), <= 0
+    if (e < -4800.0) return 0.0f;                                        // x^y < 2^-150
+    double kd = e + 0x1.8p52;
+    const int32_t ki = (int32_t)(uint32_t)d2i(kd);
+    kd -= 0x1.8p52;
+    const double rr = (e - kd) * 0.03125;
+    double q = fma(0x1.3b2b2da63a0d5p-7, rr, 0x1.c6b170b9195b7p-5);    // kPowExpPoly
+    q = fma(q, rr, 0x1.ebfbdff804db7p-3);
+    q = fma(q, rr, 0x1.62e42fef68811p-1);
+    const double s = i2d((int64_t)((uint64_t)d2i(T[32 + (ki & 31)]) + ((uint64_t)(int64_t)(ki >> 5) << 52)));
+    return (float)fma(s, q * rr, s);
+}
+
 // apply_color_adjustments (:279-305), float32, numpy operation order.
-CRT_HD F3 colour(const Dev& d, F3 v) {
+CRT_HD F3 colour(const Dev& d, F3 v, const double* __restrict__ pow_tab) {
     if (d.col_sat) {
         float l = fadd(fadd(fmul(0.2126f, v.x), fmul(0.7152f, v.y)), fmul(0.0722f, v.z));
         v.x = sat(fadd(l, fmul(fsub(v.x, l), d.sat_f)));
@@ -189,11 +263,10 @@ CRT_HD F3 colour(const Dev& d, F3 v) {
         v.z = sat(fadd(fadd(fmul(fsub(v.z, 0.5f), d.contrast), 0.5f), d.brightness));
     }
     if (d.col_gamma) {
-        // numpy's float32 power (SVML) is within 1 ulp but not correctly rounded, so this
-        // stage cannot be matched bit for bit by any other implementation.
-        v.x = sat(powf(v.x, d.inv_gamma));
-        v.y = sat(powf(v.y, d.inv_gamma));
-        v.z = sat(powf(v.z, d.inv_gamma));
+        // cannot be matched bit for bit with numpy by any implementation (see pow_unit; DESIGN.md, parity)
+        v.x = sat(pow_unit(v.x, d.inv_gamma32, pow_tab));
+        v.y = sat(pow_unit(v.y, d.inv_gamma32, pow_tab));
+        v.z = sat(pow_unit(v.z, d.inv_gamma32, pow_tab));
     }
     return v;
 }
@@ -213,28 +286,30 @@ CRT_HD F3 text_blend(const Dev& d, F3 v, int y, int x) {
 CRT_HD F3 graded_input(const Dev& d, const uint8_t* __restrict__ in, int y, int x) {
     uint8_t b0, b1, b2;
     source_bytes(d, in, y, x, b0, b1, b2);
-    F3 v = colour(d, mk3(unit(b0), unit(b1), unit(b2)));
+    F3 v = colour(d, mk3(unit(b0), unit(b1), unit(b2)), d.pow_tab);
     if (d.text_mode == 1) v = text_blend(d, v, y, x);
     return v;
 }
 
 // Same, with the u8 -> float32 conversion read from a 256-entry table of unit() values
 // (identical results; saves three IEEE divisions per pixel in the fused kernel).
-CRT_HD F3 graded_input_lut(const Dev& d, const uint8_t* __restrict__ in, int y, int x, const float* __restrict__ unit_lut) {
+CRT_HD F3 graded_input_lut(const Dev& d, const uint8_t* __restrict__ in, int y, int x, const float* __restrict__ unit_lut,
+                           const double* __restrict__ pow_tab) {
     uint8_t b0, b1, b2;
     source_bytes(d, in, y, x, b0, b1, b2);
-    F3 v = colour(d, mk3(unit_lut[b0], unit_lut[b1], unit_lut[b2]));
+    F3 v = colour(d, mk3(unit_lut[b0], unit_lut[b1], unit_lut[b2]), pow_tab);
     if (d.text_mode == 1) v = text_blend(d, v, y, x);
     return v;
 }
 
 // Same for a pixel whose pixelate source (sy, sx) is already known (regular pixelate tables:
 // the block origin), skipping the index-table loads.
-CRT_HD F3 graded_source_lut(const Dev& d, const uint8_t* __restrict__ in, int sy, int sx, int y, int x, const float* __restrict__ unit_lut) {
+CRT_HD F3 graded_source_lut(const Dev& d, const uint8_t* __restrict__ in, int sy, int sx, int y, int x, const float* __restrict__ unit_lut,
+                            const double* __restrict__ pow_tab) {
     const uint8_t* row = in + (size_t)sy * d.W * 3;
     int x0 = sx, x2 = sx;
     if (d.aberr != 0) { x0 = wrap(sx - d.aberr_mod, d.W); x2 = wrap(sx + d.aberr_mod, d.W); }
-    F3 v = colour(d, mk3(unit_lut[row[x0 * 3 + 0]], unit_lut[row[sx * 3 + 1]], unit_lut[row[x2 * 3 + 2]]));
+    F3 v = colour(d, mk3(unit_lut[row[x0 * 3 + 0]], unit_lut[row[sx * 3 + 1]], unit_lut[row[x2 * 3 + 2]]), pow_tab);
     if (d.text_mode == 1) v = text_blend(d, v, y, x);
     return v;
 }

@@ -33,6 +33,9 @@ extern "C" int emu_process(const crt_params* p, int W, int H, const void* const*
     }
     t.dn_x = dn_x.data(); t.dn_y = dn_y.data(); t.up_x = up_x.data(); t.up_y = up_y.data();
     t.nz_x = nz_x.empty() ? nullptr : nz_x.data(); t.nz_y = nz_y.empty() ? nullptr : nz_y.data();
+    static double pow_tab[POW_TAB_DOUBLES];
+    fill_pow_table(pow_tab);
+    t.pow_tab = pow_tab;
     Dev d{};
     std::string e;
     int rc = derive_dev(*p, W, H, t, &d, &e);
@@ -102,4 +105,12 @@ extern "C" int emu_plan(const crt_params* p, int W, int H, const void* const* ta
     out[0] = pl.ok; out[1] = pl.th; out[2] = pl.cap_px; out[3] = pl.cap_aux; out[4] = (long long)pl.smem;
     strncpy(why, pl.why, whylen - 1); why[whylen - 1] = 0;
     return 0;
+}
+
+// pow_unit on arrays, for the accuracy test
+extern "C" void emu_pow_unit(const float* x, float* out, int n, double y) {
+    static double pow_tab[POW_TAB_DOUBLES];
+    fill_pow_table(pow_tab);
+    const double y32 = 32.0 * (double)(float)y;
+    for (int i = 0; i < n; ++i) out[i] = pow_unit(x[i], y32, pow_tab);
 }
