@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
     __shared__ float s_rows[2 * FMAX_ROWS], s_cols[2 * FMAX_COLS];
     __shared__ int s_ci[2 * FMAX_COLS], s_ri[2 * FMAX_ROWS];       // fast bloom: up-scale tap offsets per Q column / row
     __shared__ float s_cw[FMAX_COLS], s_rw[FMAX_ROWS];              // ... and weights (cv2.resize coordinates)
-    __shared__ int s_box[4];
+    __shared__ int s_box[4], s_geo[24];
     float* T = sm;                                  // [ph][pw][3] graded input (bloom source when thresholded)
     float* A = sm + g.cap_px * 3;                   // auxiliary: ds cells | row pass (+ T1 tile)
     const int tid = threadIdx.x, lane = tid & 31;
@@ -265,7 +265,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
     __syncthreads();
 
     // ---- phase 0: footprint of the tile in the pre-warp image ------------------------------
-    Box q;
     float xn[4] = {0.f, 0.f, 0.f, 0.f};
     if (WARP) {
 #pragma unroll
@@ -288,14 +287,35 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
         bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
         if (lane == 0) { atomicMin(&s_box[0], bx0); atomicMin(&s_box[1], by0); atomicMax(&s_box[2], bx1); atomicMax(&s_box[3], by1); }
         __syncthreads();
-        q.x0 = s_box[0]; q.y0 = s_box[1]; q.x1 = s_box[2]; q.y1 = s_box[3];
-    } else {
-        q.x0 = ox0; q.y0 = oy0; q.x1 = ox1; q.y1 = oy1;
     }
-    const bool q_empty = WARP && (q.x1 < q.x0 || q.y1 < q.y0);
-    Box cells{0, 0, -1, -1};
-    Box p = q;
-    if (!q_empty) p = grow_for_bloom(d, q, &cells);
+    // Tile geometry is the same for every thread: one thread derives it (integer divisions, cv2
+    // coordinate look-ups) and publishes it through shared memory.
+    if (tid == 0) {
+        Box q0;
+        if (WARP) { q0.x0 = s_box[0]; q0.y0 = s_box[1]; q0.x1 = s_box[2]; q0.y1 = s_box[3]; }
+        else { q0.x0 = ox0; q0.y0 = oy0; q0.x1 = ox1; q0.y1 = oy1; }
+        const bool empty = WARP && (q0.x1 < q0.x0 || q0.y1 < q0.y0);
+        Box c0{0, 0, -1, -1};
+        Box p0 = q0;
+        if (!empty) p0 = grow_for_bloom(d, q0, &c0);
+        const int ps0 = (d.pix_uniform > 1 && d.text_mode != 1) ? d.pix_uniform : 1;
+        int* gq = s_geo;
+        gq[0] = q0.x0; gq[1] = q0.y0; gq[2] = q0.x1; gq[3] = q0.y1;
+        gq[4] = p0.x0; gq[5] = p0.y0; gq[6] = p0.x1; gq[7] = p0.y1;
+        gq[8] = c0.x0; gq[9] = c0.y0; gq[10] = c0.x1; gq[11] = c0.y1;
+        gq[12] = empty; gq[13] = ps0;
+        gq[14] = p0.x0 / ps0; gq[15] = p0.y0 / ps0;                       // first unique source column / row
+        gq[16] = p0.x1 / ps0 - gq[14] + 1; gq[17] = p0.y1 / ps0 - gq[15] + 1;
+        gq[18] = (int)make_magic(gq[16]);                                  // / nux
+        gq[19] = (int)make_magic(box_w(c0));                               // / dw
+        gq[20] = (int)make_magic(empty ? 1 : box_w(q0));                   // / qw
+        gq[21] = (int)make_magic(BLOOM == 2 ? box_w(q0) * 3 : 1);          // / row-pass length
+    }
+    __syncthreads();
+    Box q{s_geo[0], s_geo[1], s_geo[2], s_geo[3]};
+    const Box p{s_geo[4], s_geo[5], s_geo[6], s_geo[7]};
+    const Box cells{s_geo[8], s_geo[9], s_geo[10], s_geo[11]};
+    const bool q_empty = s_geo[12] != 0;
     const int pw = q_empty ? 0 : box_w(p), ph = q_empty ? 0 : box_h(p);
     const int qw = q_empty ? 0 : box_w(q), qh = q_empty ? 0 : box_h(q);
     // planning guarantees the region fits; a violated bound must never corrupt memory
@@ -309,10 +329,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
     const int cw = BLOOM == 2 ? qw : 0;             // row-pass columns
     float* T1 = A + ph * cw * 3;                    // [th][FTW][3], only BLOOM==2 && thr_on
     if (!q_empty) {
-        const int ps = (d.pix_uniform > 1 && d.text_mode != 1) ? d.pix_uniform : 1;
-        const int ux0 = p.x0 / ps, uy0 = p.y0 / ps;
-        const int nux = p.x1 / ps - ux0 + 1, nuy = p.y1 / ps - uy0 + 1;
-        const unsigned magic = make_magic(nux);
+        const int ps = s_geo[13], ux0 = s_geo[14], uy0 = s_geo[15], nux = s_geo[16], nuy = s_geo[17];
+        const unsigned magic = (unsigned)s_geo[18];
         for (int u = tid; u < nux * nuy; u += NT) {
             const int uy = fastdiv(u, magic), ux = u - uy * nux;
             const int xa = imax((ux0 + ux) * ps, p.x0), xe = imin((ux0 + ux) * ps + ps - 1, p.x1);
@@ -367,7 +385,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
         return mk3(lerp_cv(h0[0], h1[0], w), lerp_cv(h0[1], h1[1], w), lerp_cv(h0[2], h1[2], w));
     };
     if (BLOOM == 1 && !q_empty) {
-        const unsigned magic = make_magic(dw);
+        const unsigned magic = (unsigned)s_geo[19];
         for (int u = tid; u < dw * dh; u += NT) {
             const int r = fastdiv(u, magic), c = u - r * dw;
             const Lerp1 cy = down_coord(d, d.dn_y, cells.y0 + r), cx = down_coord(d, d.dn_x, cells.x0 + c);
@@ -383,7 +401,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
         }
         __syncthreads();
         // horizontal half of the 2x up-scale (cv2.resize works rows first), once per (cell row, Q column)
-        const unsigned magic_q = make_magic(qw);
+        const unsigned magic_q = (unsigned)s_geo[20];
         for (int u = tid; u < dh * qw; u += NT) {
             const int j = fastdiv(u, magic_q), c = u - j * qw;
             const float* dr = A + j * dw * 3;
@@ -398,7 +416,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
         // row pass over every region row, for the tile's columns; REPLICATE = clamped column index
         const int K = d.ksize, rad = K >> 1;
         const int rowlen = cw * 3;
-        const unsigned magic = make_magic(rowlen);
+        const unsigned magic = (unsigned)s_geo[21];
         for (int u = tid; u < ph * rowlen; u += NT) {
             const int r = fastdiv(u, magic), e = u - r * rowlen;
             const int c = fastdiv(e, 0x55555556u /* 2^32/3 + 1 */), ch = e - c * 3, x = q.x0 + c;
@@ -423,7 +441,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
 
     // ---- phase 3 [warp]: stages 5-10 in place over Q ----------------------------------------------
     if (WARP && !q_empty) {
-        const unsigned magic = make_magic(qw);
+        const unsigned magic = (unsigned)s_geo[20];
         for (int u = tid; u < qw * qh; u += NT) {
             const int r = fastdiv(u, magic), c = u - r * qw;
             const int y = q.y0 + r, x = q.x0 + c;

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
     __shared__ float s_unit[256];
     __shared__ double s_pow[POW_TAB_DOUBLES];
     __shared__ float s_rows[2 * 64], s_cols[2 * FTW];
+    __shared__ int s_geo[8];
     const int PH = th + 2 * R;                      // padded rows; th is even, so PH is even
     const int pitch = PH;                           // floats between consecutive x in St
     float* St = sm;                                 // [3][PW][pitch]  thresholded source, transposed
@@ -80,6 +81,15 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
     float taps[K];
 #pragma unroll
     for (int i = 0; i < K; ++i) taps[i] = d.taps[i];
+    if (tid == 0) {          // uniform integer divisions once per CTA
+        const int ps0 = (d.pix_uniform > 1 && d.text_mode != 1) ? d.pix_uniform : 1;
+        const int jx0 = imax(ox0 - K / 2, 0), jx1 = imin(ox1 + K / 2, d.W - 1), jy0 = imax(oy0 - K / 2, 0), jy1 = imin(oy1 + K / 2, d.H - 1);
+        s_geo[0] = ps0; s_geo[1] = jx0 / ps0; s_geo[2] = jy0 / ps0;
+        s_geo[3] = jx1 / ps0 - s_geo[1] + 1; s_geo[4] = jy1 / ps0 - s_geo[2] + 1;
+        s_geo[5] = (int)make_magic(s_geo[3]);
+        s_geo[6] = (int)make_magic((th + 2 * (K / 2)) >> 1);
+        s_geo[7] = (int)make_magic(th >> 2);
+    }
     __syncthreads();
     MaskTabs mt{s_rows, s_cols, s_rows + 64, s_cols + FTW};
 
@@ -88,10 +98,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
     const int PWe = ox1 - ox0 + 1 + 2 * R, PHe = oy1 - oy0 + 1 + 2 * R;
     const int ix0 = imax(px0, 0), ix1 = imin(ox1 + R, d.W - 1), iy0 = imax(py0, 0), iy1 = imin(oy1 + R, d.H - 1);
     {
-        const int ps = (d.pix_uniform > 1 && d.text_mode != 1) ? d.pix_uniform : 1;
-        const int ux0 = ix0 / ps, uy0 = iy0 / ps;
-        const int nux = ix1 / ps - ux0 + 1, nuy = iy1 / ps - uy0 + 1;
-        const unsigned magic = make_magic(nux);
+        const int ps = s_geo[0], ux0 = s_geo[1], uy0 = s_geo[2], nux = s_geo[3], nuy = s_geo[4];
+        const unsigned magic = (unsigned)s_geo[5];
         for (int u = tid; u < nux * nuy; u += NT) {
             const int uy = fastdiv(u, magic), ux = u - uy * nux;
             const int xa = imax((ux0 + ux) * ps, ix0), xe = imin((ux0 + ux) * ps + ps - 1, ix1);
@@ -139,7 +147,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
     // ---- phase 2a: row pass, 4 outputs along x for a pair of rows per task ------------------------------
     {
         const int nyp = PH >> 1;
-        const unsigned magic = make_magic(nyp);
+        const unsigned magic = (unsigned)s_geo[6];
         const int hp = pitch >> 1;                                  // float2 stride between consecutive x
         for (int u = tid; u < 3 * (FTW / 4) * nyp; u += NT) {
             const int t = fastdiv(u, magic), yp = u - t * nyp;
@@ -159,7 +167,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
     // ---- phase 2b: column pass, 4 outputs along y for a pair of columns per task ----------------------------
     {
         const int nyb = th >> 2;
-        const unsigned magic = make_magic(nyb);
+        const unsigned magic = (unsigned)s_geo[7];
         for (int u = tid; u < 3 * nyb * (FTW / 2); u += NT) {
             const int xp = u & (FTW / 2 - 1), t = u >> 5;           // FTW / 2 == 32
             const int ch = fastdiv(t, magic), yblk = t - ch * nyb;
