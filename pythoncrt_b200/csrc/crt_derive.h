@@ -139,6 +139,7 @@ inline int derive_dev(const crt_params& p, int W, int H, const TablePtrs& t, Dev
     d.warp_cx = (float)cx; d.warp_cy = (float)cy;
     d.warp_dx = (float)fmax(1.0, cx); d.warp_dy = (float)fmax(1.0, cy);
     d.warp_k = (float)(p.warp_strength * 0.5);
+    d.warp_mono = d.warp_k > -0.2f;      // d(map)/dx = 1 + k (3 x^2 + y^2) > 0 for |x|, |y| <= 1
     d.persist = (float)p.persistence; d.persist_q = (float)(1.0 - p.persistence);
     *out = d;
     return CRT_OK;

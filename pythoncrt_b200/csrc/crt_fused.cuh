@@ -84,6 +84,18 @@ CRT_HD Box grow_for_bloom(const Dev& d, const Box& q, Box* cells) {
     return p;
 }
 
+// Footprint of a tile from the min/max tap coordinates (ix, ix+1, iy, iy+1 over the sampled
+// output pixels): clipped to the image (taps outside contribute 0 and are never read); when the
+// extremes come from the perimeter only (warp_mono) one pixel of slack covers float rounding.
+CRT_HD Box footprint_box(const Dev& d, int x0, int y0, int x1, int y1, bool* empty) {
+    const int m = d.warp_mono ? 1 : 0;
+    *empty = x0 > x1 || x0 > d.W - 1 || x1 < 0 || y0 > d.H - 1 || y1 < 0;
+    Box q;
+    q.x0 = imax(x0 - m, 0); q.x1 = imin(x1 + m, d.W - 1);
+    q.y0 = imax(y0 - m, 0); q.y1 = imin(y1 + m, d.H - 1);
+    return q;
+}
+
 // Warp map with the per-row / per-column normalised coordinates hoisted (same float32
 // operations and order as warp_taps, crt_math.cuh).
 CRT_HD float warp_norm(float v, float c, float dv) { return fdiv(fsub(v, c), dv); }
@@ -270,15 +282,24 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
 #pragma unroll
         for (int k = 0; k < 4; ++k) xn[k] = warp_norm((float)(xb + k), d.warp_cx, d.warp_dx);
         int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
-        for (int y = oy0 + trow; y <= oy1; y += NT / FROW_THREADS) {
-            const float yn = warp_norm((float)y, d.warp_cy, d.warp_dy);
+        if (d.warp_mono) {
+            // monotone map: the extremes over the tile are attained on its perimeter
+            const int tw = ox1 - ox0 + 1, thh = oy1 - oy0 + 1, nper = 2 * tw + 2 * thh;
+            for (int i = tid; i < nper; i += NT) {
+                int x, y;
+                if (i < 2 * tw) { x = ox0 + (i < tw ? i : i - tw); y = i < tw ? oy0 : oy1; }
+                else { const int j = i - 2 * tw; y = oy0 + (j < thh ? j : j - thh); x = j < thh ? ox0 : ox1; }
+                const Taps t = warp_taps_n(d, warp_norm((float)x, d.warp_cx, d.warp_dx), warp_norm((float)y, d.warp_cy, d.warp_dy));
+                bx0 = imin(bx0, t.ix); bx1 = imax(bx1, t.ix + 1); by0 = imin(by0, t.iy); by1 = imax(by1, t.iy + 1);
+            }
+        } else {
+            for (int y = oy0 + trow; y <= oy1; y += NT / FROW_THREADS) {
+                const float yn = warp_norm((float)y, d.warp_cy, d.warp_dy);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (xb + k <= ox1) {
-                    const Taps t = warp_taps_n(d, xn[k], yn);
-                    if (t.ix + 1 >= 0 && t.ix < d.W && t.iy + 1 >= 0 && t.iy < d.H) {      // only taps inside the image are read
-                        bx0 = imin(bx0, imax(t.ix, 0)); bx1 = imax(bx1, imin(t.ix + 1, d.W - 1));
-                        by0 = imin(by0, imax(t.iy, 0)); by1 = imax(by1, imin(t.iy + 1, d.H - 1));
+                for (int k = 0; k < 4; ++k) {
+                    if (xb + k <= ox1) {
+                        const Taps t = warp_taps_n(d, xn[k], yn);
+                        bx0 = imin(bx0, t.ix); bx1 = imax(bx1, t.ix + 1); by0 = imin(by0, t.iy); by1 = imax(by1, t.iy + 1);
                     }
                 }
             }
@@ -292,9 +313,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
     // coordinate look-ups) and publishes it through shared memory.
     if (tid == 0) {
         Box q0;
-        if (WARP) { q0.x0 = s_box[0]; q0.y0 = s_box[1]; q0.x1 = s_box[2]; q0.y1 = s_box[3]; }
-        else { q0.x0 = ox0; q0.y0 = oy0; q0.x1 = ox1; q0.y1 = oy1; }
-        const bool empty = WARP && (q0.x1 < q0.x0 || q0.y1 < q0.y0);
+        bool empty = false;
+        if (WARP) {
+            q0 = footprint_box(d, s_box[0], s_box[1], s_box[2], s_box[3], &empty);
+        } else { q0.x0 = ox0; q0.y0 = oy0; q0.x1 = ox1; q0.y1 = oy1; }
         Box c0{0, 0, -1, -1};
         Box p0 = q0;
         if (!empty) p0 = grow_for_bloom(d, q0, &c0);
@@ -601,16 +623,18 @@ inline FusedPlan plan_fused(const Dev& hd, bool glitch_on) {
                 Box o{tx * FTW, ty * th, imin((tx + 1) * FTW, d.W) - 1, imin((ty + 1) * th, d.H) - 1};
                 Box q = o;
                 if (d.warp_on) {
-                    q = Box{0x7fffffff, 0x7fffffff, -0x7fffffff, -0x7fffffff};
-                    for (int y = o.y0; y <= o.y1; ++y)
+                    int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -0x7fffffff, y1 = -0x7fffffff;
+                    for (int y = o.y0; y <= o.y1; ++y) {
+                        const bool edge_row = y == o.y0 || y == o.y1;
                         for (int x = o.x0; x <= o.x1; ++x) {
+                            if (d.warp_mono && !edge_row && x != o.x0 && x != o.x1) continue;      // same sampling as the kernel
                             Taps t = warp_taps_n(d, xn[x], yn[y]);
-                            if (t.ix + 1 >= 0 && t.ix < d.W && t.iy + 1 >= 0 && t.iy < d.H) {
-                                q.x0 = imin(q.x0, imax(t.ix, 0)); q.x1 = imax(q.x1, imin(t.ix + 1, d.W - 1));
-                                q.y0 = imin(q.y0, imax(t.iy, 0)); q.y1 = imax(q.y1, imin(t.iy + 1, d.H - 1));
-                            }
+                            x0 = imin(x0, t.ix); x1 = imax(x1, t.ix + 1); y0 = imin(y0, t.iy); y1 = imax(y1, t.iy + 1);
                         }
-                    if (q.x1 < q.x0 || q.y1 < q.y0) continue;
+                    }
+                    bool empty = false;
+                    q = footprint_box(d, x0, y0, x1, y1, &empty);
+                    if (empty) continue;
                 }
                 Box cells{0, 0, -1, -1};
                 Box p = grow_for_bloom(d, q, &cells);

@@ -153,6 +153,7 @@ struct Dev {
     const Lerp1* nz_x; const Lerp1* nz_y;   // [W], [H] when grain > 1, else null
     // stage 11: warp (:331-348)
     int warp_on; float warp_cx, warp_cy, warp_dx, warp_dy, warp_k;
+    int warp_mono;               // map is monotone in x and in y over the frame: a tile's footprint is spanned by its perimeter
     // stage 14: persistence (:687-694 / :1086-1096)
     float persist, persist_q;    // p and float32(1 - p)
 };
