@@ -67,6 +67,9 @@ CASES = [
     _c("gauss_k3", dict(fast_bloom=False, bloom_sigma=0.4, bloom_strength=0.5)),
     _c("gauss_k5", dict(fast_bloom=False, bloom_sigma=0.7, bloom_strength=0.5)),
     _c("gauss_k25_thr", dict(fast_bloom=False, bloom_sigma=4.0, bloom_strength=1.0, bloom_threshold=0.3)),
+    _c("gauss_k13", dict(fast_bloom=False, bloom_sigma=2.0, bloom_strength=0.4, bloom_threshold=0.2)),
+    _c("gauss_k61", dict(fast_bloom=False, bloom_sigma=10.0, bloom_strength=0.6), h=112, w=160),
+    _c("warp_gauss_noglitch", dict(fast_bloom=False, bloom_sigma=1.5, bloom_strength=0.35, warp_strength=0.3)),
     _c("scan_period3_angle", dict(scanline_period_px=3.0, scanline_angle=-20.0, scanline_thickness=0.5, scanline_speed_px_s=47.0)),
     _c("scan_period5_1d", dict(scanline_period_px=5.0, scanline_speed_px_s=13.0)),
     _c("flicker_only", dict(flicker_strength=1.0, flicker_hz=7.0)),
