@@ -35,15 +35,17 @@ GAUSS = dict(fast_bloom=False, bloom_sigma=1.5, bloom_threshold=0.7, bloom_stren
 WARP = dict(warp_strength=0.15, scanline_angle=3.0, scanline_thickness=1.2)
 LIVE = dict(noise_strength=1.5, grain_size=2, flicker_strength=0.25, flicker_hz=60.0, glitch_amp_px=16, glitch_height_frac=0.25)
 WORKLOADS = {
-    "cfg1": dict(desc="CLI default chain, noise off, 640x480", w=640, h=480, frames=64, fps=30.0, over={}, cpu_frames=64),
+    "cfg1": dict(desc="CLI default chain, noise off, 640x480", w=640, h=480, frames=64, fps=30.0, over={}, cpu_frames=640),
+    "default4k": dict(desc="CLI default chain (scanline+triad+aberration+fast bloom+vignette+persistence, noise off) at 4K — the north_star target chain",
+                      w=3840, h=2160, frames=300, fps=30.0, over={}, cpu_frames=24),
     "cfg2": dict(desc="1080p full chain, gaussian bloom sigma 1.5 thr 0.7 + colour grading", w=1920, h=1080, frames=600, fps=30.0,
-                 over={**GAUSS, **GRADE}, cpu_frames=12),
+                 over={**GAUSS, **GRADE}, cpu_frames=96),
     "cfg3": dict(desc="4K, warp 0.15, scanline angle 3.0, aberration, persistence", w=3840, h=2160, frames=600, fps=30.0,
-                 over=WARP, cpu_frames=6),
+                 over=WARP, cpu_frames=16),
     "cfg4": dict(desc="4K60 full chain incl. noise/grain/flicker/glitch", w=3840, h=2160, frames=600, fps=60.0,
-                 over={**GAUSS, **GRADE, **WARP, **LIVE}, cpu_frames=4),
+                 over={**GAUSS, **GRADE, **WARP, **LIVE}, cpu_frames=8),
     "cfg5": dict(desc="8K full chain, gaussian bloom sigma 4", w=7680, h=4320, frames=150, fps=30.0,
-                 over={**GRADE, **WARP, **LIVE, **dict(fast_bloom=False, bloom_sigma=4.0, bloom_strength=0.3)}, cpu_frames=2),
+                 over={**GRADE, **WARP, **LIVE, **dict(fast_bloom=False, bloom_sigma=4.0, bloom_strength=0.3)}, cpu_frames=3),
 }
 FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md
 

@@ -349,9 +349,8 @@ CRT_HD F3 add_bloom(const Dev& d, F3 v, F3 bl) {
 }
 
 // ---- stage 6: triad -------------------------------------------------------------
-CRT_HD int lut_index(float v) {           // (np.clip(v,0,1) * 1024).astype(int32), clipped
-    int i = (int)fmul(sat(v), 1024.0f);
-    return i > 1024 ? 1024 : i;
+CRT_HD int lut_index(float v) {           // (np.clip(v,0,1) * 1024).astype(int32); the reference's outer clip to
+    return (int)fmul(sat(v), 1024.0f);    // [0, 1024] is a no-op: the product of a value in [0, 1] never exceeds 1024
 }
 CRT_HD F3 triad(const Dev& d, F3 v, int x, const float* __restrict__ fwd, const float* __restrict__ inv) {
     const float* m = d.triad_cols + (size_t)x * 3;
