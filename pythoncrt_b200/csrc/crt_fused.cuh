@@ -45,6 +45,7 @@ struct FusedPlan {
     int nt = 256;                       // threads per CTA (512 for tall tiles: same shared memory, twice the resident warps)
     int cap_px = 0;                     // capacity of the P-region buffer in pixels
     int cap_aux = 0;                    // floats of the auxiliary buffer (ds cells / row pass / T1 tile)
+    int ps2 = 0;                        // 1: the pixel_size-2 block kernel (crt_fused_ps2.cuh)
     int gauss_k = 0;                    // != 0: the packed-FP32 gaussian kernel (crt_fused_gauss.cuh) with this tap count
     size_t smem = 0;
 };
@@ -589,6 +590,11 @@ inline FusedPlan plan_fused(const Dev& hd, bool glitch_on) {
     if (glitch_on) { pl.why = "glitch gather is handled by the staged kernels"; return pl; }
     if (d.warp_on && d.bloom_mode == 2) { pl.why = "warp + gaussian bloom is handled by the staged kernels"; return pl; }
     if ((size_t)d.W * d.H * 3 >= ((size_t)1 << 31)) { pl.why = "frame too large for 32-bit indexing"; return pl; }
+    if (d.pix_uniform == 2 && d.even_dims && (d.W & 3) == 0 && !d.warp_on && !glitch_on && d.text_mode == 0 && d.bloom_mode != 2 &&
+        !env_int("CRT_NO_PS2", 0)) {            // == fused_ps2_supported (crt_fused_ps2.cuh): the default-chain block kernel
+        pl.ok = true; pl.why = ""; pl.ps2 = 1; pl.th = 32; pl.nt = 256; pl.smem = 0;
+        return pl;
+    }
     // grid sizing: at least two waves of CTAs over the 148 SMs when the frame allows it
     auto enough_tiles = [&](int th) { return (long long)((d.W + FTW - 1) / FTW) * ((d.H + th - 1) / th) >= 2 * 148; };
     if (d.bloom_mode == 2 && !d.warp_on && fused_gauss_supported(d.ksize) && d.W >= 4 && d.H >= 4) {

@@ -1,0 +1,134 @@
+// crt_fused_ps2.cuh — fused tile kernel specialised for the reference's DEFAULT chain
+// shape: pixel_size 2 (regular pixelate tables, even frame size), fast bloom or none, no
+// warp / glitch / text layer.  This is the chain BASELINE.json's north_star names.
+//
+// With pixel_size 2 every aligned 2x2 block of the frame shows ONE source pixel, and the
+// fast bloom's 2x down-scale cell of that block is exactly that pixel's value
+// (fma(s - s, 0.5, s) == s in cv2.resize's arithmetic).  The tile therefore needs only one
+// graded value per block (34 x 18 blocks for a 64 x 32 tile instead of 68 x 36 pixels), no
+// down-scale pass, and each thread produces a 4 x 2 pixel patch from a 4 x 3 neighbourhood
+// of block values held in registers: cv2's 2x up-scale (rows first, then columns, every
+// lerp fma(q - p, w, p) with w = 0.25 / 0.75) costs ~16 instructions per pixel.  Clamped
+// block indices reproduce cv2.resize's edge rule exactly (a lerp between equal values
+// returns the value).  Everything else (triad LUT, masks, persistence, stores) is shared
+// with the general fused kernel (crt_fused.cuh).  ~25 KB static shared memory, no dynamic.
+#pragma once
+#include "crt_fused.cuh"
+
+namespace crt {
+
+constexpr int P2_TW = 64, P2_TH = 32;                 // output tile
+constexpr int P2_BW = P2_TW / 2 + 2, P2_BH = P2_TH / 2 + 2;   // blocks incl. one halo block each side (34 x 18)
+constexpr int P2_NT = 256;                            // 16 x 16 threads, 4 x 2 pixels each
+
+CRT_HD bool fused_ps2_supported(const Dev& d, bool glitch_on) {
+    return d.pix_uniform == 2 && d.even_dims && (d.W & 3) == 0 && !d.warp_on && !glitch_on && d.text_mode == 0 && d.bloom_mode != 2;
+}
+
+#if defined(__CUDACC__)
+
+template <bool BLOOM>
+__global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                     float* __restrict__ state, float* __restrict__ q_out, int has_prev) {
+    __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
+    __shared__ float s_unit[256];
+    __shared__ double s_pow[POW_TAB_DOUBLES];
+    __shared__ float s_rows[2 * P2_TH], s_cols[2 * P2_TW];
+    __shared__ __align__(16) float Us[3][P2_BH][P2_BW + 2];      // graded block values, planar (row pitch 36 floats)
+    __shared__ __align__(16) float Ss[3][P2_BH][P2_BW + 2];      // thresholded bloom source (only when the threshold is on)
+    const int tid = threadIdx.x;
+    const int ox0 = blockIdx.x * P2_TW, oy0 = blockIdx.y * P2_TH;
+    const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + P2_TH, d.H) - 1;
+
+    const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
+    const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
+    if (d.triad_mode >= 2) {
+        reinterpret_cast<float4*>(s_fwd)[tid] = reinterpret_cast<const float4*>(lut_a)[tid];
+        reinterpret_cast<float4*>(s_inv)[tid] = reinterpret_cast<const float4*>(lut_b)[tid];
+        if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
+    }
+    s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
+    if (d.col_gamma && tid < POW_TAB_DOUBLES) s_pow[tid] = d.pow_tab[tid];
+    MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
+    if (tid < P2_TH) {
+        const int y = oy0 + tid;
+        if (d.scan_mode == 1) mt.row_scan[tid] = scan_row(d, f, y);
+        else if (d.scan_mode == 2) { double t = ((double)y + f.phase) * d.scan_inv_period; mt.row_scan[tid] = (float)(t - floor(t)); }
+        if (d.vig_mode == 1) { const float ny = ((float)y - d.vig_cy) * d.vig_iry; mt.row_vig[tid] = ny * ny; }
+    } else if (tid >= 64 && tid < 64 + P2_TW) {
+        const int c = tid - 64, x = ox0 + c;
+        if (d.scan_mode == 2) { double t = (d.scan_tan * (double)x) * d.scan_inv_period; mt.col_scan[c] = (float)(t - floor(t)); }
+        if (d.vig_mode == 1) { const float nx = ((float)x - d.vig_cx) * d.vig_irx; mt.col_vig[c] = nx * nx; }
+    }
+    __syncthreads();        // s_unit / s_pow ready
+
+    // ---- phase 1: one graded value per 2x2 block (tile + one halo block, clamped = cv2's edge rule) ----
+    const int gbx0 = (ox0 >> 1) - 1, gby0 = (oy0 >> 1) - 1;
+    for (int u = tid; u < P2_BW * P2_BH; u += P2_NT) {
+        const int bj = u / P2_BW, bi = u - bj * P2_BW;
+        const int gbi = imin(imax(gbx0 + bi, 0), d.hw - 1), gbj = imin(imax(gby0 + bj, 0), d.hh - 1);
+        const F3 v1 = graded_source_lut(d, in, 2 * gbj, 2 * gbi, 2 * gbj, 2 * gbi, s_unit, s_pow);
+        Us[0][bj][bi] = v1.x; Us[1][bj][bi] = v1.y; Us[2][bj][bi] = v1.z;
+        if (BLOOM && d.thr_on) {
+            const F3 s = bloom_src(d, v1);
+            Ss[0][bj][bi] = s.x; Ss[1][bj][bi] = s.y; Ss[2][bj][bi] = s.z;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 4: every thread owns 4 x 2 output pixels = two blocks side by side ------------------------
+    const int tx = tid & 15, ty = tid >> 4;
+    const int xb = ox0 + 4 * tx, y0 = oy0 + 2 * ty;
+    if (xb > ox1 || y0 > oy1) return;
+    const int bi = 2 * tx + 1, bj = ty + 1;                 // first of the two blocks, in halo coordinates
+    float bl[2][4][3];                                      // bloom of the 8 pixels
+    float t1[2][3];                                         // graded value of the two blocks
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        t1[0][ch] = Us[ch][bj][bi]; t1[1][ch] = Us[ch][bj][bi + 1];
+        if (BLOOM) {
+            const float (*src)[P2_BW + 2] = d.thr_on ? Ss[ch] : Us[ch];
+            float h[3][4];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                // cells bi-1 .. bi+2 of block row bj-1+r (bi - 1 is even: 8-byte aligned pairs)
+                const float2 ca = *reinterpret_cast<const float2*>(&src[bj - 1 + r][bi - 1]);
+                const float2 cb = *reinterpret_cast<const float2*>(&src[bj - 1 + r][bi + 1]);
+                const float d01 = fsub(ca.y, ca.x), d12 = fsub(cb.x, ca.y), d23 = fsub(cb.y, cb.x);
+                h[r][0] = ffma(d01, 0.75f, ca.x);           // x = 2i     : lerp(c[i-1], c[i], 0.75)
+                h[r][1] = ffma(d12, 0.25f, ca.y);           // x = 2i + 1 : lerp(c[i], c[i+1], 0.25)
+                h[r][2] = ffma(d12, 0.75f, ca.y);           // x = 2i + 2 : lerp(c[i], c[i+1], 0.75)
+                h[r][3] = ffma(d23, 0.25f, cb.x);           // x = 2i + 3 : lerp(c[i+1], c[i+2], 0.25)
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                bl[0][k][ch] = ffma(fsub(h[1][k], h[0][k]), 0.75f, h[0][k]);     // y = 2j     : lerp(row j-1, row j, 0.75)
+                bl[1][k][ch] = ffma(fsub(h[2][k], h[1][k]), 0.25f, h[1][k]);     // y = 2j + 1 : lerp(row j, row j+1, 0.25)
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int y = y0 + r;
+        if (y > oy1) break;
+        auto pixel = [&](int yy, int x, int k) -> F3 {
+            F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
+            if (BLOOM) v = add_bloom(d, v, mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]));
+            return after_bloom_fast(d, f, v, yy, x, s_fwd, s_inv, mt, yy - oy0, x - ox0);
+        };
+        finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
+    }
+}
+
+inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
+                         cudaStream_t st, int* launches) {
+    dim3 grid((d.W + P2_TW - 1) / P2_TW, (d.H + P2_TH - 1) / P2_TH);
+    if (d.bloom_mode == 1) k_fused_ps2<true><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
+    else k_fused_ps2<false><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
+    ++*launches;
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace crt
