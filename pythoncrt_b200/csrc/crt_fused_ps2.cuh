@@ -27,7 +27,11 @@ CRT_HD bool fused_ps2_supported(const Dev& d, bool glitch_on) {
 
 #if defined(__CUDACC__)
 
-template <bool BLOOM>
+// FAST: the per-pixel tail is specialised for the default chain's feature set — regular triad mask
+// through the composite tables, per-row scanlines (or none), analytic vignette (or none), optional
+// flicker folded into the row factor, no noise.  Tiles that touch the mask's irregular edge columns
+// and every other feature set take the general tail (after_bloom_fast).
+template <bool BLOOM, bool FAST>
 __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                      float* __restrict__ state, float* __restrict__ q_out, int has_prev) {
     __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
@@ -107,6 +111,38 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
             }
         }
     }
+    const bool fast = FAST && ox0 >= d.comp_x0 && ox1 <= d.comp_x1;        // block-uniform
+    if (fast) {
+        float cvig[4];
+        const float* tab[4][3];                                     // composite table (bright / dim) per column and channel
+        const int ph0 = xb - 3 * (int)__umulhi((unsigned)xb, 0x55555556u);     // xb % 3
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            cvig[k] = d.vig_mode ? mt.col_vig[xb - ox0 + k] : 0.f;
+            const int ph = (ph0 + k) % 3;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) tab[k][ch] = ph == ch ? s_fwd : s_inv;
+        }
+        const float vs = d.vig_mode ? d.vig_strength : 0.f;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int y = y0 + r;
+            if (y > oy1) break;
+            const float rfac = (d.scan_mode ? mt.row_scan[y - oy0] : 1.0f) * (f.flicker_on ? f.flicker : 1.0f);
+            const float rvig = d.vig_mode ? mt.row_vig[y - oy0] : 0.f;
+            auto pixel = [&](int, int, int k) -> F3 {
+                F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
+                if (BLOOM) v = add_bloom(d, v, mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]));
+                const float m = rfac * __fmaf_rn(-vs, __saturatef(rvig + cvig[k]), 1.0f);
+                v.x = __saturatef(tab[k][0][lut_index(v.x)] * m);
+                v.y = __saturatef(tab[k][1][lut_index(v.y)] * m);
+                v.z = __saturatef(tab[k][2][lut_index(v.z)] * m);
+                return v;
+            };
+            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
+        }
+        return;
+    }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int y = y0 + r;
@@ -123,8 +159,14 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
 inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
                          cudaStream_t st, int* launches) {
     dim3 grid((d.W + P2_TW - 1) / P2_TW, (d.H + P2_TH - 1) / P2_TH);
-    if (d.bloom_mode == 1) k_fused_ps2<true><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
-    else k_fused_ps2<false><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
+    const bool fast = d.triad_mode == 2 && d.triad_comp && d.scan_mode <= 1 && d.vig_mode <= 1 && !d.noise_on;
+    if (d.bloom_mode == 1) {
+        if (fast) k_fused_ps2<true, true><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
+        else k_fused_ps2<true, false><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
+    } else {
+        if (fast) k_fused_ps2<false, true><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
+        else k_fused_ps2<false, false><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
+    }
     ++*launches;
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
