@@ -14,6 +14,7 @@
 // with the general fused kernel (crt_fused.cuh).  ~25 KB static shared memory, no dynamic.
 #pragma once
 #include "crt_fused.cuh"
+#include "crt_tma.cuh"
 
 namespace crt {
 
@@ -156,10 +157,210 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
     }
 }
 
+
+// ---- TMA variant ---------------------------------------------------------------------------------
+// Same arithmetic; the persistence state tile is fetched with one bulk asynchronous copy per row
+// (cp.async.bulk, completion on an mbarrier) issued before any other work, so the 12 B/px state read
+// overlaps the block grading; results are staged in shared memory and leave with bulk stores (state
+// rows and packed uint8 rows).  No thread issues a global load/store for state or output.
+// Requires W % 16 == 0 (16-byte multiples for the uint8 rows).
+constexpr int P2_STATE_BYTES = P2_TH * P2_TW * 3 * 4, P2_OUT_BYTES = P2_TH * P2_TW * 3, P2_US_BYTES = 3 * P2_BH * (P2_BW + 2) * 4;
+
+template <typename PixelFn>
+__device__ __forceinline__ void finish_quad_smem(const Dev& d, float* __restrict__ srow, uint8_t* __restrict__ orow, bool to_u8, int has_prev,
+                                                 int y, int xb, PixelFn&& pixel) {
+    const float pp = d.persist, pq = d.persist_q;
+    float4* sp = reinterpret_cast<float4*>(srow);
+    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa, pc = pa;
+    if (has_prev) { pa = sp[0]; pb = sp[1]; pc = sp[2]; }
+    const float prev[12] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, pc.x, pc.y, pc.z, pc.w};
+    float res[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        F3 v = pixel(y, xb + k, k);
+        if (has_prev) { v.x = blend_fast(prev[k * 3], v.x, pp, pq); v.y = blend_fast(prev[k * 3 + 1], v.y, pp, pq); v.z = blend_fast(prev[k * 3 + 2], v.z, pp, pq); }
+        res[k * 3] = v.x; res[k * 3 + 1] = v.y; res[k * 3 + 2] = v.z;
+    }
+    sp[0] = make_float4(res[0], res[1], res[2], res[3]);
+    sp[1] = make_float4(res[4], res[5], res[6], res[7]);
+    sp[2] = make_float4(res[8], res[9], res[10], res[11]);
+    if (to_u8) {
+        uint32_t* op = reinterpret_cast<uint32_t*>(orow);
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            op[j] = quantise_fast(res[j * 4]) | (quantise_fast(res[j * 4 + 1]) << 8) | (quantise_fast(res[j * 4 + 2]) << 16) |
+                    (quantise_fast(res[j * 4 + 3]) << 24);
+    }
+}
+
+template <bool BLOOM, bool FAST>
+__global__ void __launch_bounds__(P2_NT) k_fused_ps2_tma(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                         float* __restrict__ state, float* __restrict__ q_out, int has_prev) {
+    extern __shared__ __align__(128) unsigned char dsm[];
+    float* s_state = reinterpret_cast<float*>(dsm);                               // [TH][TW*3] float32
+    uint8_t* s_out = dsm + P2_STATE_BYTES;                                          // [TH][TW*3] uint8
+    float (*Us)[P2_BH][P2_BW + 2] = reinterpret_cast<float (*)[P2_BH][P2_BW + 2]>(dsm + P2_STATE_BYTES + P2_OUT_BYTES);
+    float (*Ss)[P2_BH][P2_BW + 2] = reinterpret_cast<float (*)[P2_BH][P2_BW + 2]>(dsm + P2_STATE_BYTES + P2_OUT_BYTES + P2_US_BYTES);
+    __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
+    __shared__ float s_unit[256];
+    __shared__ double s_pow[POW_TAB_DOUBLES];
+    __shared__ float s_rows[2 * P2_TH], s_cols[2 * P2_TW];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x;
+    const int ox0 = blockIdx.x * P2_TW, oy0 = blockIdx.y * P2_TH;
+    const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + P2_TH, d.H) - 1;
+    const int rows = oy1 - oy0 + 1, tw = ox1 - ox0 + 1;
+    float* gdst = q_out ? q_out : state;                    // float rows written at the end (pre-warp image in the two-pass path)
+    const bool load_prev = has_prev && !q_out;
+
+    if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (load_prev && tid < 32) {                            // warp 0: one bulk copy per tile row, all in flight at once
+        if (tid == 0) mbar_expect_tx(&s_bar, (uint32_t)(rows * tw * 12));
+        __syncwarp();
+        if (tid < rows) bulk_g2s(s_state + tid * (P2_TW * 3), state + ((size_t)(oy0 + tid) * d.W + ox0) * 3, (uint32_t)(tw * 12), &s_bar);
+    }
+
+    const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
+    const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
+    if (d.triad_mode >= 2) {
+        reinterpret_cast<float4*>(s_fwd)[tid] = reinterpret_cast<const float4*>(lut_a)[tid];
+        reinterpret_cast<float4*>(s_inv)[tid] = reinterpret_cast<const float4*>(lut_b)[tid];
+        if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
+    }
+    s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
+    if (d.col_gamma && tid < POW_TAB_DOUBLES) s_pow[tid] = d.pow_tab[tid];
+    MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
+    if (tid < P2_TH) {
+        const int y = oy0 + tid;
+        if (d.scan_mode == 1) mt.row_scan[tid] = scan_row(d, f, y);
+        else if (d.scan_mode == 2) { double t = ((double)y + f.phase) * d.scan_inv_period; mt.row_scan[tid] = (float)(t - floor(t)); }
+        if (d.vig_mode == 1) { const float ny = ((float)y - d.vig_cy) * d.vig_iry; mt.row_vig[tid] = ny * ny; }
+    } else if (tid >= 64 && tid < 64 + P2_TW) {
+        const int c = tid - 64, x = ox0 + c;
+        if (d.scan_mode == 2) { double t = (d.scan_tan * (double)x) * d.scan_inv_period; mt.col_scan[c] = (float)(t - floor(t)); }
+        if (d.vig_mode == 1) { const float nx = ((float)x - d.vig_cx) * d.vig_irx; mt.col_vig[c] = nx * nx; }
+    }
+    __syncthreads();
+
+    // ---- phase 1: one graded value per 2x2 block ----
+    const int gbx0 = (ox0 >> 1) - 1, gby0 = (oy0 >> 1) - 1;
+    for (int u = tid; u < P2_BW * P2_BH; u += P2_NT) {
+        const int bj = u / P2_BW, bi = u - bj * P2_BW;
+        const int gbi = imin(imax(gbx0 + bi, 0), d.hw - 1), gbj = imin(imax(gby0 + bj, 0), d.hh - 1);
+        const F3 v1 = graded_source_lut(d, in, 2 * gbj, 2 * gbi, 2 * gbj, 2 * gbi, s_unit, s_pow);
+        Us[0][bj][bi] = v1.x; Us[1][bj][bi] = v1.y; Us[2][bj][bi] = v1.z;
+        if (BLOOM && d.thr_on) {
+            const F3 sv = bloom_src(d, v1);
+            Ss[0][bj][bi] = sv.x; Ss[1][bj][bi] = sv.y; Ss[2][bj][bi] = sv.z;
+        }
+    }
+    __syncthreads();
+    if (load_prev) mbar_wait(&s_bar, 0);                    // state tile has landed
+
+    // ---- phase 4 ----
+    const int tx = tid & 15, ty = tid >> 4;
+    const int xb = ox0 + 4 * tx, y0 = oy0 + 2 * ty;
+    if (xb <= ox1 && y0 <= oy1) {
+        const int bi = 2 * tx + 1, bj = ty + 1;
+        float bl[2][4][3];
+        float t1[2][3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            t1[0][ch] = Us[ch][bj][bi]; t1[1][ch] = Us[ch][bj][bi + 1];
+            if (BLOOM) {
+                const float (*src)[P2_BW + 2] = d.thr_on ? Ss[ch] : Us[ch];
+                float h[3][4];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float2 ca = *reinterpret_cast<const float2*>(&src[bj - 1 + r][bi - 1]);
+                    const float2 cb = *reinterpret_cast<const float2*>(&src[bj - 1 + r][bi + 1]);
+                    const float d01 = fsub(ca.y, ca.x), d12 = fsub(cb.x, ca.y), d23 = fsub(cb.y, cb.x);
+                    h[r][0] = ffma(d01, 0.75f, ca.x); h[r][1] = ffma(d12, 0.25f, ca.y);
+                    h[r][2] = ffma(d12, 0.75f, ca.y); h[r][3] = ffma(d23, 0.25f, cb.x);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    bl[0][k][ch] = ffma(fsub(h[1][k], h[0][k]), 0.75f, h[0][k]);
+                    bl[1][k][ch] = ffma(fsub(h[2][k], h[1][k]), 0.25f, h[1][k]);
+                }
+            }
+        }
+        const bool fast = FAST && ox0 >= d.comp_x0 && ox1 <= d.comp_x1;
+        float cvig[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* tab[4][3];
+        const int ph0 = xb - 3 * (int)__umulhi((unsigned)xb, 0x55555556u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (fast && d.vig_mode) cvig[k] = mt.col_vig[xb - ox0 + k];
+            const int ph = (ph0 + k) % 3;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) tab[k][ch] = ph == ch ? s_fwd : s_inv;
+        }
+        const float vs = d.vig_mode ? d.vig_strength : 0.f;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int y = y0 + r;
+            if (y > oy1) break;
+            float* srow = s_state + (y - oy0) * (P2_TW * 3) + 12 * tx;
+            uint8_t* orow = s_out + (y - oy0) * (P2_TW * 3) + 12 * tx;
+            if (fast) {
+                const float rfac = (d.scan_mode ? mt.row_scan[y - oy0] : 1.0f) * (f.flicker_on ? f.flicker : 1.0f);
+                const float rvig = d.vig_mode ? mt.row_vig[y - oy0] : 0.f;
+                auto pixel = [&](int, int, int k) -> F3 {
+                    F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
+                    if (BLOOM) v = add_bloom(d, v, mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]));
+                    const float m = rfac * __fmaf_rn(-vs, __saturatef(rvig + cvig[k]), 1.0f);
+                    v.x = __saturatef(tab[k][0][lut_index(v.x)] * m);
+                    v.y = __saturatef(tab[k][1][lut_index(v.y)] * m);
+                    v.z = __saturatef(tab[k][2][lut_index(v.z)] * m);
+                    return v;
+                };
+                finish_quad_smem(d, srow, orow, !q_out, load_prev, y, xb, pixel);
+            } else {
+                auto pixel = [&](int yy, int x, int k) -> F3 {
+                    F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
+                    if (BLOOM) v = add_bloom(d, v, mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]));
+                    return after_bloom_fast(d, f, v, yy, x, s_fwd, s_inv, mt, yy - oy0, x - ox0);
+                };
+                finish_quad_smem(d, srow, orow, !q_out, load_prev, y, xb, pixel);
+            }
+        }
+    }
+    fence_proxy_async();                                    // results in shared memory -> visible to the bulk-copy engine
+    __syncthreads();
+    if (tid < rows) {
+        if (gdst) bulk_s2g(gdst + ((size_t)(oy0 + tid) * d.W + ox0) * 3, s_state + tid * (P2_TW * 3), (uint32_t)(tw * 12));
+        if (!q_out) bulk_s2g(out + ((size_t)(oy0 + tid) * d.W + ox0) * 3, s_out + tid * (P2_TW * 3), (uint32_t)(tw * 3));
+        bulk_commit();
+        bulk_wait_read();
+    }
+}
+
 inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
                          cudaStream_t st, int* launches) {
     dim3 grid((d.W + P2_TW - 1) / P2_TW, (d.H + P2_TH - 1) / P2_TH);
     const bool fast = d.triad_mode == 2 && d.triad_comp && d.scan_mode <= 1 && d.vig_mode <= 1 && !d.noise_on;
+    if ((d.W & 15) == 0 && !env_int("CRT_NO_TMA", 0)) {      // bulk-copy variant (rows are 16-byte multiples)
+        const size_t smem = P2_STATE_BYTES + P2_OUT_BYTES + P2_US_BYTES * ((d.bloom_mode == 1 && d.thr_on) ? 2 : 1);
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(k_fused_ps2_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(k_fused_ps2_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(k_fused_ps2_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(k_fused_ps2_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            configured = true;
+        }
+        if (d.bloom_mode == 1) {
+            if (fast) k_fused_ps2_tma<true, true><<<grid, P2_NT, smem, st>>>(d, f, in, out, state, q_out, has_prev);
+            else k_fused_ps2_tma<true, false><<<grid, P2_NT, smem, st>>>(d, f, in, out, state, q_out, has_prev);
+        } else {
+            if (fast) k_fused_ps2_tma<false, true><<<grid, P2_NT, smem, st>>>(d, f, in, out, state, q_out, has_prev);
+            else k_fused_ps2_tma<false, false><<<grid, P2_NT, smem, st>>>(d, f, in, out, state, q_out, has_prev);
+        }
+        ++*launches;
+        return cudaGetLastError() == cudaSuccess ? 0 : 2;
+    }
     if (d.bloom_mode == 1) {
         if (fast) k_fused_ps2<true, true><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
         else k_fused_ps2<true, false><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
