@@ -15,6 +15,7 @@
 #pragma once
 #include "crt_fused.cuh"
 #include "crt_tma.cuh"
+#include <cuda_pipeline.h>
 
 namespace crt {
 
@@ -41,9 +42,28 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
     __shared__ float s_rows[2 * P2_TH], s_cols[2 * P2_TW];
     __shared__ __align__(16) float Us[3][P2_BH][P2_BW + 2];      // graded block values, planar (row pitch 36 floats)
     __shared__ __align__(16) float Ss[3][P2_BH][P2_BW + 2];      // thresholded bloom source (only when the threshold is on)
+    extern __shared__ float4 s_prev[];                           // [6][P2_NT] this thread's previous state, fetched asynchronously
     const int tid = threadIdx.x;
     const int ox0 = blockIdx.x * P2_TW, oy0 = blockIdx.y * P2_TH;
     const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + P2_TH, d.H) - 1;
+
+    // The 12 B/px persistence state is the bulk of the HBM traffic: start fetching this thread's
+    // 4 x 2 pixels now with LDGSTS (cp.async, 16 bytes each, no registers held) so that the
+    // latency is covered by the block grading below.  Nobody else touches these shared-memory slots.
+    const bool prefetch = has_prev && !q_out;
+    if (prefetch) {
+        const int px = ox0 + 4 * (tid & 15), py = oy0 + 2 * (tid >> 4);
+        if (px <= ox1) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (py + r > oy1) break;
+                const float4* src = reinterpret_cast<const float4*>(state + ((size_t)(py + r) * d.W + px) * 3);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) __pipeline_memcpy_async(&s_prev[(r * 3 + j) * P2_NT + tid], src + j, 16);
+            }
+        }
+        __pipeline_commit();
+    }
 
     const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
     const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
@@ -85,6 +105,8 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
     const int tx = tid & 15, ty = tid >> 4;
     const int xb = ox0 + 4 * tx, y0 = oy0 + 2 * ty;
     if (xb > ox1 || y0 > oy1) return;
+    if (prefetch) __pipeline_wait_prior(0);                 // this thread's state has landed
+    const float4* myprev = prefetch ? s_prev + tid : nullptr;
     const int bi = 2 * tx + 1, bj = ty + 1;                 // first of the two blocks, in halo coordinates
     float bl[2][4][3];                                      // bloom of the 8 pixels
     float t1[2][3];                                         // graded value of the two blocks
@@ -140,7 +162,7 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
                 v.z = __saturatef(tab[k][2][lut_index(v.z)] * m);
                 return v;
             };
-            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
+            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel, myprev ? myprev + r * 3 * P2_NT : nullptr, P2_NT);
         }
         return;
     }
@@ -153,7 +175,7 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
             if (BLOOM) v = add_bloom(d, v, mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]));
             return after_bloom_fast(d, f, v, yy, x, s_fwd, s_inv, mt, yy - oy0, x - ox0);
         };
-        finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
+        finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel, myprev ? myprev + r * 3 * P2_NT : nullptr, P2_NT);
     }
 }
 
@@ -164,6 +186,10 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
 // overlaps the block grading; results are staged in shared memory and leave with bulk stores (state
 // rows and packed uint8 rows).  No thread issues a global load/store for state or output.
 // Requires W % 16 == 0 (16-byte multiples for the uint8 rows).
+// MEASURED (round 1, run 18): correct, but SLOWER than the LDGSTS variant below — 8 193 vs 12 657
+// frames/s on the default chain at 4K — because a tile issues 96 row-sized (768 B / 192 B) 1-D bulk
+// copies that serialise in the copy engine.  Kept opt-in (CRT_TMA=1) as the base for a 2-D
+// tensor-map version (one copy per tile); not the default path.
 constexpr int P2_STATE_BYTES = P2_TH * P2_TW * 3 * 4, P2_OUT_BYTES = P2_TH * P2_TW * 3, P2_US_BYTES = 3 * P2_BH * (P2_BW + 2) * 4;
 
 template <typename PixelFn>
@@ -341,7 +367,7 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
                          cudaStream_t st, int* launches) {
     dim3 grid((d.W + P2_TW - 1) / P2_TW, (d.H + P2_TH - 1) / P2_TH);
     const bool fast = d.triad_mode == 2 && d.triad_comp && d.scan_mode <= 1 && d.vig_mode <= 1 && !d.noise_on;
-    if ((d.W & 15) == 0 && !env_int("CRT_NO_TMA", 0)) {      // bulk-copy variant (rows are 16-byte multiples)
+    if ((d.W & 15) == 0 && env_int("CRT_TMA", 0)) {      // bulk-copy variant: opt-in, measured slower (see header note)
         const size_t smem = P2_STATE_BYTES + P2_OUT_BYTES + P2_US_BYTES * ((d.bloom_mode == 1 && d.thr_on) ? 2 : 1);
         static bool configured = false;
         if (!configured) {
@@ -361,12 +387,13 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
         ++*launches;
         return cudaGetLastError() == cudaSuccess ? 0 : 2;
     }
+    const size_t pre = 6 * P2_NT * sizeof(float4);            // cp.async landing slots for the previous state
     if (d.bloom_mode == 1) {
-        if (fast) k_fused_ps2<true, true><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
-        else k_fused_ps2<true, false><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
+        if (fast) k_fused_ps2<true, true><<<grid, P2_NT, pre, st>>>(d, f, in, out, state, q_out, has_prev);
+        else k_fused_ps2<true, false><<<grid, P2_NT, pre, st>>>(d, f, in, out, state, q_out, has_prev);
     } else {
-        if (fast) k_fused_ps2<false, true><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
-        else k_fused_ps2<false, false><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
+        if (fast) k_fused_ps2<false, true><<<grid, P2_NT, pre, st>>>(d, f, in, out, state, q_out, has_prev);
+        else k_fused_ps2<false, false><<<grid, P2_NT, pre, st>>>(d, f, in, out, state, q_out, has_prev);
     }
     ++*launches;
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
