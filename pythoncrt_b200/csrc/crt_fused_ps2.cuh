@@ -136,12 +136,13 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
     }
     const bool fast = FAST && ox0 >= d.comp_x0 && ox1 <= d.comp_x1;        // block-uniform
     if (fast) {
-        float cvig[4];
+        float cvig[4], cscan[4];
         const float* tab[4][3];                                     // composite table (bright / dim) per column and channel
         const int ph0 = xb - 3 * (int)__umulhi((unsigned)xb, 0x55555556u);     // xb % 3
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             cvig[k] = d.vig_mode ? mt.col_vig[xb - ox0 + k] : 0.f;
+            cscan[k] = d.scan_mode == 2 ? mt.col_scan[xb - ox0 + k] : 0.f;
             const int ph = (ph0 + k) % 3;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) tab[k][ch] = ph == ch ? s_fwd : s_inv;
@@ -151,12 +152,21 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
         for (int r = 0; r < 2; ++r) {
             const int y = y0 + r;
             if (y > oy1) break;
-            const float rfac = (d.scan_mode ? mt.row_scan[y - oy0] : 1.0f) * (f.flicker_on ? f.flicker : 1.0f);
+            const float rscan = d.scan_mode ? mt.row_scan[y - oy0] : 1.0f;         // mask (mode 1) or phase fraction (mode 2)
+            const float flick = f.flicker_on ? f.flicker : 1.0f;
+            const float rfac = (d.scan_mode == 2 ? 1.0f : rscan) * flick;
             const float rvig = d.vig_mode ? mt.row_vig[y - oy0] : 0.f;
             auto pixel = [&](int, int, int k) -> F3 {
                 F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
                 if (BLOOM) v = add_bloom(d, v, mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]));
-                const float m = rfac * __fmaf_rn(-vs, __saturatef(rvig + cvig[k]), 1.0f);
+                float m = rfac * __fmaf_rn(-vs, __saturatef(rvig + cvig[k]), 1.0f);
+                if (d.scan_mode == 2) {             // slanted / shaped scanlines: same formula as mask_at
+                    float t = rscan + cscan[k];
+                    t = t >= 1.0f ? t - 1.0f : t;
+                    const float sv = fmaxf(__fmaf_rn(-0.5f, __sinf(__fmaf_rn(6.283185307f, t, -3.14159265f)), 0.5f), 0.0f);
+                    const float shaped = (d.scan_inv_sharp == 1.0f) ? sv : __powf(sv, d.scan_inv_sharp);
+                    m *= __fmaf_rn(-d.scan_strength, shaped, 1.0f);
+                }
                 v.x = __saturatef(tab[k][0][lut_index(v.x)] * m);
                 v.y = __saturatef(tab[k][1][lut_index(v.y)] * m);
                 v.z = __saturatef(tab[k][2][lut_index(v.z)] * m);
@@ -366,7 +376,7 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2_tma(Dev d, FrameDev f, cons
 inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
                          cudaStream_t st, int* launches) {
     dim3 grid((d.W + P2_TW - 1) / P2_TW, (d.H + P2_TH - 1) / P2_TH);
-    const bool fast = d.triad_mode == 2 && d.triad_comp && d.scan_mode <= 1 && d.vig_mode <= 1 && !d.noise_on;
+    const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1 && !d.noise_on;
     if ((d.W & 15) == 0 && env_int("CRT_TMA", 0)) {      // bulk-copy variant: opt-in, measured slower (see header note)
         const size_t smem = P2_STATE_BYTES + P2_OUT_BYTES + P2_US_BYTES * ((d.bloom_mode == 1 && d.thr_on) ? 2 : 1);
         static bool configured = false;
@@ -388,6 +398,18 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
         return cudaGetLastError() == cudaSuccess ? 0 : 2;
     }
     const size_t pre = 6 * P2_NT * sizeof(float4);            // cp.async landing slots for the previous state
+    {   // static (26 KB) + dynamic (24 KB) shared memory exceeds the 48 KB default: opt in once per device
+        static bool configured[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!configured[dev & 63]) {
+            cudaFuncSetAttribute(k_fused_ps2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre);
+            cudaFuncSetAttribute(k_fused_ps2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre);
+            cudaFuncSetAttribute(k_fused_ps2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre);
+            cudaFuncSetAttribute(k_fused_ps2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre);
+            configured[dev & 63] = true;
+        }
+    }
     if (d.bloom_mode == 1) {
         if (fast) k_fused_ps2<true, true><<<grid, P2_NT, pre, st>>>(d, f, in, out, state, q_out, has_prev);
         else k_fused_ps2<true, false><<<grid, P2_NT, pre, st>>>(d, f, in, out, state, q_out, has_prev);
