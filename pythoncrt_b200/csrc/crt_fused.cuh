@@ -192,15 +192,15 @@ __device__ __forceinline__ F3 after_bloom_fast(const Dev& d, const FrameDev& f, 
 template <typename PixelFn>
 __device__ __forceinline__ void finish_quad(const Dev& d, float* __restrict__ state, uint8_t* __restrict__ out, float* __restrict__ q_out,
                                             int has_prev, int y, int xb, int npx, PixelFn&& pixel,
-                                            const float4* prev_smem = nullptr, int prev_stride = 0) {
+                                            bool prev_given = false, float4 ga = float4(), float4 gb = float4(), float4 gc = float4()) {
     const float pp = d.persist, pq = d.persist_q;
     const bool vec = (d.W & 3) == 0;
     const int o = (y * d.W + xb) * 3;               // < 2^31 (checked by plan_fused)
     float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa, pc = pa;       // previous state of the 4 pixels
     if (q_out) { has_prev = 0; state = q_out; }
     if (has_prev) {
-        if (prev_smem) {                            // already fetched into shared memory (cp.async)
-            pa = prev_smem[0]; pb = prev_smem[prev_stride]; pc = prev_smem[2 * prev_stride];
+        if (prev_given) {                           // the caller fetched the previous state early
+            pa = ga; pb = gb; pc = gc;
         } else if (vec) {
             const float4* sp = reinterpret_cast<const float4*>(state + o);
             pa = sp[0]; pb = sp[1]; pc = sp[2];

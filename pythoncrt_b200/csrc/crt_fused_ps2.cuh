@@ -15,7 +15,6 @@
 #pragma once
 #include "crt_fused.cuh"
 #include "crt_tma.cuh"
-#include <cuda_pipeline.h>
 
 namespace crt {
 
@@ -42,28 +41,9 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
     __shared__ float s_rows[2 * P2_TH], s_cols[2 * P2_TW];
     __shared__ __align__(16) float Us[3][P2_BH][P2_BW + 2];      // graded block values, planar (row pitch 36 floats)
     __shared__ __align__(16) float Ss[3][P2_BH][P2_BW + 2];      // thresholded bloom source (only when the threshold is on)
-    extern __shared__ float4 s_prev[];                           // [6][P2_NT] this thread's previous state, fetched asynchronously
     const int tid = threadIdx.x;
     const int ox0 = blockIdx.x * P2_TW, oy0 = blockIdx.y * P2_TH;
     const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + P2_TH, d.H) - 1;
-
-    // The 12 B/px persistence state is the bulk of the HBM traffic: start fetching this thread's
-    // 4 x 2 pixels now with LDGSTS (cp.async, 16 bytes each, no registers held) so that the
-    // latency is covered by the block grading below.  Nobody else touches these shared-memory slots.
-    const bool prefetch = has_prev && !q_out;
-    if (prefetch) {
-        const int px = ox0 + 4 * (tid & 15), py = oy0 + 2 * (tid >> 4);
-        if (px <= ox1) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (py + r > oy1) break;
-                const float4* src = reinterpret_cast<const float4*>(state + ((size_t)(py + r) * d.W + px) * 3);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) __pipeline_memcpy_async(&s_prev[(r * 3 + j) * P2_NT + tid], src + j, 16);
-            }
-        }
-        __pipeline_commit();
-    }
 
     const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
     const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
@@ -89,14 +69,34 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
 
     // ---- phase 1: one graded value per 2x2 block (tile + one halo block, clamped = cv2's edge rule) ----
     const int gbx0 = (ox0 >> 1) - 1, gby0 = (oy0 >> 1) - 1;
-    for (int u = tid; u < P2_BW * P2_BH; u += P2_NT) {
-        const int bj = u / P2_BW, bi = u - bj * P2_BW;
-        const int gbi = imin(imax(gbx0 + bi, 0), d.hw - 1), gbj = imin(imax(gby0 + bj, 0), d.hh - 1);
-        const F3 v1 = graded_source_lut(d, in, 2 * gbj, 2 * gbi, 2 * gbj, 2 * gbi, s_unit, s_pow);
-        Us[0][bj][bi] = v1.x; Us[1][bj][bi] = v1.y; Us[2][bj][bi] = v1.z;
-        if (BLOOM && d.thr_on) {
-            const F3 s = bloom_src(d, v1);
-            Ss[0][bj][bi] = s.x; Ss[1][bj][bi] = s.y; Ss[2][bj][bi] = s.z;
+    {
+        constexpr int NIT = (P2_BW * P2_BH + P2_NT - 1) / P2_NT;          // 3 blocks per thread at most
+        uint8_t raw[NIT][3];
+        const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {                                  // all loads first: their latencies overlap
+            const int u = tid + it * P2_NT;
+            if (u < P2_BW * P2_BH) {
+                const int bj = u / P2_BW, bi = u - bj * P2_BW;
+                const int sx = 2 * imin(imax(gbx0 + bi, 0), d.hw - 1), sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
+                const uint8_t* row = in + (size_t)sy * d.W * 3;
+                raw[it][0] = row[wrap(sx - a0, d.W) * 3 + 0];
+                raw[it][1] = row[sx * 3 + 1];
+                raw[it][2] = row[wrap(sx + a0, d.W) * 3 + 2];
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int u = tid + it * P2_NT;
+            if (u < P2_BW * P2_BH) {
+                const int bj = u / P2_BW, bi = u - bj * P2_BW;
+                const F3 v1 = colour(d, mk3(s_unit[raw[it][0]], s_unit[raw[it][1]], s_unit[raw[it][2]]), s_pow);
+                Us[0][bj][bi] = v1.x; Us[1][bj][bi] = v1.y; Us[2][bj][bi] = v1.z;
+                if (BLOOM && d.thr_on) {
+                    const F3 sv = bloom_src(d, v1);
+                    Ss[0][bj][bi] = sv.x; Ss[1][bj][bi] = sv.y; Ss[2][bj][bi] = sv.z;
+                }
+            }
         }
     }
     __syncthreads();
@@ -105,8 +105,17 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
     const int tx = tid & 15, ty = tid >> 4;
     const int xb = ox0 + 4 * tx, y0 = oy0 + 2 * ty;
     if (xb > ox1 || y0 > oy1) return;
-    if (prefetch) __pipeline_wait_prior(0);                 // this thread's state has landed
-    const float4* myprev = prefetch ? s_prev + tid : nullptr;
+    // previous state of both rows: issue the six 16-byte loads now, use them after the bloom arithmetic
+    float4 pv[2][3];
+    const bool do_prev = has_prev && !q_out;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        pv[r][0] = pv[r][1] = pv[r][2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (do_prev && y0 + r <= oy1) {
+            const float4* sp = reinterpret_cast<const float4*>(state + ((size_t)(y0 + r) * d.W + xb) * 3);
+            pv[r][0] = sp[0]; pv[r][1] = sp[1]; pv[r][2] = sp[2];
+        }
+    }
     const int bi = 2 * tx + 1, bj = ty + 1;                 // first of the two blocks, in halo coordinates
     float bl[2][4][3];                                      // bloom of the 8 pixels
     float t1[2][3];                                         // graded value of the two blocks
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
                 v.z = __saturatef(tab[k][2][lut_index(v.z)] * m);
                 return v;
             };
-            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel, myprev ? myprev + r * 3 * P2_NT : nullptr, P2_NT);
+            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel, do_prev, pv[r][0], pv[r][1], pv[r][2]);
         }
         return;
     }
@@ -185,7 +194,7 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
             if (BLOOM) v = add_bloom(d, v, mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]));
             return after_bloom_fast(d, f, v, yy, x, s_fwd, s_inv, mt, yy - oy0, x - ox0);
         };
-        finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel, myprev ? myprev + r * 3 * P2_NT : nullptr, P2_NT);
+        finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel, do_prev, pv[r][0], pv[r][1], pv[r][2]);
     }
 }
 
@@ -397,25 +406,12 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
         ++*launches;
         return cudaGetLastError() == cudaSuccess ? 0 : 2;
     }
-    const size_t pre = 6 * P2_NT * sizeof(float4);            // cp.async landing slots for the previous state
-    {   // static (26 KB) + dynamic (24 KB) shared memory exceeds the 48 KB default: opt in once per device
-        static bool configured[64] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (!configured[dev & 63]) {
-            cudaFuncSetAttribute(k_fused_ps2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre);
-            cudaFuncSetAttribute(k_fused_ps2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre);
-            cudaFuncSetAttribute(k_fused_ps2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre);
-            cudaFuncSetAttribute(k_fused_ps2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre);
-            configured[dev & 63] = true;
-        }
-    }
     if (d.bloom_mode == 1) {
-        if (fast) k_fused_ps2<true, true><<<grid, P2_NT, pre, st>>>(d, f, in, out, state, q_out, has_prev);
-        else k_fused_ps2<true, false><<<grid, P2_NT, pre, st>>>(d, f, in, out, state, q_out, has_prev);
+        if (fast) k_fused_ps2<true, true><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
+        else k_fused_ps2<true, false><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
     } else {
-        if (fast) k_fused_ps2<false, true><<<grid, P2_NT, pre, st>>>(d, f, in, out, state, q_out, has_prev);
-        else k_fused_ps2<false, false><<<grid, P2_NT, pre, st>>>(d, f, in, out, state, q_out, has_prev);
+        if (fast) k_fused_ps2<false, true><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
+        else k_fused_ps2<false, false><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
     }
     ++*launches;
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
