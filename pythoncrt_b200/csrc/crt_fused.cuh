@@ -129,8 +129,18 @@ __device__ __forceinline__ float gather4_fast(float a, float b, float c, float e
     return __fmaf_rn(e, t.w11, __fmaf_rn(c, t.w10, __fmaf_rn(b, t.w01, a * t.w00)));
 }
 __device__ __forceinline__ float blend_fast(float prev, float v, float p, float q) { return __saturatef(__fmaf_rn(p, prev, q * v)); }
-// values are already clipped to [0, 1] (or exceed 1 by an ulp after the gather): |.| and the upper clamp are no-ops
-__device__ __forceinline__ uint32_t quantise_fast(float v) { return (uint32_t)__float2int_rn(fminf(v * 255.0f, 255.0f)); }
+// Float -> integer conversions run on the quarter-rate conversion pipe; both conversions of the chain are
+// done on the FMA pipe instead by adding a power of two whose ulp is 1:
+//   quantise: values are already clipped to [0, 1] (an ulp above 1 after the gather still rounds to 255);
+//             the low byte of v * 255 + 1.5 * 2^23 (round-to-nearest-even) is round-half-even(255 v)
+//   LUT index: v * 1024 is exact in float32, so v * 1024 + 2^23 rounded toward zero is 2^23 + floor(1024 v),
+//             the reference's truncating index (crt_filter.py:250), for v in [0, 1]
+__device__ __forceinline__ uint32_t quantise_bits(float v) { return __float_as_uint(__fmaf_rn(v, 255.0f, 12582912.0f)); }
+__device__ __forceinline__ uint32_t quantise_fast(float v) { return quantise_bits(v) & 0xffu; }
+__device__ __forceinline__ uint32_t pack4(float a, float b, float c, float e) {
+    return __byte_perm(__byte_perm(quantise_bits(a), quantise_bits(b), 0x0040), __byte_perm(quantise_bits(c), quantise_bits(e), 0x0040), 0x5410);
+}
+__device__ __forceinline__ int lut_index_fast(float v01) { return (int)(__float_as_uint(__fmaf_rz(v01, 1024.0f, 8388608.0f)) & 0x7ffu); }
 
 // Per-tile tables for the masks applied after the triad LUT.
 struct MaskTabs {
@@ -163,9 +173,9 @@ __device__ __forceinline__ F3 after_bloom_fast(const Dev& d, const FrameDev& f, 
         if (d.triad_comp) {
             if (x >= d.comp_x0 && x <= d.comp_x1) {               // regular column: one composite look-up per channel
                 const int ph = x - 3 * (int)__umulhi((unsigned)x, 0x55555556u);     // x % 3
-                v.x = (ph == 0 ? fwd : inv)[lut_index(v.x)];
-                v.y = (ph == 1 ? fwd : inv)[lut_index(v.y)];
-                v.z = (ph == 2 ? fwd : inv)[lut_index(v.z)];
+                v.x = (ph == 0 ? fwd : inv)[lut_index_fast(__saturatef(v.x))];
+                v.y = (ph == 1 ? fwd : inv)[lut_index_fast(__saturatef(v.y))];
+                v.z = (ph == 2 ? fwd : inv)[lut_index_fast(__saturatef(v.z))];
             } else {
                 v = triad(d, v, x, d.lut_fwd, d.lut_inv);         // mask edge columns: full path from global memory
             }
@@ -233,8 +243,7 @@ __device__ __forceinline__ void finish_quad(const Dev& d, float* __restrict__ st
         uint32_t w[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j)
-            w[j] = quantise_fast(res[j * 4]) | (quantise_fast(res[j * 4 + 1]) << 8) | (quantise_fast(res[j * 4 + 2]) << 16) |
-                   (quantise_fast(res[j * 4 + 3]) << 24);
+            w[j] = pack4(res[j * 4], res[j * 4 + 1], res[j * 4 + 2], res[j * 4 + 3]);
         uint32_t* op = reinterpret_cast<uint32_t*>(out + o);
         op[0] = w[0]; op[1] = w[1]; op[2] = w[2];
     } else {

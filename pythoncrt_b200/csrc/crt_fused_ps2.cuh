@@ -33,7 +33,7 @@ CRT_HD bool fused_ps2_supported(const Dev& d, bool glitch_on) {
 // flicker folded into the row factor, no noise.  Tiles that touch the mask's irregular edge columns
 // and every other feature set take the general tail (after_bloom_fast).
 template <bool BLOOM, bool FAST>
-__global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+__global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                      float* __restrict__ state, float* __restrict__ q_out, int has_prev) {
     __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
     __shared__ float s_unit[256];
@@ -105,17 +105,6 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
     const int tx = tid & 15, ty = tid >> 4;
     const int xb = ox0 + 4 * tx, y0 = oy0 + 2 * ty;
     if (xb > ox1 || y0 > oy1) return;
-    // previous state of both rows: issue the six 16-byte loads now, use them after the bloom arithmetic
-    float4 pv[2][3];
-    const bool do_prev = has_prev && !q_out;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        pv[r][0] = pv[r][1] = pv[r][2] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (do_prev && y0 + r <= oy1) {
-            const float4* sp = reinterpret_cast<const float4*>(state + ((size_t)(y0 + r) * d.W + xb) * 3);
-            pv[r][0] = sp[0]; pv[r][1] = sp[1]; pv[r][2] = sp[2];
-        }
-    }
     const int bi = 2 * tx + 1, bj = ty + 1;                 // first of the two blocks, in halo coordinates
     float bl[2][4][3];                                      // bloom of the 8 pixels
     float t1[2][3];                                         // graded value of the two blocks
@@ -176,12 +165,12 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
                     const float shaped = (d.scan_inv_sharp == 1.0f) ? sv : __powf(sv, d.scan_inv_sharp);
                     m *= __fmaf_rn(-d.scan_strength, shaped, 1.0f);
                 }
-                v.x = __saturatef(tab[k][0][lut_index(v.x)] * m);
-                v.y = __saturatef(tab[k][1][lut_index(v.y)] * m);
-                v.z = __saturatef(tab[k][2][lut_index(v.z)] * m);
+                v.x = __saturatef(tab[k][0][lut_index_fast(__saturatef(v.x))] * m);
+                v.y = __saturatef(tab[k][1][lut_index_fast(__saturatef(v.y))] * m);
+                v.z = __saturatef(tab[k][2][lut_index_fast(__saturatef(v.z))] * m);
                 return v;
             };
-            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel, do_prev, pv[r][0], pv[r][1], pv[r][2]);
+            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
         }
         return;
     }
@@ -194,7 +183,7 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2(Dev d, FrameDev f, const ui
             if (BLOOM) v = add_bloom(d, v, mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]));
             return after_bloom_fast(d, f, v, yy, x, s_fwd, s_inv, mt, yy - oy0, x - ox0);
         };
-        finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel, do_prev, pv[r][0], pv[r][1], pv[r][2]);
+        finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
     }
 }
 
@@ -233,8 +222,7 @@ __device__ __forceinline__ void finish_quad_smem(const Dev& d, float* __restrict
         uint32_t* op = reinterpret_cast<uint32_t*>(orow);
 #pragma unroll
         for (int j = 0; j < 3; ++j)
-            op[j] = quantise_fast(res[j * 4]) | (quantise_fast(res[j * 4 + 1]) << 8) | (quantise_fast(res[j * 4 + 2]) << 16) |
-                    (quantise_fast(res[j * 4 + 3]) << 24);
+            op[j] = pack4(res[j * 4], res[j * 4 + 1], res[j * 4 + 2], res[j * 4 + 3]);
     }
 }
 
