@@ -142,6 +142,18 @@ __device__ __forceinline__ uint32_t pack4(float a, float b, float c, float e) {
 }
 __device__ __forceinline__ int lut_index_fast(float v01) { return (int)(__float_as_uint(__fmaf_rz(v01, 1024.0f, 8388608.0f)) & 0x7ffu); }
 
+// The persistence state (12 B/px read) is the bulk of the HBM traffic and is consumed at the very end of
+// a tile's work: ask L2 for the tile's rows at kernel start so that the final loads hit L2 instead of
+// waiting on DRAM (no registers or shared memory held; one 128-byte line per thread).
+__device__ __forceinline__ void prefetch_state_tile(const float* __restrict__ state, int W, int x0, int y0, int tw, int rows, int tid, int nthreads) {
+    const int lines_per_row = (tw * 12 + 127) >> 7;
+    for (int i = tid; i < rows * lines_per_row; i += nthreads) {
+        const int r = i / lines_per_row, sgm = i - r * lines_per_row;
+        const char* p = reinterpret_cast<const char*>(state + ((size_t)(y0 + r) * W + x0) * 3) + (sgm << 7);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+}
+
 // Per-tile tables for the masks applied after the triad LUT.
 struct MaskTabs {
     float* row_scan;    // scan_mode 1: row mask;  scan_mode 2: phase fraction of the row
@@ -273,6 +285,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
     const int ox0 = blockIdx.x * FTW, oy0 = blockIdx.y * g.th;
     const int ox1 = imin(ox0 + FTW, d.W) - 1, oy1 = imin(oy0 + g.th, d.H) - 1;
     const int trow = tid / FROW_THREADS, xb = ox0 + (tid % FROW_THREADS) * 4;    // this thread's pixel quad
+    if (has_prev && !q_out) prefetch_state_tile(state, d.W, ox0, oy0, ox1 - ox0 + 1, oy1 - oy0 + 1, tid, NT);
 
     // triad tables in shared memory: the composite (bright, dim) pair when the mask is regular, else (forward, inverse)
     const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;

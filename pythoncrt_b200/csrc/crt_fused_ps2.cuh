@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const
     const int tid = threadIdx.x;
     const int ox0 = blockIdx.x * P2_TW, oy0 = blockIdx.y * P2_TH;
     const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + P2_TH, d.H) - 1;
+    if (has_prev && !q_out) prefetch_state_tile(state, d.W, ox0, oy0, ox1 - ox0 + 1, oy1 - oy0 + 1, tid, P2_NT);
 
     const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
     const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
