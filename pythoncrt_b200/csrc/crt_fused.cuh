@@ -142,9 +142,8 @@ __device__ __forceinline__ uint32_t pack4(float a, float b, float c, float e) {
 }
 __device__ __forceinline__ int lut_index_fast(float v01) { return (int)(__float_as_uint(__fmaf_rz(v01, 1024.0f, 8388608.0f)) & 0x7ffu); }
 
-// The persistence state (12 B/px read) is the bulk of the HBM traffic and is consumed at the very end of
-// a tile's work: ask L2 for the tile's rows at kernel start so that the final loads hit L2 instead of
-// waiting on DRAM (no registers or shared memory held; one 128-byte line per thread).
+// L2 prefetch of a tile's persistence-state rows (one 128-byte line per thread).  MEASURED (round 1, run 23):
+// issuing it at kernel start made the kernels 2-4 % slower, so no kernel calls it; kept for experiments.
 __device__ __forceinline__ void prefetch_state_tile(const float* __restrict__ state, int W, int x0, int y0, int tw, int rows, int tid, int nthreads) {
     const int lines_per_row = (tw * 12 + 127) >> 7;
     for (int i = tid; i < rows * lines_per_row; i += nthreads) {
@@ -285,7 +284,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
     const int ox0 = blockIdx.x * FTW, oy0 = blockIdx.y * g.th;
     const int ox1 = imin(ox0 + FTW, d.W) - 1, oy1 = imin(oy0 + g.th, d.H) - 1;
     const int trow = tid / FROW_THREADS, xb = ox0 + (tid % FROW_THREADS) * 4;    // this thread's pixel quad
-    if (has_prev && !q_out) prefetch_state_tile(state, d.W, ox0, oy0, ox1 - ox0 + 1, oy1 - oy0 + 1, tid, NT);
 
     // triad tables in shared memory: the composite (bright, dim) pair when the mask is regular, else (forward, inverse)
     const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;

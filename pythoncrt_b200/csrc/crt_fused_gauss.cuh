@@ -65,7 +65,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
     const int ox0 = blockIdx.x * FTW, oy0 = blockIdx.y * th;
     const int ox1 = imin(ox0 + FTW, d.W) - 1, oy1 = imin(oy0 + th, d.H) - 1;
     const int trow = tid / FROW_THREADS, xb = ox0 + (tid % FROW_THREADS) * 4;
-    if (has_prev && !q_out) prefetch_state_tile(state, d.W, ox0, oy0, ox1 - ox0 + 1, oy1 - oy0 + 1, tid, NT);
 
     // triad tables in shared memory: the composite (bright, dim) pair when the mask is regular, else (forward, inverse)
     const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;

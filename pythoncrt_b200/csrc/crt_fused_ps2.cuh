@@ -42,10 +42,6 @@ __global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const
     __shared__ __align__(16) float Us[3][P2_BH][P2_BW + 2];      // graded block values, planar (row pitch 36 floats)
     __shared__ __align__(16) float Ss[3][P2_BH][P2_BW + 2];      // thresholded bloom source (only when the threshold is on)
     const int tid = threadIdx.x;
-    const int ox0 = blockIdx.x * P2_TW, oy0 = blockIdx.y * P2_TH;
-    const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + P2_TH, d.H) - 1;
-    if (has_prev && !q_out) prefetch_state_tile(state, d.W, ox0, oy0, ox1 - ox0 + 1, oy1 - oy0 + 1, tid, P2_NT);
-
     const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
     const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
     if (d.triad_mode >= 2) {
@@ -56,6 +52,13 @@ __global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const
     s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
     if (d.col_gamma && tid < POW_TAB_DOUBLES) s_pow[tid] = d.pow_tab[tid];
     MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
+    // Persistent CTAs: the tables above are staged once, then the CTA walks over tiles
+    // (tile = blockIdx.x, blockIdx.x + gridDim.x, ...; consecutive CTAs work on neighbouring tiles).
+    const int tiles_x = (d.W + P2_TW - 1) / P2_TW, ntiles = tiles_x * ((d.H + P2_TH - 1) / P2_TH);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tby = tile / tiles_x, tbx = tile - tby * tiles_x;
+    const int ox0 = tbx * P2_TW, oy0 = tby * P2_TH;
+    const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + P2_TH, d.H) - 1;
     if (tid < P2_TH) {
         const int y = oy0 + tid;
         if (d.scan_mode == 1) mt.row_scan[tid] = scan_row(d, f, y);
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const
         if (d.scan_mode == 2) { double t = (d.scan_tan * (double)x) * d.scan_inv_period; mt.col_scan[c] = (float)(t - floor(t)); }
         if (d.vig_mode == 1) { const float nx = ((float)x - d.vig_cx) * d.vig_irx; mt.col_vig[c] = nx * nx; }
     }
-    __syncthreads();        // s_unit / s_pow ready
+    __syncthreads();        // tables ready (and, from the second tile on, the previous tile's block values are dead)
 
     // ---- phase 1: one graded value per 2x2 block (tile + one halo block, clamped = cv2's edge rule) ----
     const int gbx0 = (ox0 >> 1) - 1, gby0 = (oy0 >> 1) - 1;
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const
     // ---- phase 4: every thread owns 4 x 2 output pixels = two blocks side by side ------------------------
     const int tx = tid & 15, ty = tid >> 4;
     const int xb = ox0 + 4 * tx, y0 = oy0 + 2 * ty;
-    if (xb > ox1 || y0 > oy1) return;
+    if (xb <= ox1 && y0 <= oy1) {
     const int bi = 2 * tx + 1, bj = ty + 1;                 // first of the two blocks, in halo coordinates
     float bl[2][4][3];                                      // bloom of the 8 pixels
     float t1[2][3];                                         // graded value of the two blocks
@@ -173,19 +176,22 @@ __global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const
             };
             finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
         }
-        return;
-    }
+    } else {
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int y = y0 + r;
-        if (y > oy1) break;
-        auto pixel = [&](int yy, int x, int k) -> F3 {
-            F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
-            if (BLOOM) v = add_bloom(d, v, mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]));
-            return after_bloom_fast(d, f, v, yy, x, s_fwd, s_inv, mt, yy - oy0, x - ox0);
-        };
-        finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
+        for (int r = 0; r < 2; ++r) {
+            const int y = y0 + r;
+            if (y > oy1) break;
+            auto pixel = [&](int yy, int x, int k) -> F3 {
+                F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
+                if (BLOOM) v = add_bloom(d, v, mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]));
+                return after_bloom_fast(d, f, v, yy, x, s_fwd, s_inv, mt, yy - oy0, x - ox0);
+            };
+            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
+        }
     }
+    }                       // this thread's patch
+    __syncthreads();        // everyone is done with this tile's tables / block values
+    }                       // tile loop
 }
 
 
@@ -374,6 +380,16 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2_tma(Dev d, FrameDev f, cons
 inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
                          cudaStream_t st, int* launches) {
     dim3 grid((d.W + P2_TW - 1) / P2_TW, (d.H + P2_TH - 1) / P2_TH);
+    const int ntiles = (int)(grid.x * grid.y);
+    static int resident = 0;                                     // CTAs the GPU holds at once: SMs x 4 (launch bounds)
+    if (!resident) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        resident = sms * 4 * env_int("CRT_PS2_WAVES", 1);
+        if (env_int("CRT_PS2_PERSIST", 1) == 0) resident = 1 << 30;
+    }
+    const dim3 pgrid(ntiles < resident ? ntiles : resident);       // persistent 1-D grid (the TMA variant keeps the 2-D grid)
     const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1 && !d.noise_on;
     if ((d.W & 15) == 0 && env_int("CRT_TMA", 0)) {      // bulk-copy variant: opt-in, measured slower (see header note)
         const size_t smem = P2_STATE_BYTES + P2_OUT_BYTES + P2_US_BYTES * ((d.bloom_mode == 1 && d.thr_on) ? 2 : 1);
@@ -396,11 +412,11 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
         return cudaGetLastError() == cudaSuccess ? 0 : 2;
     }
     if (d.bloom_mode == 1) {
-        if (fast) k_fused_ps2<true, true><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
-        else k_fused_ps2<true, false><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
+        if (fast) k_fused_ps2<true, true><<<pgrid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
+        else k_fused_ps2<true, false><<<pgrid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
     } else {
-        if (fast) k_fused_ps2<false, true><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
-        else k_fused_ps2<false, false><<<grid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
+        if (fast) k_fused_ps2<false, true><<<pgrid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
+        else k_fused_ps2<false, false><<<pgrid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
     }
     ++*launches;
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
