@@ -15,6 +15,7 @@
 #include "crt_fused.cuh"
 #include "crt_fused_gauss.cuh"
 #include "crt_fused_ps2.cuh"
+#include "crt_fused_gauss_ps2.cuh"
 
 using namespace crt;
 
@@ -254,7 +255,8 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         int rc;
         if (want_fused) {
             prof_mark(ctx, st, false);
-            rc = ctx->plan.ps2 ? run_fused_ps2(d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches)
+            rc = (ctx->plan.ps2 && ctx->plan.gauss_k) ? run_fused_gauss_ps2(d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches)
+               : ctx->plan.ps2 ? run_fused_ps2(d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches)
                : ctx->plan.gauss_k ? run_fused_gauss(ctx->plan.th, ctx->plan.nt, d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches)
                                    : run_fused(ctx->plan, d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches);
             fused_used = 1;
@@ -262,7 +264,8 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         } else if (want_two_pass) {
             const FusedPlan& pq = ctx->plan_q;
             prof_mark(ctx, st, false);
-            rc = pq.ps2 ? run_fused_ps2(ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
+            rc = (pq.ps2 && pq.gauss_k) ? run_fused_gauss_ps2(ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
+               : pq.ps2 ? run_fused_ps2(ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
                : pq.gauss_k ? run_fused_gauss(pq.th, pq.nt, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
                             : run_fused(pq, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches);
             prof_mark(ctx, st, true);

@@ -618,6 +618,11 @@ inline FusedPlan plan_fused(const Dev& hd, bool glitch_on) {
         pl.ok = true; pl.why = ""; pl.ps2 = 1; pl.th = 32; pl.nt = 256; pl.smem = 0;
         return pl;
     }
+    if (d.bloom_mode == 2 && d.pix_uniform == 2 && d.even_dims && (d.W & 3) == 0 && !d.warp_on && d.text_mode == 0 &&
+        fused_gauss_supported(d.ksize) && !env_int("CRT_NO_PS2", 0)) {     // == fused_gauss_ps2_supported: block-resolution gaussian
+        pl.ok = true; pl.why = ""; pl.ps2 = 1; pl.gauss_k = d.ksize; pl.bloom = 2; pl.th = 32; pl.nt = 256; pl.smem = 0;
+        return pl;
+    }
     // grid sizing: at least two waves of CTAs over the 148 SMs when the frame allows it
     auto enough_tiles = [&](int th) { return (long long)((d.W + FTW - 1) / FTW) * ((d.H + th - 1) / th) >= 2 * 148; };
     if (d.bloom_mode == 2 && !d.warp_on && fused_gauss_supported(d.ksize) && d.W >= 4 && d.H >= 4) {

@@ -1,0 +1,237 @@
+// crt_fused_gauss_ps2.cuh — gaussian-bloom chain at pixel_size 2 (BASELINE.json configs[1]):
+// the separable blur of crt_fused_gauss.cuh evaluated at BLOCK resolution.
+//
+// With pixel_size 2 and even frame dimensions the thresholded bloom source is constant over
+// aligned 2x2 blocks, S(x, y) = Sb(x >> 1, y >> 1), and cv2's REPLICATE border is a clamp of
+// the block index.  cv2.GaussianBlur's float32 arithmetic is kept bit for bit (same tap order,
+// same fused multiply-adds); what changes is how much of it has to be evaluated:
+//   * graded input + threshold: one value per block of tile + halo (36 x 20 blocks for a
+//     64 x 32 tile and K = 9, instead of 72 x 40 pixels);
+//   * row pass: its result depends on the block row only, so it runs over 20 block rows instead
+//     of 40 pixel rows.  A task blocks four outputs along x for a pair of block rows; the K + 3
+//     taps it needs are only (K + 3) / 2 + 1 distinct block columns (LDS.64 each, transposed
+//     planar source Sb[ch][bx][by]), combined with FMUL2 / FFMA2 in cv2's order;
+//   * column pass: merged into the output phase.  A thread owns a 4 x 2 pixel patch; the 2 K + 1
+//     row-pass rows it needs are R + 1 distinct block rows, read as (x, x+1) pairs, and the
+//     blurred values stay in registers (no blurred tile in shared memory, no extra barrier).
+// The per-pixel tail (triad LUT, masks, persistence, stores) is ps2_patch_tail (crt_fused_ps2.cuh).
+// Shared memory: ~31 KB dynamic + ~11 KB static for K = 9 -> four 256-thread CTAs per SM.
+#pragma once
+#include "crt_fused_gauss.cuh"
+#include "crt_fused_ps2.cuh"
+
+namespace crt {
+
+// geometry of the block-resolution tile for a K-tap kernel (radius R = K / 2)
+struct GaussPs2Geo {
+    int hb;        // halo blocks per side = ceil(R / 2)
+    int off;       // R & 1: pixel offset of the halo origin inside its block
+    int nbx, nby;  // blocks per tile incl. halo
+    int pitch;     // floats between consecutive bx in Sb (even, == 2 mod 4: fewest bank conflicts)
+};
+CRT_HD GaussPs2Geo gauss_ps2_geo(int K) {
+    GaussPs2Geo g;
+    const int R = K / 2;
+    g.hb = (R + 1) / 2; g.off = R & 1;
+    g.nbx = P2_TW / 2 + 2 * g.hb; g.nby = P2_TH / 2 + 2 * g.hb;
+    g.pitch = (g.nby & 3) == 2 ? g.nby : g.nby + 2;
+    return g;
+}
+inline size_t fused_gauss_ps2_smem(int K) {
+    const GaussPs2Geo g = gauss_ps2_geo(K);
+    return sizeof(float) * ((size_t)3 * g.nbx * g.pitch + (size_t)3 * g.nby * P2_TW + (size_t)3 * (P2_TH / 2) * (P2_TW / 2));
+}
+CRT_HD bool fused_gauss_ps2_supported(const Dev& d, bool glitch_on) {
+    return d.bloom_mode == 2 && d.pix_uniform == 2 && d.even_dims && (d.W & 3) == 0 && !d.warp_on && !glitch_on && d.text_mode == 0;
+}
+
+#if defined(__CUDACC__)
+
+template <int K, bool FAST, int MINB>
+__global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                           float* __restrict__ state, float* __restrict__ q_out, int has_prev) {
+    constexpr int R = K / 2, HB = (R + 1) / 2, OFF = R & 1;
+    constexpr int NBX = P2_TW / 2 + 2 * HB, NBY = P2_TH / 2 + 2 * HB;
+    constexpr int PITCH = (NBY & 3) == 2 ? NBY : NBY + 2;
+    constexpr int MR = ((K + 2 + OFF) >> 1) + 1;                  // distinct block columns under 4 outputs' taps
+    constexpr int MC = ((2 * R + 1 + OFF) >> 1) + 1;              // distinct block rows under 2 output rows' taps
+    extern __shared__ __align__(16) float sm[];
+    __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
+    __shared__ float s_unit[256];
+    __shared__ double s_pow[POW_TAB_DOUBLES];
+    __shared__ float s_rows[2 * P2_TH], s_cols[2 * P2_TW];
+    float* Sb = sm;                                 // [3][NBX][PITCH]   thresholded bloom source per block, transposed
+    float* Rp = Sb + 3 * NBX * PITCH;               // [3][NBY][P2_TW]   row-pass result per block row
+    float* T1 = Rp + 3 * NBY * P2_TW;               // [3][TH/2][TW/2]   graded block values of the tile
+    const int tid = threadIdx.x;
+    const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
+    const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
+    if (d.triad_mode >= 2) {
+        reinterpret_cast<float4*>(s_fwd)[tid] = reinterpret_cast<const float4*>(lut_a)[tid];
+        reinterpret_cast<float4*>(s_inv)[tid] = reinterpret_cast<const float4*>(lut_b)[tid];
+        if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
+    }
+    s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
+    if (d.col_gamma && tid < POW_TAB_DOUBLES) s_pow[tid] = d.pow_tab[tid];
+    float taps[K];                                  // the kernel is symmetric: R + 1 registers
+#pragma unroll
+    for (int i = 0; i <= R; ++i) { taps[R + i] = d.taps[R + i]; taps[R - i] = taps[R + i]; }
+    MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
+    __syncthreads();
+    const int tiles_x = (d.W + P2_TW - 1) / P2_TW, ntiles = tiles_x * ((d.H + P2_TH - 1) / P2_TH);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {      // persistent CTAs, tables staged once
+        const int tby = tile / tiles_x, tbx = tile - tby * tiles_x;
+        const int ox0 = tbx * P2_TW, oy0 = tby * P2_TH;
+        const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + P2_TH, d.H) - 1;
+        if (tid < P2_TH) {
+            const int y = oy0 + tid;
+            if (d.scan_mode == 1) mt.row_scan[tid] = scan_row(d, f, y);
+            else if (d.scan_mode == 2) { double t = ((double)y + f.phase) * d.scan_inv_period; mt.row_scan[tid] = (float)(t - floor(t)); }
+            if (d.vig_mode == 1) { const float ny = ((float)y - d.vig_cy) * d.vig_iry; mt.row_vig[tid] = ny * ny; }
+        } else if (tid >= 64 && tid < 64 + P2_TW) {
+            const int c = tid - 64, x = ox0 + c;
+            if (d.scan_mode == 2) { double t = (d.scan_tan * (double)x) * d.scan_inv_period; mt.col_scan[c] = (float)(t - floor(t)); }
+            if (d.vig_mode == 1) { const float nx = ((float)x - d.vig_cx) * d.vig_irx; mt.col_vig[c] = nx * nx; }
+        }
+
+        // ---- phase 1: graded value + bloom source per block of tile + halo (clamped block index = REPLICATE) ----
+        const int gbx0 = (ox0 >> 1) - HB, gby0 = (oy0 >> 1) - HB;
+        {
+            constexpr int NIT = (NBX * NBY + P2_NT - 1) / P2_NT;
+            uint8_t raw[NIT][3];
+            const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {                              // all loads first: their latencies overlap
+                const int u = tid + it * P2_NT;
+                if (u < NBX * NBY) {
+                    const int bj = u / NBX, bi = u - bj * NBX;
+                    const int sx = 2 * imin(imax(gbx0 + bi, 0), d.hw - 1), sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
+                    const uint8_t* row = in + (size_t)sy * d.W * 3;
+                    raw[it][0] = row[wrap(sx - a0, d.W) * 3 + 0];
+                    raw[it][1] = row[sx * 3 + 1];
+                    raw[it][2] = row[wrap(sx + a0, d.W) * 3 + 2];
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int u = tid + it * P2_NT;
+                if (u < NBX * NBY) {
+                    const int bj = u / NBX, bi = u - bj * NBX;
+                    const F3 v1 = colour(d, mk3(s_unit[raw[it][0]], s_unit[raw[it][1]], s_unit[raw[it][2]]), s_pow);
+                    const F3 sv = bloom_src(d, v1);
+                    float* s = Sb + bi * PITCH + bj;
+                    s[0] = sv.x; s[NBX * PITCH] = sv.y; s[2 * NBX * PITCH] = sv.z;
+                    const int ti = bi - HB, tj = bj - HB;
+                    if ((unsigned)ti < (unsigned)(P2_TW / 2) && (unsigned)tj < (unsigned)(P2_TH / 2)) {
+                        float* t = T1 + tj * (P2_TW / 2) + ti;
+                        t[0] = v1.x; t[(P2_TH / 2) * (P2_TW / 2)] = v1.y; t[2 * (P2_TH / 2) * (P2_TW / 2)] = v1.z;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: row pass over block rows; a task = 4 outputs along x for a pair of block rows ----
+        for (int u = tid; u < 3 * (NBY / 2) * (P2_TW / 4); u += P2_NT) {
+            const int xblk = u & (P2_TW / 4 - 1), t = u >> 4;                // P2_TW / 4 == 16
+            const int ch = t / (NBY / 2), yp = t - ch * (NBY / 2);
+            const float2* src = reinterpret_cast<const float2*>(Sb + (ch * NBX + 2 * xblk) * PITCH) + yp;
+            float2 v[MR];
+#pragma unroll
+            for (int m = 0; m < MR; ++m) v[m] = src[m * (PITCH / 2)];
+            float2 r[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                float2 a[K];
+#pragma unroll
+                for (int i = 0; i < K; ++i) a[i] = v[(jj + i + OFF) >> 1];
+                r[jj] = gauss_row2<K>(a, taps);
+            }
+            float* o0 = Rp + (ch * NBY + 2 * yp) * P2_TW + xblk * 4;
+            *reinterpret_cast<float4*>(o0) = make_float4(r[0].x, r[1].x, r[2].x, r[3].x);
+            *reinterpret_cast<float4*>(o0 + P2_TW) = make_float4(r[0].y, r[1].y, r[2].y, r[3].y);
+        }
+        __syncthreads();
+
+        // ---- phase 3 + 4: column pass in registers, then the per-pixel tail for a 4 x 2 patch ----
+        const int tx = tid & 15, ty = tid >> 4;
+        const int xb = ox0 + 4 * tx, y0 = oy0 + 2 * ty;
+        if (xb <= ox1 && y0 <= oy1) {
+            float bl[2][4][3];
+            float t1[2][3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float2 tv = *reinterpret_cast<const float2*>(T1 + (ch * (P2_TH / 2) + ty) * (P2_TW / 2) + 2 * tx);
+                t1[0][ch] = tv.x; t1[1][ch] = tv.y;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {                                   // pixel pairs (xb, xb+1), (xb+2, xb+3)
+                    const float2* src = reinterpret_cast<const float2*>(Rp + (ch * NBY + ty) * P2_TW + 4 * tx + 2 * h);
+                    float2 v[MC];
+#pragma unroll
+                    for (int m = 0; m < MC; ++m) v[m] = src[m * (P2_TW / 2)];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        // pixel row 2 ty + r, tap e in [-R, R] -> block row ty + ((r + e + R + OFF) >> 1)
+                        float2 s = __fmul2_rn(v[(r + R + OFF) >> 1], splat2(taps[R]));
+#pragma unroll
+                        for (int i = 1; i <= R; ++i)
+                            s = __ffma2_rn(__fadd2_rn(v[(r + i + R + OFF) >> 1], v[(r - i + R + OFF) >> 1]), splat2(taps[R + i]), s);
+                        bl[r][2 * h][ch] = s.x; bl[r][2 * h + 1][ch] = s.y;
+                    }
+                }
+            }
+            ps2_patch_tail<true, FAST>(d, f, mt, s_fwd, s_inv, state, out, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
+                                       [&](int r, int k) { return mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]); });
+        }
+        __syncthreads();        // everyone is done with this tile's tables before the next tile overwrites them
+    }
+}
+
+template <int K, int MINB>
+inline int launch_fused_gauss_ps2_t(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
+                                    int has_prev, cudaStream_t st) {
+    static bool configured[64] = {};
+    static int resident = 0;
+    const size_t smem = fused_gauss_ps2_smem(K);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        if (cudaFuncSetAttribute(k_fused_gauss_ps2<K, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+        if (cudaFuncSetAttribute(k_fused_gauss_ps2<K, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+        configured[dev & 63] = true;
+    }
+    if (!resident) {
+        int sms = 148, per_sm = 4;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_gauss_ps2<K, true, MINB>, P2_NT, smem);
+        resident = sms * (per_sm > 0 ? per_sm : 1);
+        if (env_int("CRT_PS2_PERSIST", 1) == 0) resident = 1 << 30;
+    }
+    const int ntiles = ((d.W + P2_TW - 1) / P2_TW) * ((d.H + P2_TH - 1) / P2_TH);
+    const dim3 grid(ntiles < resident ? ntiles : resident);
+    const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1 && !d.noise_on;
+    if (fast) k_fused_gauss_ps2<K, true, MINB><<<grid, P2_NT, smem, st>>>(d, f, in, out, state, q_out, has_prev);
+    else k_fused_gauss_ps2<K, false, MINB><<<grid, P2_NT, smem, st>>>(d, f, in, out, state, q_out, has_prev);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
+inline int run_fused_gauss_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
+                               cudaStream_t st, int* launches) {
+    int rc = 4;
+    static const int minb = env_int("CRT_GPS2_MINB", 4);        // CTAs per SM the kernel is compiled for (64 vs 80 registers)
+    switch (d.ksize) {
+        case 5: rc = minb == 3 ? launch_fused_gauss_ps2_t<5, 3>(d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_ps2_t<5, 4>(d, f, in, out, state, q_out, has_prev, st); break;
+        case 7: rc = minb == 3 ? launch_fused_gauss_ps2_t<7, 3>(d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_ps2_t<7, 4>(d, f, in, out, state, q_out, has_prev, st); break;
+        case 9: rc = minb == 3 ? launch_fused_gauss_ps2_t<9, 3>(d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_ps2_t<9, 4>(d, f, in, out, state, q_out, has_prev, st); break;
+        case 11: rc = minb == 3 ? launch_fused_gauss_ps2_t<11, 3>(d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_ps2_t<11, 4>(d, f, in, out, state, q_out, has_prev, st); break;
+        case 13: rc = minb == 3 ? launch_fused_gauss_ps2_t<13, 3>(d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_ps2_t<13, 4>(d, f, in, out, state, q_out, has_prev, st); break;
+        case 25: rc = minb == 3 ? launch_fused_gauss_ps2_t<25, 3>(d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_ps2_t<25, 4>(d, f, in, out, state, q_out, has_prev, st); break;
+        default: break;
+    }
+    ++*launches;
+    return rc;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace crt

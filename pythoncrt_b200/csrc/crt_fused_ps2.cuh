@@ -28,6 +28,67 @@ CRT_HD bool fused_ps2_supported(const Dev& d, bool glitch_on) {
 
 #if defined(__CUDACC__)
 
+// Stages 5-10, persistence and stores for a thread's 4 x 2 pixel patch (two 2x2 blocks side by side).
+// t1 = graded value of the two blocks, bloom(r, k) = blurred bloom source of pixel k of row r.
+template <bool BLOOM, bool FAST, typename BloomFn>
+__device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, const MaskTabs& mt, const float* s_fwd, const float* s_inv,
+                                               float* __restrict__ state, uint8_t* __restrict__ out, float* __restrict__ q_out, int has_prev,
+                                               int ox0, int oy0, int ox1, int oy1, int xb, int y0, const float (&t1)[2][3], BloomFn&& bloom) {
+    const bool fast = FAST && ox0 >= d.comp_x0 && ox1 <= d.comp_x1;        // block-uniform
+    if (fast) {
+        float cvig[4], cscan[4];
+        const float* tab[4][3];                                     // composite table (bright / dim) per column and channel
+        const int ph0 = xb - 3 * (int)__umulhi((unsigned)xb, 0x55555556u);     // xb % 3
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            cvig[k] = d.vig_mode ? mt.col_vig[xb - ox0 + k] : 0.f;
+            cscan[k] = d.scan_mode == 2 ? mt.col_scan[xb - ox0 + k] : 0.f;
+            const int ph = (ph0 + k) % 3;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) tab[k][ch] = ph == ch ? s_fwd : s_inv;
+        }
+        const float vs = d.vig_mode ? d.vig_strength : 0.f;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int y = y0 + r;
+            if (y > oy1) break;
+            const float rscan = d.scan_mode ? mt.row_scan[y - oy0] : 1.0f;         // mask (mode 1) or phase fraction (mode 2)
+            const float flick = f.flicker_on ? f.flicker : 1.0f;
+            const float rfac = (d.scan_mode == 2 ? 1.0f : rscan) * flick;
+            const float rvig = d.vig_mode ? mt.row_vig[y - oy0] : 0.f;
+            auto pixel = [&](int, int, int k) -> F3 {
+                F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
+                if (BLOOM) v = add_bloom(d, v, bloom(r, k));
+                float m = rfac * __fmaf_rn(-vs, __saturatef(rvig + cvig[k]), 1.0f);
+                if (d.scan_mode == 2) {             // slanted / shaped scanlines: same formula as mask_at
+                    float t = rscan + cscan[k];
+                    t = t >= 1.0f ? t - 1.0f : t;
+                    const float sv = fmaxf(__fmaf_rn(-0.5f, __sinf(__fmaf_rn(6.283185307f, t, -3.14159265f)), 0.5f), 0.0f);
+                    const float shaped = (d.scan_inv_sharp == 1.0f) ? sv : __powf(sv, d.scan_inv_sharp);
+                    m *= __fmaf_rn(-d.scan_strength, shaped, 1.0f);
+                }
+                v.x = __saturatef(tab[k][0][lut_index_fast(__saturatef(v.x))] * m);
+                v.y = __saturatef(tab[k][1][lut_index_fast(__saturatef(v.y))] * m);
+                v.z = __saturatef(tab[k][2][lut_index_fast(__saturatef(v.z))] * m);
+                return v;
+            };
+            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int y = y0 + r;
+            if (y > oy1) break;
+            auto pixel = [&](int yy, int x, int k) -> F3 {
+                F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
+                if (BLOOM) v = add_bloom(d, v, bloom(r, k));
+                return after_bloom_fast(d, f, v, yy, x, s_fwd, s_inv, mt, yy - oy0, x - ox0);
+            };
+            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
+        }
+    }
+}
+
 // FAST: the per-pixel tail is specialised for the default chain's feature set — regular triad mask
 // through the composite tables, per-row scanlines (or none), analytic vignette (or none), optional
 // flicker folded into the row factor, no noise.  Tiles that touch the mask's irregular edge columns
@@ -136,59 +197,8 @@ __global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const
             }
         }
     }
-    const bool fast = FAST && ox0 >= d.comp_x0 && ox1 <= d.comp_x1;        // block-uniform
-    if (fast) {
-        float cvig[4], cscan[4];
-        const float* tab[4][3];                                     // composite table (bright / dim) per column and channel
-        const int ph0 = xb - 3 * (int)__umulhi((unsigned)xb, 0x55555556u);     // xb % 3
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            cvig[k] = d.vig_mode ? mt.col_vig[xb - ox0 + k] : 0.f;
-            cscan[k] = d.scan_mode == 2 ? mt.col_scan[xb - ox0 + k] : 0.f;
-            const int ph = (ph0 + k) % 3;
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) tab[k][ch] = ph == ch ? s_fwd : s_inv;
-        }
-        const float vs = d.vig_mode ? d.vig_strength : 0.f;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int y = y0 + r;
-            if (y > oy1) break;
-            const float rscan = d.scan_mode ? mt.row_scan[y - oy0] : 1.0f;         // mask (mode 1) or phase fraction (mode 2)
-            const float flick = f.flicker_on ? f.flicker : 1.0f;
-            const float rfac = (d.scan_mode == 2 ? 1.0f : rscan) * flick;
-            const float rvig = d.vig_mode ? mt.row_vig[y - oy0] : 0.f;
-            auto pixel = [&](int, int, int k) -> F3 {
-                F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
-                if (BLOOM) v = add_bloom(d, v, mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]));
-                float m = rfac * __fmaf_rn(-vs, __saturatef(rvig + cvig[k]), 1.0f);
-                if (d.scan_mode == 2) {             // slanted / shaped scanlines: same formula as mask_at
-                    float t = rscan + cscan[k];
-                    t = t >= 1.0f ? t - 1.0f : t;
-                    const float sv = fmaxf(__fmaf_rn(-0.5f, __sinf(__fmaf_rn(6.283185307f, t, -3.14159265f)), 0.5f), 0.0f);
-                    const float shaped = (d.scan_inv_sharp == 1.0f) ? sv : __powf(sv, d.scan_inv_sharp);
-                    m *= __fmaf_rn(-d.scan_strength, shaped, 1.0f);
-                }
-                v.x = __saturatef(tab[k][0][lut_index_fast(__saturatef(v.x))] * m);
-                v.y = __saturatef(tab[k][1][lut_index_fast(__saturatef(v.y))] * m);
-                v.z = __saturatef(tab[k][2][lut_index_fast(__saturatef(v.z))] * m);
-                return v;
-            };
-            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
-        }
-    } else {
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int y = y0 + r;
-            if (y > oy1) break;
-            auto pixel = [&](int yy, int x, int k) -> F3 {
-                F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
-                if (BLOOM) v = add_bloom(d, v, mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]));
-                return after_bloom_fast(d, f, v, yy, x, s_fwd, s_inv, mt, yy - oy0, x - ox0);
-            };
-            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
-        }
-    }
+    ps2_patch_tail<BLOOM, FAST>(d, f, mt, s_fwd, s_inv, state, out, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
+                                [&](int r, int k) { return mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]); });
     }                       // this thread's patch
     __syncthreads();        // everyone is done with this tile's tables / block values
     }                       // tile loop
