@@ -182,6 +182,10 @@ int crt_reset_state(crt_ctx* ctx);
  * crt_profile_end synchronises them and returns the summed duration and count. */
 int crt_profile_begin(crt_ctx* ctx, int max_samples);
 int crt_profile_end(crt_ctx* ctx, double* total_ms, int* samples);
+/* Time only one launch in `every` (default 1 = all).  An event between two frames' kernels
+ * serialises them; with a stride the other launches keep their overlap (programmatic dependent
+ * launch), so the timed region's throughput is not the profiler's. */
+int crt_profile_sample_every(crt_ctx* ctx, int every);
 
 /* Device-side generators (counter-based RNG), used when noise_mode/glitch_mode == 1;
  * exposed so a host can pre-generate and inspect the draws. */

@@ -21,7 +21,7 @@ POLICY_AUTO, POLICY_STAGED, POLICY_FUSED = 0, 1, 2
 # every symbol include/crt_b200.h declares
 EXPORTS = ("crt_abi_version", "crt_create", "crt_destroy", "crt_last_error", "crt_set_params", "crt_set_table",
            "crt_set_policy", "crt_process", "crt_process_static", "crt_process_host", "crt_reset_state",
-           "crt_generate_noise", "crt_generate_glitch", "crt_profile_begin", "crt_profile_end")
+           "crt_generate_noise", "crt_generate_glitch", "crt_profile_begin", "crt_profile_end", "crt_profile_sample_every")
 
 
 class CrtParamsC(C.Structure):
@@ -108,6 +108,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.crt_generate_glitch.argtypes = [vp, C.POINTER(CrtFrameC), vp, vp]
     lib.crt_profile_begin.restype = C.c_int
     lib.crt_profile_begin.argtypes = [vp, i32]
+    lib.crt_profile_sample_every.restype = C.c_int
+    lib.crt_profile_sample_every.argtypes = [vp, i32]
     lib.crt_profile_end.restype = C.c_int
     lib.crt_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     if lib.crt_abi_version() != ABI_VERSION:

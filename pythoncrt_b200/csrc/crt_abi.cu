@@ -63,7 +63,8 @@ struct crt_ctx {
     Dev dev_q{};                        // parameter block of that first pass
     std::vector<cudaEvent_t> prof_ev;   // start/stop pairs (crt_profile_begin/end)
     int prof_cap = 0, prof_n = 0;
-    bool prof_on = false;
+    int prof_every = 1, prof_tick = 0;  // one launch in prof_every is timed (crt_profile_sample_every)
+    bool prof_on = false, prof_open = false;
     std::string err;
 };
 
@@ -166,8 +167,10 @@ int gen_glitch(crt_ctx* ctx, const crt_frame& fr, const GlitchGeom& g, int32_t* 
 // bench.py timing hook: events around the dominant kernel of a frame
 void prof_mark(crt_ctx* ctx, cudaStream_t st, bool stop) {
     if (!ctx->prof_on || ctx->prof_n >= ctx->prof_cap) return;
+    if (!stop) ctx->prof_open = (ctx->prof_tick++ % ctx->prof_every) == 0;
+    if (!ctx->prof_open) return;
     cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + (stop ? 1 : 0)], st);
-    if (stop) ++ctx->prof_n;
+    if (stop) { ++ctx->prof_n; ctx->prof_open = false; }
 }
 
 // One frame through the staged kernels.
@@ -214,6 +217,7 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
     if (ctx->policy == 2 && !want_fused && !want_two_pass)
         return fail(ctx, CRT_ERR_UNSUPPORTED, std::string("fused kernel not available: ") + ctx->plan.why);
     if (want_two_pass && !ctx->scratch.q) CU(cudaMalloc((void**)&ctx->scratch.q, frame_px * 3 * sizeof(float)));
+    static const bool use_pdl = env_int("CRT_PDL", 1) != 0;
     for (int i = 0; i < n_frames; ++i) {
         const crt_frame& fr = frames[i];
         FrameDev f = derive_frame(p, fr);
@@ -252,11 +256,14 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         uint8_t* out_i = d_out ? d_out + (size_t)i * frame_px * 3 : nullptr;
         float* img_i = d_img ? d_img + (size_t)i * frame_px * 3 : nullptr;
         float* state_i = (persist || (d_state && !d_img)) ? d_state : nullptr;
+        // Frames after the first may overlap the previous frame's kernel tail (launch_pdl, crt_fused.cuh).  Never frame 0:
+        // its input may come from the caller's immediately preceding kernel.
+        const bool pdl = i > 0 && use_pdl;
         int rc;
         if (want_fused) {
             prof_mark(ctx, st, false);
-            rc = (ctx->plan.ps2 && ctx->plan.gauss_k) ? run_fused_gauss_ps2(d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches)
-               : ctx->plan.ps2 ? run_fused_ps2(d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches)
+            rc = (ctx->plan.ps2 && ctx->plan.gauss_k) ? run_fused_gauss_ps2(d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches, pdl)
+               : ctx->plan.ps2 ? run_fused_ps2(d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches, pdl)
                : ctx->plan.gauss_k ? run_fused_gauss(ctx->plan.th, ctx->plan.nt, d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches)
                                    : run_fused(ctx->plan, d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches);
             fused_used = 1;
@@ -264,8 +271,8 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         } else if (want_two_pass) {
             const FusedPlan& pq = ctx->plan_q;
             prof_mark(ctx, st, false);
-            rc = (pq.ps2 && pq.gauss_k) ? run_fused_gauss_ps2(ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
-               : pq.ps2 ? run_fused_ps2(ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
+            rc = (pq.ps2 && pq.gauss_k) ? run_fused_gauss_ps2(ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl)
+               : pq.ps2 ? run_fused_ps2(ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl)
                : pq.gauss_k ? run_fused_gauss(pq.th, pq.nt, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
                             : run_fused(pq, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches);
             prof_mark(ctx, st, true);
@@ -455,7 +462,13 @@ int crt_profile_begin(crt_ctx* ctx, int max_samples) {
         CU(cudaEventCreate(&e));
         ctx->prof_ev.push_back(e);
     }
-    ctx->prof_cap = max_samples; ctx->prof_n = 0; ctx->prof_on = true;
+    ctx->prof_cap = max_samples; ctx->prof_n = 0; ctx->prof_tick = 0; ctx->prof_open = false; ctx->prof_on = true;
+    return CRT_OK;
+}
+
+int crt_profile_sample_every(crt_ctx* ctx, int every) {
+    if (!ctx || every < 1) return CRT_ERR_INVALID;
+    ctx->prof_every = every;
     return CRT_OK;
 }
 

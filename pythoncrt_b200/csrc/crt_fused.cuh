@@ -62,6 +62,30 @@ struct FusedGeom { int th, cap_px, cap_aux; };
 
 inline int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 
+#if defined(__CUDACC__)
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Consecutive frames depend on each other only through the persistence state, which a tile kernel
+// touches in its last phase.  A kernel launched with launch_pdl(pdl = true) may therefore start while
+// the previous kernel in the stream is still draining its last wave: the staging of tables, the graded
+// input and the blur of its first tiles overlap that tail (and the launch latency); griddep_wait()
+// then blocks until the previous kernel has completed and its writes are visible.  Every access to
+// memory that another kernel of the stream writes (state, pre-warp image, noise plane) must come after
+// griddep_wait(); the frame input and the parameter tables are never written by this library's kernels.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
+
 // ---- region helpers ------------------------------------------------------------------------
 struct Box { int x0, y0, x1, y1; };     // inclusive
 CRT_HD int box_w(const Box& b) { return b.x1 - b.x0 + 1; }

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
     float* Rp = Sb + 3 * NBX * PITCH;               // [3][NBY][P2_TW]   row-pass result per block row
     float* T1 = Rp + 3 * NBY * P2_TW;               // [3][TH/2][TW/2]   graded block values of the tile
     const int tid = threadIdx.x;
+    griddep_launch_dependents();        // the next frame's kernel may begin its state-independent phases (see launch_pdl)
     const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
     const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
     if (d.triad_mode >= 2) {
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
             *reinterpret_cast<float4*>(o0 + P2_TW) = make_float4(r[0].y, r[1].y, r[2].y, r[3].y);
         }
         __syncthreads();
+        griddep_wait();         // previous kernel of the stream complete: state / pre-warp image / noise may be touched from here on
 
         // ---- phase 3 + 4: column pass in registers, then the per-pixel tail for a 4 x 2 patch ----
         const int tx = tid & 15, ty = tid >> 4;
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
 
 template <int K, int MINB>
 inline int launch_fused_gauss_ps2_t(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
-                                    int has_prev, cudaStream_t st) {
+                                    int has_prev, cudaStream_t st, bool pdl) {
     static bool configured[64] = {};
     static int resident = 0;
     const size_t smem = fused_gauss_ps2_smem(K);
@@ -210,22 +212,22 @@ inline int launch_fused_gauss_ps2_t(const Dev& d, const FrameDev& f, const uint8
     const int ntiles = ((d.W + P2_TW - 1) / P2_TW) * ((d.H + P2_TH - 1) / P2_TH);
     const dim3 grid(ntiles < resident ? ntiles : resident);
     const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1 && !d.noise_on;
-    if (fast) k_fused_gauss_ps2<K, true, MINB><<<grid, P2_NT, smem, st>>>(d, f, in, out, state, q_out, has_prev);
-    else k_fused_gauss_ps2<K, false, MINB><<<grid, P2_NT, smem, st>>>(d, f, in, out, state, q_out, has_prev);
-    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+    const cudaError_t e = launch_pdl(fast ? k_fused_gauss_ps2<K, true, MINB> : k_fused_gauss_ps2<K, false, MINB>, grid, dim3(P2_NT), smem, st, pdl,
+                                     d, f, in, out, state, q_out, has_prev);
+    return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
 }
 
 inline int run_fused_gauss_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
-                               cudaStream_t st, int* launches) {
+                               cudaStream_t st, int* launches, bool pdl = false) {
     int rc = 4;
-    static const int minb = env_int("CRT_GPS2_MINB", 4);        // CTAs per SM the kernel is compiled for (64 vs 80 registers)
+    static const int minb = env_int("CRT_GPS2_MINB", 3);        // CTAs per SM the kernel is compiled for (64 vs 80 registers)
     switch (d.ksize) {
-        case 5: rc = minb == 3 ? launch_fused_gauss_ps2_t<5, 3>(d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_ps2_t<5, 4>(d, f, in, out, state, q_out, has_prev, st); break;
-        case 7: rc = minb == 3 ? launch_fused_gauss_ps2_t<7, 3>(d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_ps2_t<7, 4>(d, f, in, out, state, q_out, has_prev, st); break;
-        case 9: rc = minb == 3 ? launch_fused_gauss_ps2_t<9, 3>(d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_ps2_t<9, 4>(d, f, in, out, state, q_out, has_prev, st); break;
-        case 11: rc = minb == 3 ? launch_fused_gauss_ps2_t<11, 3>(d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_ps2_t<11, 4>(d, f, in, out, state, q_out, has_prev, st); break;
-        case 13: rc = minb == 3 ? launch_fused_gauss_ps2_t<13, 3>(d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_ps2_t<13, 4>(d, f, in, out, state, q_out, has_prev, st); break;
-        case 25: rc = minb == 3 ? launch_fused_gauss_ps2_t<25, 3>(d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_ps2_t<25, 4>(d, f, in, out, state, q_out, has_prev, st); break;
+        case 5: rc = minb == 3 ? launch_fused_gauss_ps2_t<5, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<5, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 7: rc = minb == 3 ? launch_fused_gauss_ps2_t<7, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<7, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 9: rc = minb == 3 ? launch_fused_gauss_ps2_t<9, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<9, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 11: rc = minb == 3 ? launch_fused_gauss_ps2_t<11, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<11, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 13: rc = minb == 3 ? launch_fused_gauss_ps2_t<13, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<13, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 25: rc = minb == 3 ? launch_fused_gauss_ps2_t<25, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<25, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
         default: break;
     }
     ++*launches;

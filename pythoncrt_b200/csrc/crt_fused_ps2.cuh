@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const
     __shared__ __align__(16) float Us[3][P2_BH][P2_BW + 2];      // graded block values, planar (row pitch 36 floats)
     __shared__ __align__(16) float Ss[3][P2_BH][P2_BW + 2];      // thresholded bloom source (only when the threshold is on)
     const int tid = threadIdx.x;
+    griddep_launch_dependents();        // the next frame's kernel may begin its state-independent phases (see launch_pdl)
     const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
     const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
     if (d.triad_mode >= 2) {
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const
         }
     }
     __syncthreads();
+    griddep_wait();         // previous kernel of the stream complete: state / pre-warp image / noise may be touched from here on
 
     // ---- phase 4: every thread owns 4 x 2 output pixels = two blocks side by side ------------------------
     const int tx = tid & 15, ty = tid >> 4;
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2_tma(Dev d, FrameDev f, cons
 }
 
 inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
-                         cudaStream_t st, int* launches) {
+                         cudaStream_t st, int* launches, bool pdl = false) {
     dim3 grid((d.W + P2_TW - 1) / P2_TW, (d.H + P2_TH - 1) / P2_TH);
     const int ntiles = (int)(grid.x * grid.y);
     static int resident = 0;                                     // CTAs the GPU holds at once: SMs x 4 (launch bounds)
@@ -421,15 +423,11 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
         ++*launches;
         return cudaGetLastError() == cudaSuccess ? 0 : 2;
     }
-    if (d.bloom_mode == 1) {
-        if (fast) k_fused_ps2<true, true><<<pgrid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
-        else k_fused_ps2<true, false><<<pgrid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
-    } else {
-        if (fast) k_fused_ps2<false, true><<<pgrid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
-        else k_fused_ps2<false, false><<<pgrid, P2_NT, 0, st>>>(d, f, in, out, state, q_out, has_prev);
-    }
+    auto kern = d.bloom_mode == 1 ? (fast ? k_fused_ps2<true, true> : k_fused_ps2<true, false>)
+                                  : (fast ? k_fused_ps2<false, true> : k_fused_ps2<false, false>);
+    const cudaError_t e = launch_pdl(kern, pgrid, dim3(P2_NT), 0, st, pdl, d, f, in, out, state, q_out, has_prev);
     ++*launches;
-    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+    return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
 }
 
 #endif  // __CUDACC__

@@ -212,8 +212,9 @@ class CrtEngine:
         """'state_prev = None' for the host-buffer path (crt_filter.py:1765)."""
         self._check(self.lib.crt_reset_state(self.ctx), "crt_reset_state")
 
-    def profile_begin(self, max_samples: int = 8192) -> None:
-        """Start recording CUDA events around the dominant kernel of every frame (bench.py)."""
+    def profile_begin(self, max_samples: int = 8192, every: int = 1) -> None:
+        """Start recording CUDA events around the dominant kernel of one frame in `every` (bench.py)."""
+        self._check(self.lib.crt_profile_sample_every(self.ctx, int(every)), "crt_profile_sample_every")
         self._check(self.lib.crt_profile_begin(self.ctx, int(max_samples)), "crt_profile_begin")
 
     def profile_end(self):
