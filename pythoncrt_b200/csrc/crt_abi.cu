@@ -43,7 +43,7 @@ struct crt_ctx {
     size_t tab_bytes[CRT_TABLE_COUNT] = {};
     std::vector<int32_t> h_pix_x, h_pix_y;                 // host copies (tile planning, pix_uniform)
     std::vector<float> h_cols, h_fwd, h_inv;               // host copies of the triad tables (composite LUT)
-    double* pow_tab = nullptr;                             // device tables of pow_unit
+    float* pow_tab = nullptr;                              // device tables of pow_unit
     float* comp_lut = nullptr;                             // device [2][1028] (16-byte aligned tables of 1025)
     std::vector<Lerp1> h_dn_x, h_dn_y, h_up_x, h_up_y;     // host copies of the fast-bloom coordinate tables
     Lerp1 *dn_x = nullptr, *dn_y = nullptr, *up_x = nullptr, *up_y = nullptr, *nz_x = nullptr, *nz_y = nullptr;
@@ -314,7 +314,7 @@ int crt_create(int device, int width, int height, crt_ctx** out_ctx) {
     if (!rc) rc = upload(c, &c->up_x, c->h_up_x);
     if (!rc) rc = upload(c, &c->up_y, c->h_up_y);
     if (!rc) {
-        double tab[POW_TAB_DOUBLES];
+        float tab[POW_TAB_FLOATS];
         fill_pow_table(tab);
         if (cudaMalloc((void**)&c->pow_tab, sizeof(tab)) != cudaSuccess || cudaMemcpy(c->pow_tab, tab, sizeof(tab), cudaMemcpyHostToDevice) != cudaSuccess)
             rc = fail(c, CRT_ERR_CUDA, "pow table upload failed");

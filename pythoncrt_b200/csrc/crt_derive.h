@@ -15,7 +15,7 @@ struct TablePtrs {
     const void* tab[CRT_TABLE_COUNT];
     size_t bytes[CRT_TABLE_COUNT];
     const Lerp1 *dn_x, *dn_y, *up_x, *up_y, *nz_x, *nz_y;
-    const double* pow_tab;   // [POW_TAB_DOUBLES] from fill_pow_table, in the caller's address space
+    const float* pow_tab;    // [POW_TAB_FLOATS] from fill_pow_table, in the caller's address space
     int pix_uniform;     // see Dev::pix_uniform (the caller inspects its host copy of the pixelate tables)
 };
 
@@ -62,7 +62,6 @@ inline int derive_dev(const crt_params& p, int W, int H, const TablePtrs& t, Dev
     d.contrast = (float)p.contrast; d.brightness = (float)p.brightness;
     d.col_gamma = p.gamma != 1.0 && p.gamma > 0.0;
     d.inv_gamma = d.col_gamma ? (float)(1.0 / p.gamma) : 1.0f;
-    d.inv_gamma32 = 32.0 * (double)d.inv_gamma;          // numpy narrows 1/gamma to float32 first
     d.pow_tab = t.pow_tab;
     d.text_mode = p.text_mode;
     if (p.text_mode) {

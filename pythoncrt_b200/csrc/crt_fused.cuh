@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
     extern __shared__ __align__(16) float sm[];
     __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
     __shared__ float s_unit[256];
-    __shared__ double s_pow[POW_TAB_DOUBLES];
+    __shared__ __align__(16) float s_pow[POW_TAB_FLOATS];
     __shared__ float s_rows[2 * FMAX_ROWS], s_cols[2 * FMAX_COLS];
     __shared__ int s_ci[2 * FMAX_COLS], s_ri[2 * FMAX_ROWS];       // fast bloom: up-scale tap offsets per Q column / row
     __shared__ float s_cw[FMAX_COLS], s_rw[FMAX_ROWS];              // ... and weights (cv2.resize coordinates)
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
         if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
     }
     if (tid < 256) s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
-    if (d.col_gamma && tid < POW_TAB_DOUBLES) s_pow[tid] = d.pow_tab[tid];
+    if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += blockDim.x) s_pow[i] = d.pow_tab[i];
     if (WARP && tid < 4) s_box[tid] = (tid < 2) ? 0x7fffffff : -0x7fffffff;
     __syncthreads();
 

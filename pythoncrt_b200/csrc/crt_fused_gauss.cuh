@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
     extern __shared__ __align__(16) float sm[];
     __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
     __shared__ float s_unit[256];
-    __shared__ double s_pow[POW_TAB_DOUBLES];
+    __shared__ __align__(16) float s_pow[POW_TAB_FLOATS];
     __shared__ float s_rows[2 * 64], s_cols[2 * FTW];
     __shared__ int s_geo[8];
     const int PH = th + 2 * R;                      // padded rows; th is even, so PH is even
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
         if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
     }
     if (tid < 256) s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
-    if (d.col_gamma && tid < POW_TAB_DOUBLES) s_pow[tid] = d.pow_tab[tid];
+    if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += blockDim.x) s_pow[i] = d.pow_tab[i];
     float taps[K];
 #pragma unroll
     for (int i = 0; i < K; ++i) taps[i] = d.taps[i];

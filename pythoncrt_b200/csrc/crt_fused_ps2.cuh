@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const
                                                      float* __restrict__ state, float* __restrict__ q_out, int has_prev) {
     __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
     __shared__ float s_unit[256];
-    __shared__ double s_pow[POW_TAB_DOUBLES];
+    __shared__ __align__(16) float s_pow[POW_TAB_FLOATS];
     __shared__ float s_rows[2 * P2_TH], s_cols[2 * P2_TW];
     __shared__ __align__(16) float Us[3][P2_BH][P2_BW + 2];      // graded block values, planar (row pitch 36 floats)
     __shared__ __align__(16) float Ss[3][P2_BH][P2_BW + 2];      // thresholded bloom source (only when the threshold is on)
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const
         if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
     }
     s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
-    if (d.col_gamma && tid < POW_TAB_DOUBLES) s_pow[tid] = d.pow_tab[tid];
+    if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += blockDim.x) s_pow[i] = d.pow_tab[i];
     MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
     // Persistent CTAs: the tables above are staged once, then the CTA walks over tiles
     // (tile = blockIdx.x, blockIdx.x + gridDim.x, ...; consecutive CTAs work on neighbouring tiles).
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2_tma(Dev d, FrameDev f, cons
     float (*Ss)[P2_BH][P2_BW + 2] = reinterpret_cast<float (*)[P2_BH][P2_BW + 2]>(dsm + P2_STATE_BYTES + P2_OUT_BYTES + P2_US_BYTES);
     __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
     __shared__ float s_unit[256];
-    __shared__ double s_pow[POW_TAB_DOUBLES];
+    __shared__ __align__(16) float s_pow[POW_TAB_FLOATS];
     __shared__ float s_rows[2 * P2_TH], s_cols[2 * P2_TW];
     __shared__ __align__(8) uint64_t s_bar;
     const int tid = threadIdx.x;
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2_tma(Dev d, FrameDev f, cons
         if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
     }
     s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
-    if (d.col_gamma && tid < POW_TAB_DOUBLES) s_pow[tid] = d.pow_tab[tid];
+    if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += blockDim.x) s_pow[i] = d.pow_tab[i];
     MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
     if (tid < P2_TH) {
         const int y = oy0 + tid;

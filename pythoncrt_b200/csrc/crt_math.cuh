@@ -40,10 +40,10 @@ namespace crt {
 #define CRT_POW_TABLE static const
 #include "crt_pow_tables.h"     // host copies; kernels read the same values through Dev::pow_tab / shared memory
 #undef CRT_POW_TABLE
-constexpr int POW_TAB_DOUBLES = 64;     // [invc 16 | logc 16 | 2^(j/32) 32]
-inline void fill_pow_table(double* t) {
-    for (int i = 0; i < 16; ++i) { t[i] = kPowInvC[i]; t[16 + i] = kPowLogC[i]; }
-    for (int j = 0; j < 32; ++j) t[32 + j] = kPowExp2[j];
+constexpr int POW_TAB_FLOATS = 32 * 4 + 32 * 2;     // [log: 32 x (invc, logc_hi, logc_lo, 0) | exp2: 32 x (hi, lo)]
+inline void fill_pow_table(float* t) {
+    for (int i = 0; i < 32; ++i) for (int c = 0; c < 4; ++c) t[4 * i + c] = kPowLog[i][c];
+    for (int j = 0; j < 32; ++j) { t[128 + 2 * j] = kPowExp2[j][0]; t[128 + 2 * j + 1] = kPowExp2[j][1]; }
 }
 
 // ---- exact float32 primitives ------------------------------------------------
@@ -116,8 +116,7 @@ struct Dev {
     // stage 3: colour (:279-305)
     int col_sat, col_temp, col_bc, col_gamma;
     float sat_f, gain0, gain2, contrast, brightness, inv_gamma;
-    double inv_gamma32;          // 32 * float32(1 / gamma), for pow_unit
-    const double* pow_tab;       // [POW_TAB_DOUBLES] tables of pow_unit
+    const float* pow_tab;        // [POW_TAB_FLOATS] tables of pow_unit (16-byte aligned)
     // text layer (:588-598 / :653-663)
     int text_mode;               // 0 none, 1 before, 2 after
     const uint8_t* text;         // [H][W][4]
@@ -185,12 +184,18 @@ CRT_HD void source_bytes(const Dev& d, const uint8_t* __restrict__ in, int y, in
 }
 
 // ---- x^y for the colour gamma (:304) ------------------------------------------------------------
-// numpy evaluates np.power(img, 1/gamma, dtype=float32) with SVML: within 1 ulp, not correctly
-// rounded, not reproducible elsewhere.  pow_unit is the table-driven scheme of glibc's powf
-// (16-entry log2 table + degree-6 polynomial, 32-entry exp2 table + degree-4 polynomial) in
-// double, rounded once: correctly rounded for all but ~1e-4 of inputs, max 1 ulp, ~40
-// instructions of which half run on the otherwise idle FP64 pipe (CUDA's powf: ~110).
-// Domain: x in [0, 1] (the stage input is clipped), y > 0, y32 = 32 * y.
+// numpy evaluates np.power(img, 1/gamma, dtype=float32) with SVML: within 1 ulp, correctly rounded
+// for only ~80 % of inputs, not reproducible elsewhere.  pow_unit is a table-driven float32 scheme
+// with double-float (hi, lo) intermediates where the precision is needed:
+//   log2 x = k + logc_i + log2(1 + r)   32 mantissa sub-intervals, r = m * invc_i - 1 held as an exact
+//                                       (hi, lo) pair, c1 * r as a double-float product, the r^2.. r^4
+//                                       terms in plain float32, the sum by Fast2Sum;
+//   E = y * log2 x                      double-float times float;
+//   x^y = 2^n * T_j * 2^f               n + j / 32 split off with a magic-number add, T_j = 2^(j/32)
+//                                       as (hi, lo), 2^f - 1 by a degree-4 polynomial, one final rounding.
+// ~50 float32 / integer instructions, no FP64 and no 64-bit integer work (the double version this
+// replaces compiled to ~115).  Error < 0.51 ulp; correctly rounded for ~99 % of inputs.
+// Domain: x in [0, 1] (the stage input is clipped), y > 0.  Results below 2^-125 flush to 0.
 CRT_HD uint32_t f2u(float f) {
 #if CRT_DEVICE_CODE
     return __float_as_uint(f);
@@ -205,49 +210,65 @@ CRT_HD float u2f(uint32_t u) {
     float f; memcpy(&f, &u, 4); return f;
 #endif
 }
-CRT_HD int64_t d2i(double v) {
-#if CRT_DEVICE_CODE
-    return __double_as_longlong(v);
-#else
-    int64_t u; memcpy(&u, &v, 8); return u;
-#endif
-}
-CRT_HD double i2d(int64_t u) {
-#if CRT_DEVICE_CODE
-    return __longlong_as_double(u);
-#else
-    double v; memcpy(&v, &u, 8); return v;
-#endif
-}
-CRT_HD float pow_unit(float x, double y32, const double* __restrict__ T) {
+CRT_HD float pow_unit(float x, float y, const float* __restrict__ T) {
     if (!(x >= 1.17549435e-38f)) return 0.0f;             // 0 (and sub-normals, which the chain never produces) -> 0
     const uint32_t ix = f2u(x), tmp = ix - 0x3f330000u;
-    const int i = (int)((tmp >> 19) & 15u);
+    const uint32_t i = (tmp >> 18) & 31u;
     const uint32_t top = tmp & 0xff800000u;
-    const double z = (double)u2f(ix - top);
-    const double k = (double)((int32_t)top >> 23);
-    const double r = fma(z, T[i], -1.0);
-    double p = 0x1.27cd35133559fp-2 + r * -0x1.ed17545dcd181p-3;      // kPowLogPoly[4], [5]
-    p = fma(p, r, -0x1.71546af33f6cfp-2);
-    p = fma(p, r, 0x1.ec7093a7cb7a1p-2);
-    p = fma(p, r, -0x1.71547652f0ec0p-1);
-    p = fma(p, r, 0x1.71547652cb19ap+0);
-    const double lg = fma(p, r, T[16 + i] + k);                          // log2(x)
-    const double e = lg * y32;                                           // 32 * log2(x^y), <= 0
-    if (e < -4800.0) return 0.0f;                                        // x^y < 2^-150
-    double kd = e + 0x1.8p52;
-    const int32_t ki = (int32_t)(uint32_t)d2i(kd);
-    kd -= 0x1.8p52;
-    const double rr = (e - kd) * 0.03125;
-    double q = fma(0x1.3b2b2da63a0d5p-7, rr, 0x1.c6b170b9195b7p-5);    // kPowExpPoly
-    q = fma(q, rr, 0x1.ebfbdff804db7p-3);
-    q = fma(q, rr, 0x1.62e42fef68811p-1);
-    const double s = i2d((int64_t)((uint64_t)d2i(T[32 + (ki & 31)]) + ((uint64_t)(int64_t)(ki >> 5) << 52)));
-    return (float)fma(s, q * rr, s);
+    const float m = u2f(ix - top);                                         // x = 2^k * m, m in [0.7, 1.4)
+    const float kf = fsub(u2f(0x4b400000u + (uint32_t)((int32_t)top >> 23)), 12582912.0f);      // (float)k without a conversion
+#if CRT_DEVICE_CODE
+    const float4 lt = *reinterpret_cast<const float4*>(T + 4 * i);
+    const float invc = lt.x, lch = lt.y, lcl = lt.z;
+#else
+    const float invc = T[4 * i], lch = T[4 * i + 1], lcl = T[4 * i + 2];
+#endif
+    // r = m * invc - 1 exactly, as rh + rl
+    const float ph = fmul(m, invc), rl = ffma(m, invc, -ph), rh = fsub(ph, 1.0f);
+    // c1 * r, c1 = 1 / ln 2 = c1h + c1l
+    const float c1h = 0x1.715476p+0f, c1l = 0x1.4ae0cp-26f;
+    const float P = fmul(c1h, rh);
+    float lo = ffma(c1h, rh, -P);
+    lo = ffma(c1l, rh, lo);
+    lo = ffma(c1h, rl, lo);
+    // c1 * (-r^2/2 + r^3/3 - r^4/4 + r^5/5)
+    const float r2 = fmul(rh, rh);
+    float q = ffma((float)(1.4426950408889634 / 5.0), rh, (float)(-1.4426950408889634 / 4.0));
+    q = ffma(q, rh, (float)(1.4426950408889634 / 3.0));
+    q = ffma(q, rh, (float)(-1.4426950408889634 / 2.0));
+    lo = ffma(r2, q, lo);
+    // log2 x = (k + logc_hi) + P + lo + logc_lo;  |k + logc_hi| >= 2 |P| or it is 0 (Fast2Sum is exact)
+    const float S = fadd(kf, lch);
+    const float hi = fadd(S, P);
+    lo = fadd(fadd(lo, lcl), fsub(P, fsub(hi, S)));
+    // E = y * log2 x as Eh + El
+    const float E0 = fmul(y, hi);
+    float El = ffma(y, lo, ffma(y, hi, -E0));                             // lo carries the r^2.. terms: up to 2^-12
+    const float Eh = fadd(E0, El);                                        // renormalise so that |El| <= ulp(Eh) / 2
+    El = fsub(El, fsub(Eh, E0));
+    if (Eh < -125.0f) return 0.0f;
+    const float t = fadd(Eh, 393216.0f);                                  // 1.5 * 2^18: ulp 2^-5, the mantissa holds round(32 Eh)
+    const uint32_t ki = f2u(t);
+    const float f = fsub(Eh, fsub(t, 393216.0f));                         // exact, |f| <= 2^-6
+    const uint32_t j = ki & 31u;
+#if CRT_DEVICE_CODE
+    const float2 tj = *reinterpret_cast<const float2*>(T + 128 + 2 * j);
+    const float th = tj.x, tl = tj.y;
+#else
+    const float th = T[128 + 2 * j], tl = T[128 + 2 * j + 1];
+#endif
+    const float ln2 = (float)0.6931471805599453;
+    float e = ffma((float)0.009618129107628477, f, (float)0.05550410866482158);     // ln2^4 / 24, ln2^3 / 6
+    e = ffma(e, f, (float)0.2402265069591007);                            // ln2^2 / 2
+    e = ffma(e, f, ln2);
+    e = fmul(e, f);
+    e = ffma(El, ln2, e);                                                 // 2^(f + El) - 1
+    const float res = fadd(th, ffma(th, e, tl));
+    return u2f(f2u(res) + ((ki & ~31u) << 18));                           // * 2^n, n = (round(32 Eh) - j) / 32
 }
 
 // apply_color_adjustments (:279-305), float32, numpy operation order.
-CRT_HD F3 colour(const Dev& d, F3 v, const double* __restrict__ pow_tab) {
+CRT_HD F3 colour(const Dev& d, F3 v, const float* __restrict__ pow_tab) {
     if (d.col_sat) {
         float l = fadd(fadd(fmul(0.2126f, v.x), fmul(0.7152f, v.y)), fmul(0.0722f, v.z));
         v.x = sat(fadd(l, fmul(fsub(v.x, l), d.sat_f)));
@@ -265,9 +286,9 @@ CRT_HD F3 colour(const Dev& d, F3 v, const double* __restrict__ pow_tab) {
     }
     if (d.col_gamma) {
         // cannot be matched bit for bit with numpy by any implementation (see pow_unit; DESIGN.md, parity)
-        v.x = sat(pow_unit(v.x, d.inv_gamma32, pow_tab));
-        v.y = sat(pow_unit(v.y, d.inv_gamma32, pow_tab));
-        v.z = sat(pow_unit(v.z, d.inv_gamma32, pow_tab));
+        v.x = sat(pow_unit(v.x, d.inv_gamma, pow_tab));
+        v.y = sat(pow_unit(v.y, d.inv_gamma, pow_tab));
+        v.z = sat(pow_unit(v.z, d.inv_gamma, pow_tab));
     }
     return v;
 }
@@ -295,7 +316,7 @@ CRT_HD F3 graded_input(const Dev& d, const uint8_t* __restrict__ in, int y, int 
 // Same, with the u8 -> float32 conversion read from a 256-entry table of unit() values
 // (identical results; saves three IEEE divisions per pixel in the fused kernel).
 CRT_HD F3 graded_input_lut(const Dev& d, const uint8_t* __restrict__ in, int y, int x, const float* __restrict__ unit_lut,
-                           const double* __restrict__ pow_tab) {
+                           const float* __restrict__ pow_tab) {
     uint8_t b0, b1, b2;
     source_bytes(d, in, y, x, b0, b1, b2);
     F3 v = colour(d, mk3(unit_lut[b0], unit_lut[b1], unit_lut[b2]), pow_tab);
@@ -306,7 +327,7 @@ CRT_HD F3 graded_input_lut(const Dev& d, const uint8_t* __restrict__ in, int y, 
 // Same for a pixel whose pixelate source (sy, sx) is already known (regular pixelate tables:
 // the block origin), skipping the index-table loads.
 CRT_HD F3 graded_source_lut(const Dev& d, const uint8_t* __restrict__ in, int sy, int sx, int y, int x, const float* __restrict__ unit_lut,
-                            const double* __restrict__ pow_tab) {
+                            const float* __restrict__ pow_tab) {
     const uint8_t* row = in + (size_t)sy * d.W * 3;
     int x0 = sx, x2 = sx;
     if (d.aberr != 0) { x0 = wrap(sx - d.aberr_mod, d.W); x2 = wrap(sx + d.aberr_mod, d.W); }

@@ -33,7 +33,7 @@ extern "C" int emu_process(const crt_params* p, int W, int H, const void* const*
     }
     t.dn_x = dn_x.data(); t.dn_y = dn_y.data(); t.up_x = up_x.data(); t.up_y = up_y.data();
     t.nz_x = nz_x.empty() ? nullptr : nz_x.data(); t.nz_y = nz_y.empty() ? nullptr : nz_y.data();
-    static double pow_tab[POW_TAB_DOUBLES];
+    alignas(16) static float pow_tab[POW_TAB_FLOATS];
     fill_pow_table(pow_tab);
     t.pow_tab = pow_tab;
     Dev d{};
@@ -109,8 +109,7 @@ extern "C" int emu_plan(const crt_params* p, int W, int H, const void* const* ta
 
 // pow_unit on arrays, for the accuracy test
 extern "C" void emu_pow_unit(const float* x, float* out, int n, double y) {
-    static double pow_tab[POW_TAB_DOUBLES];
+    alignas(16) static float pow_tab[POW_TAB_FLOATS];
     fill_pow_table(pow_tab);
-    const double y32 = 32.0 * (double)(float)y;
-    for (int i = 0; i < n; ++i) out[i] = pow_unit(x[i], y32, pow_tab);
+    for (int i = 0; i < n; ++i) out[i] = pow_unit(x[i], (float)y, pow_tab);
 }

@@ -35,17 +35,24 @@ def test_static_image_matches_apply_static_effects():
 
 def test_pow_unit_is_correctly_rounded_almost_everywhere():
     """csrc/crt_math.cuh pow_unit (colour gamma): against float64 pow rounded once.  numpy's own
-    float32 power differs from that reference in ~20 % of inputs (SVML, <= 1 ulp)."""
+    float32 power differs from that reference in ~20 % of inputs (SVML, <= 1 ulp); pow_unit in < 1 %
+    over the GUI's gamma range (0.1 .. 5), never by more than 1 ulp.  The error grows with 1 / gamma:
+    at the CLI's floor (gamma = 0.001, y = 1000) a few ulp are allowed."""
     import ctypes as C
     L = host_emu.lib()
     rng = np.random.default_rng(0)
     x = rng.random(400_000, dtype=np.float32)
     x[:256] = np.arange(256, dtype=np.float32) / 255
     x[256:259] = [1.0, 1e-30, 0.0]
+    x[300:20300] = np.float32(0.5) + rng.random(20000, dtype=np.float32) * np.float32(0.0117)     # widest |r| of the log table
     out = np.empty_like(x)
-    for gamma in (1.1, 2.2, 0.8, 3.0, 5.0, 0.2, 0.05, 0.001):
+    for gamma, max_ulp, max_miss in ((1.1, 1, 1e-2), (2.2, 1, 1e-2), (0.8, 1, 1e-2), (3.0, 1, 1e-2), (5.0, 1, 1e-2), (0.5, 1, 1e-2),
+                                     (0.2, 1, 2e-2), (0.1, 1, 4e-2), (0.05, 1, 8e-2), (0.001, 16, 1.0)):
         y = np.float32(1.0 / gamma)
         L.emu_pow_unit(x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_int(x.size), C.c_double(float(y)))
         ref = np.power(x.astype(np.float64), np.float64(y)).astype(np.float32)
-        ulp = np.abs(out.view(np.int32).astype(np.int64) - ref.view(np.int32))
-        assert ulp.max() <= 1 and (ulp > 0).mean() < 1e-3, (gamma, ulp.max(), (ulp > 0).mean())
+        big = ref > 1e-37                                   # results below 2^-125 flush to zero
+        ulp = np.abs(out.view(np.int32).astype(np.int64) - ref.view(np.int32))[big]
+        assert ulp.max() <= max_ulp and (ulp > 0).mean() < max_miss, (gamma, ulp.max(), (ulp > 0).mean())
+        assert np.all(out[~big] < 1e-37)
+        assert out[256] == 1.0 and out[258] == 0.0
