@@ -103,30 +103,28 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
             const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {                              // all loads first: their latencies overlap
-                const int u = tid + it * P2_NT;
-                if (u < NBX * NBY) {
-                    const int bj = u / NBX, bi = u - bj * NBX;
-                    const int sx = 2 * imin(imax(gbx0 + bi, 0), d.hw - 1), sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
-                    const uint8_t* row = in + (size_t)sy * d.W * 3;
-                    raw[it][0] = row[wrap(sx - a0, d.W) * 3 + 0];
-                    raw[it][1] = row[sx * 3 + 1];
-                    raw[it][2] = row[wrap(sx + a0, d.W) * 3 + 2];
-                }
+                if ((tid & ~31) + it * P2_NT >= NBX * NBY) break;            // warp-uniform: whole surplus warps skip the iteration
+                const int u = imin(tid + it * P2_NT, NBX * NBY - 1);         // surplus lanes repeat the last block (no divergence)
+                const int bj = u / NBX, bi = u - bj * NBX;
+                const int sx = 2 * imin(imax(gbx0 + bi, 0), d.hw - 1), sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
+                const uint8_t* row = in + (size_t)sy * d.W * 3;
+                raw[it][0] = row[wrap(sx - a0, d.W) * 3 + 0];
+                raw[it][1] = row[sx * 3 + 1];
+                raw[it][2] = row[wrap(sx + a0, d.W) * 3 + 2];
             }
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
-                const int u = tid + it * P2_NT;
-                if (u < NBX * NBY) {
-                    const int bj = u / NBX, bi = u - bj * NBX;
-                    const F3 v1 = colour(d, mk3(s_unit[raw[it][0]], s_unit[raw[it][1]], s_unit[raw[it][2]]), s_pow);
-                    const F3 sv = bloom_src(d, v1);
-                    float* s = Sb + bi * PITCH + bj;
-                    s[0] = sv.x; s[NBX * PITCH] = sv.y; s[2 * NBX * PITCH] = sv.z;
-                    const int ti = bi - HB, tj = bj - HB;
-                    if ((unsigned)ti < (unsigned)(P2_TW / 2) && (unsigned)tj < (unsigned)(P2_TH / 2)) {
-                        float* t = T1 + tj * (P2_TW / 2) + ti;
-                        t[0] = v1.x; t[(P2_TH / 2) * (P2_TW / 2)] = v1.y; t[2 * (P2_TH / 2) * (P2_TW / 2)] = v1.z;
-                    }
+                if ((tid & ~31) + it * P2_NT >= NBX * NBY) break;
+                const int u = imin(tid + it * P2_NT, NBX * NBY - 1);
+                const int bj = u / NBX, bi = u - bj * NBX;
+                const F3 v1 = colour(d, mk3(s_unit[raw[it][0]], s_unit[raw[it][1]], s_unit[raw[it][2]]), s_pow);
+                const F3 sv = bloom_src(d, v1);
+                float* s = Sb + bi * PITCH + bj;
+                s[0] = sv.x; s[NBX * PITCH] = sv.y; s[2 * NBX * PITCH] = sv.z;
+                const int ti = bi - HB, tj = bj - HB;
+                if ((unsigned)ti < (unsigned)(P2_TW / 2) && (unsigned)tj < (unsigned)(P2_TH / 2)) {
+                    float* t = T1 + tj * (P2_TW / 2) + ti;
+                    t[0] = v1.x; t[(P2_TH / 2) * (P2_TW / 2)] = v1.y; t[2 * (P2_TH / 2) * (P2_TW / 2)] = v1.z;
                 }
             }
         }

@@ -211,7 +211,8 @@ CRT_HD float u2f(uint32_t u) {
 #endif
 }
 CRT_HD float pow_unit(float x, float y, const float* __restrict__ T) {
-    if (!(x >= 1.17549435e-38f)) return 0.0f;             // 0 (and sub-normals, which the chain never produces) -> 0
+    // Straight-line code (the two special cases are selects at the end), so that the three channels'
+    // evaluations interleave in the instruction stream.
     const uint32_t ix = f2u(x), tmp = ix - 0x3f330000u;
     const uint32_t i = (tmp >> 18) & 31u;
     const uint32_t top = tmp & 0xff800000u;
@@ -246,7 +247,6 @@ CRT_HD float pow_unit(float x, float y, const float* __restrict__ T) {
     float El = ffma(y, lo, ffma(y, hi, -E0));                             // lo carries the r^2.. terms: up to 2^-12
     const float Eh = fadd(E0, El);                                        // renormalise so that |El| <= ulp(Eh) / 2
     El = fsub(El, fsub(Eh, E0));
-    if (Eh < -125.0f) return 0.0f;
     const float t = fadd(Eh, 393216.0f);                                  // 1.5 * 2^18: ulp 2^-5, the mantissa holds round(32 Eh)
     const uint32_t ki = f2u(t);
     const float f = fsub(Eh, fsub(t, 393216.0f));                         // exact, |f| <= 2^-6
@@ -264,7 +264,9 @@ CRT_HD float pow_unit(float x, float y, const float* __restrict__ T) {
     e = fmul(e, f);
     e = ffma(El, ln2, e);                                                 // 2^(f + El) - 1
     const float res = fadd(th, ffma(th, e, tl));
-    return u2f(f2u(res) + ((ki & ~31u) << 18));                           // * 2^n, n = (round(32 Eh) - j) / 32
+    const float out = u2f(f2u(res) + ((ki & ~31u) << 18));                // * 2^n, n = (round(32 Eh) - j) / 32
+    // x = 0 (and sub-normals, which the chain never produces) -> 0; results below 2^-125 -> 0
+    return (x >= 1.17549435e-38f && Eh >= -125.0f) ? out : 0.0f;
 }
 
 // apply_color_adjustments (:279-305), float32, numpy operation order.
