@@ -56,7 +56,10 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
     constexpr int MR = ((K + 2 + OFF) >> 1) + 1;                  // distinct block columns under 4 outputs' taps
     constexpr int MC = ((2 * R + 1 + OFF) >> 1) + 1;              // distinct block rows under 2 output rows' taps
     extern __shared__ __align__(16) float sm[];
-    __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
+    __shared__ __align__(16) float s_lut[2 * 1028];
+    __shared__ __align__(16) int s_sel[3][12];
+    float* const s_fwd = s_lut;
+    float* const s_inv = s_lut + 1028;
     __shared__ float s_unit[256];
     __shared__ __align__(16) float s_pow[POW_TAB_FLOATS];
     __shared__ float s_rows[2 * P2_TH], s_cols[2 * P2_TW];
@@ -73,6 +76,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
         if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
     }
     s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
+    ps2_fill_sel(s_sel, tid);
     if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += blockDim.x) s_pow[i] = d.pow_tab[i];
     float taps[K];                                  // the kernel is symmetric: R + 1 registers
 #pragma unroll
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
         const int gbx0 = (ox0 >> 1) - HB, gby0 = (oy0 >> 1) - HB;
         {
             constexpr int NIT = (NBX * NBY + P2_NT - 1) / P2_NT;
-            uint8_t raw[NIT][3];
+            uint32_t raw[NIT][3];                                 // 32-bit: a byte array would live in local memory
             const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {                              // all loads first: their latencies overlap
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
                     }
                 }
             }
-            ps2_patch_tail<true, FAST>(d, f, mt, s_fwd, s_inv, state, out, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
+            ps2_patch_tail<true, FAST>(d, f, mt, s_fwd, s_inv, s_sel, state, out, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
                                        [&](int r, int k) { return mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]); });
         }
         __syncthreads();        // everyone is done with this tile's tables before the next tile overwrites them

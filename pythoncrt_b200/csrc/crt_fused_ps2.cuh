@@ -32,20 +32,21 @@ CRT_HD bool fused_ps2_supported(const Dev& d, bool glitch_on) {
 // t1 = graded value of the two blocks, bloom(r, k) = blurred bloom source of pixel k of row r.
 template <bool BLOOM, bool FAST, typename BloomFn>
 __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, const MaskTabs& mt, const float* s_fwd, const float* s_inv,
-                                               float* __restrict__ state, uint8_t* __restrict__ out, float* __restrict__ q_out, int has_prev,
+                                               const int (*s_sel)[12], float* __restrict__ state, uint8_t* __restrict__ out, float* __restrict__ q_out, int has_prev,
                                                int ox0, int oy0, int ox1, int oy1, int xb, int y0, const float (&t1)[2][3], BloomFn&& bloom) {
     const bool fast = FAST && ox0 >= d.comp_x0 && ox1 <= d.comp_x1;        // block-uniform
     if (fast) {
         float cvig[4], cscan[4];
-        const float* tab[4][3];                                     // composite table (bright / dim) per column and channel
+        // composite table (bright: s_fwd, dim: s_inv == s_fwd + 1028) per column and channel, as index offsets
+        // looked up by the quad's mask phase (s_sel, filled once per CTA by ps2_fill_sel)
         const int ph0 = xb - 3 * (int)__umulhi((unsigned)xb, 0x55555556u);     // xb % 3
+        const int4* selp = reinterpret_cast<const int4*>(s_sel[ph0]);
+        const int4 sa = selp[0], sb = selp[1], sc = selp[2];
+        const int off[4][3] = {{sa.x, sa.y, sa.z}, {sa.w, sb.x, sb.y}, {sb.z, sb.w, sc.x}, {sc.y, sc.z, sc.w}};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             cvig[k] = d.vig_mode ? mt.col_vig[xb - ox0 + k] : 0.f;
             cscan[k] = d.scan_mode == 2 ? mt.col_scan[xb - ox0 + k] : 0.f;
-            const int ph = (ph0 + k) % 3;
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) tab[k][ch] = ph == ch ? s_fwd : s_inv;
         }
         const float vs = d.vig_mode ? d.vig_strength : 0.f;
 #pragma unroll
@@ -67,9 +68,9 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
                     const float shaped = (d.scan_inv_sharp == 1.0f) ? sv : __powf(sv, d.scan_inv_sharp);
                     m *= __fmaf_rn(-d.scan_strength, shaped, 1.0f);
                 }
-                v.x = __saturatef(tab[k][0][lut_index_fast(__saturatef(v.x))] * m);
-                v.y = __saturatef(tab[k][1][lut_index_fast(__saturatef(v.y))] * m);
-                v.z = __saturatef(tab[k][2][lut_index_fast(__saturatef(v.z))] * m);
+                v.x = __saturatef(s_fwd[lut_index_fast(__saturatef(v.x)) + off[k][0]] * m);
+                v.y = __saturatef(s_fwd[lut_index_fast(__saturatef(v.y)) + off[k][1]] * m);
+                v.z = __saturatef(s_fwd[lut_index_fast(__saturatef(v.z)) + off[k][2]] * m);
                 return v;
             };
             finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
@@ -89,14 +90,25 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
     }
 }
 
+// s_sel[p][3 k + ch]: index offset of the table column k (0..3) of a quad with xb % 3 == p uses for channel ch
+__device__ __forceinline__ void ps2_fill_sel(int (*s_sel)[12], int tid) {
+    if (tid < 36) {
+        const int p = tid / 12, e = tid - 12 * p, k = e / 3, ch = e - 3 * k;
+        s_sel[p][e] = ((p + k) % 3 == ch) ? 0 : 1028;
+    }
+}
+
 // FAST: the per-pixel tail is specialised for the default chain's feature set — regular triad mask
 // through the composite tables, per-row scanlines (or none), analytic vignette (or none), optional
 // flicker folded into the row factor, no noise.  Tiles that touch the mask's irregular edge columns
 // and every other feature set take the general tail (after_bloom_fast).
-template <bool BLOOM, bool FAST>
-__global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+template <bool BLOOM, bool FAST, int MINB>
+__global__ void __launch_bounds__(P2_NT, MINB) k_fused_ps2(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                      float* __restrict__ state, float* __restrict__ q_out, int has_prev) {
-    __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
+    __shared__ __align__(16) float s_lut[2 * 1028];
+    __shared__ __align__(16) int s_sel[3][12];
+    float* const s_fwd = s_lut;
+    float* const s_inv = s_lut + 1028;
     __shared__ float s_unit[256];
     __shared__ __align__(16) float s_pow[POW_TAB_FLOATS];
     __shared__ float s_rows[2 * P2_TH], s_cols[2 * P2_TW];
@@ -112,6 +124,7 @@ __global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const
         if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
     }
     s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
+    ps2_fill_sel(s_sel, tid);
     if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += blockDim.x) s_pow[i] = d.pow_tab[i];
     MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
     // Persistent CTAs: the tables above are staged once, then the CTA walks over tiles
@@ -137,7 +150,7 @@ __global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const
     const int gbx0 = (ox0 >> 1) - 1, gby0 = (oy0 >> 1) - 1;
     {
         constexpr int NIT = (P2_BW * P2_BH + P2_NT - 1) / P2_NT;          // 3 blocks per thread at most
-        uint8_t raw[NIT][3];
+        uint32_t raw[NIT][3];                                 // 32-bit: a byte array would live in local memory
         const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {                                  // all loads first: their latencies overlap
@@ -199,7 +212,7 @@ __global__ void __launch_bounds__(P2_NT, 4) k_fused_ps2(Dev d, FrameDev f, const
             }
         }
     }
-    ps2_patch_tail<BLOOM, FAST>(d, f, mt, s_fwd, s_inv, state, out, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
+    ps2_patch_tail<BLOOM, FAST>(d, f, mt, s_fwd, s_inv, s_sel, state, out, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
                                 [&](int r, int k) { return mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]); });
     }                       // this thread's patch
     __syncthreads();        // everyone is done with this tile's tables / block values
@@ -393,12 +406,13 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
                          cudaStream_t st, int* launches, bool pdl = false) {
     dim3 grid((d.W + P2_TW - 1) / P2_TW, (d.H + P2_TH - 1) / P2_TH);
     const int ntiles = (int)(grid.x * grid.y);
-    static int resident = 0;                                     // CTAs the GPU holds at once: SMs x 4 (launch bounds)
+    static int resident = 0;                                     // CTAs the GPU holds at once: SMs x MINB (launch bounds)
+    static const int minb = env_int("CRT_PS2_MINB", 4);
     if (!resident) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        resident = sms * 4 * env_int("CRT_PS2_WAVES", 1);
+        resident = sms * (minb == 3 ? 3 : 4) * env_int("CRT_PS2_WAVES", 1);
         if (env_int("CRT_PS2_PERSIST", 1) == 0) resident = 1 << 30;
     }
     const dim3 pgrid(ntiles < resident ? ntiles : resident);       // persistent 1-D grid (the TMA variant keeps the 2-D grid)
@@ -423,8 +437,8 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
         ++*launches;
         return cudaGetLastError() == cudaSuccess ? 0 : 2;
     }
-    auto kern = d.bloom_mode == 1 ? (fast ? k_fused_ps2<true, true> : k_fused_ps2<true, false>)
-                                  : (fast ? k_fused_ps2<false, true> : k_fused_ps2<false, false>);
+    auto kern = d.bloom_mode == 1 ? (fast ? (minb == 3 ? k_fused_ps2<true, true, 3> : k_fused_ps2<true, true, 4>) : k_fused_ps2<true, false, 4>)
+                                  : (fast ? k_fused_ps2<false, true, 4> : k_fused_ps2<false, false, 4>);
     const cudaError_t e = launch_pdl(kern, pgrid, dim3(P2_NT), 0, st, pdl, d, f, in, out, state, q_out, has_prev);
     ++*launches;
     return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
