@@ -84,8 +84,9 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
     MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
     __syncthreads();
     const int tiles_x = (d.W + P2_TW - 1) / P2_TW, ntiles = tiles_x * ((d.H + P2_TH - 1) / P2_TH);
+    const int step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;      // tile += gridDim.x without a division per tile
+    int tby = blockIdx.x / tiles_x, tbx = blockIdx.x - tby * tiles_x;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {      // persistent CTAs, tables staged once
-        const int tby = tile / tiles_x, tbx = tile - tby * tiles_x;
         const int ox0 = tbx * P2_TW, oy0 = tby * P2_TH;
         const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + P2_TH, d.H) - 1;
         if (tid < P2_TH) {
@@ -105,16 +106,35 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
             constexpr int NIT = (NBX * NBY + P2_NT - 1) / P2_NT;
             uint32_t raw[NIT][3];                                 // 32-bit: a byte array would live in local memory
             const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
+            // all loads first: their latencies overlap.  Tiles away from the left / right frame edge need neither the
+            // block clamp nor the aberration wrap in x: one 32-bit offset per block, byte offsets per channel.
+            const int as = a0 > (d.W >> 1) ? a0 - d.W : a0;                 // signed shift (aberr_mod is taken modulo W)
+            const int aa = as < 0 ? -as : as;
+            if (2 * gbx0 - aa >= 0 && 2 * (gbx0 + NBX - 1) + aa < d.W) {    // tile-uniform
+                const int W3 = d.W * 3;
 #pragma unroll
-            for (int it = 0; it < NIT; ++it) {                              // all loads first: their latencies overlap
-                if ((tid & ~31) + it * P2_NT >= NBX * NBY) break;            // warp-uniform: whole surplus warps skip the iteration
-                const int u = imin(tid + it * P2_NT, NBX * NBY - 1);         // surplus lanes repeat the last block (no divergence)
-                const int bj = u / NBX, bi = u - bj * NBX;
-                const int sx = 2 * imin(imax(gbx0 + bi, 0), d.hw - 1), sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
-                const uint8_t* row = in + (size_t)sy * d.W * 3;
-                raw[it][0] = row[wrap(sx - a0, d.W) * 3 + 0];
-                raw[it][1] = row[sx * 3 + 1];
-                raw[it][2] = row[wrap(sx + a0, d.W) * 3 + 2];
+                for (int it = 0; it < NIT; ++it) {
+                    if ((tid & ~31) + it * P2_NT >= NBX * NBY) break;        // warp-uniform: whole surplus warps skip the iteration
+                    const int u = imin(tid + it * P2_NT, NBX * NBY - 1);     // surplus lanes repeat the last block (no divergence)
+                    const int bj = u / NBX, bi = u - bj * NBX;
+                    const int sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
+                    const uint8_t* p = in + (unsigned)(sy * W3 + 6 * (gbx0 + bi));      // < 2^31 (checked by plan_fused)
+                    raw[it][0] = p[-3 * as];
+                    raw[it][1] = p[1];
+                    raw[it][2] = p[3 * as + 2];
+                }
+            } else {
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    if ((tid & ~31) + it * P2_NT >= NBX * NBY) break;
+                    const int u = imin(tid + it * P2_NT, NBX * NBY - 1);
+                    const int bj = u / NBX, bi = u - bj * NBX;
+                    const int sx = 2 * imin(imax(gbx0 + bi, 0), d.hw - 1), sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
+                    const uint8_t* row = in + (size_t)sy * d.W * 3;
+                    raw[it][0] = row[wrap(sx - a0, d.W) * 3 + 0];
+                    raw[it][1] = row[sx * 3 + 1];
+                    raw[it][2] = row[wrap(sx + a0, d.W) * 3 + 2];
+                }
             }
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
@@ -188,6 +208,8 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
                                        [&](int r, int k) { return mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]); });
         }
         __syncthreads();        // everyone is done with this tile's tables before the next tile overwrites them
+        tbx += step_x; tby += step_y;
+        if (tbx >= tiles_x) { tbx -= tiles_x; ++tby; }
     }
 }
 

@@ -130,8 +130,9 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_ps2(Dev d, FrameDev f, co
     // Persistent CTAs: the tables above are staged once, then the CTA walks over tiles
     // (tile = blockIdx.x, blockIdx.x + gridDim.x, ...; consecutive CTAs work on neighbouring tiles).
     const int tiles_x = (d.W + P2_TW - 1) / P2_TW, ntiles = tiles_x * ((d.H + P2_TH - 1) / P2_TH);
+    const int step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;      // tile += gridDim.x without a division per tile
+    int tby = blockIdx.x / tiles_x, tbx = blockIdx.x - tby * tiles_x;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int tby = tile / tiles_x, tbx = tile - tby * tiles_x;
     const int ox0 = tbx * P2_TW, oy0 = tby * P2_TH;
     const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + P2_TH, d.H) - 1;
     if (tid < P2_TH) {
@@ -152,16 +153,36 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_ps2(Dev d, FrameDev f, co
         constexpr int NIT = (P2_BW * P2_BH + P2_NT - 1) / P2_NT;          // 3 blocks per thread at most
         uint32_t raw[NIT][3];                                 // 32-bit: a byte array would live in local memory
         const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
+        // all loads first: their latencies overlap.  Tiles away from the left / right frame edge need neither the
+        // block clamp nor the aberration wrap in x: one 32-bit offset per block, byte offsets per channel.
+        const int as = a0 > (d.W >> 1) ? a0 - d.W : a0;                     // signed shift (aberr_mod is taken modulo W)
+        const int aa = as < 0 ? -as : as;
+        if (2 * gbx0 - aa >= 0 && 2 * (gbx0 + P2_BW - 1) + aa < d.W) {      // tile-uniform
+            const int W3 = d.W * 3;
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) {                                  // all loads first: their latencies overlap
-            const int u = tid + it * P2_NT;
-            if (u < P2_BW * P2_BH) {
-                const int bj = u / P2_BW, bi = u - bj * P2_BW;
-                const int sx = 2 * imin(imax(gbx0 + bi, 0), d.hw - 1), sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
-                const uint8_t* row = in + (size_t)sy * d.W * 3;
-                raw[it][0] = row[wrap(sx - a0, d.W) * 3 + 0];
-                raw[it][1] = row[sx * 3 + 1];
-                raw[it][2] = row[wrap(sx + a0, d.W) * 3 + 2];
+            for (int it = 0; it < NIT; ++it) {
+                const int u = tid + it * P2_NT;
+                if (u < P2_BW * P2_BH) {
+                    const int bj = u / P2_BW, bi = u - bj * P2_BW;
+                    const int sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
+                    const uint8_t* p = in + (unsigned)(sy * W3 + 6 * (gbx0 + bi));      // < 2^31 (checked by plan_fused)
+                    raw[it][0] = p[-3 * as];
+                    raw[it][1] = p[1];
+                    raw[it][2] = p[3 * as + 2];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int u = tid + it * P2_NT;
+                if (u < P2_BW * P2_BH) {
+                    const int bj = u / P2_BW, bi = u - bj * P2_BW;
+                    const int sx = 2 * imin(imax(gbx0 + bi, 0), d.hw - 1), sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
+                    const uint8_t* row = in + (size_t)sy * d.W * 3;
+                    raw[it][0] = row[wrap(sx - a0, d.W) * 3 + 0];
+                    raw[it][1] = row[sx * 3 + 1];
+                    raw[it][2] = row[wrap(sx + a0, d.W) * 3 + 2];
+                }
             }
         }
 #pragma unroll
@@ -216,6 +237,8 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_ps2(Dev d, FrameDev f, co
                                 [&](int r, int k) { return mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]); });
     }                       // this thread's patch
     __syncthreads();        // everyone is done with this tile's tables / block values
+    tbx += step_x; tby += step_y;
+    if (tbx >= tiles_x) { tbx -= tiles_x; ++tby; }
     }                       // tile loop
 }
 
