@@ -12,6 +12,7 @@
 // block indices reproduce cv2.resize's edge rule exactly (a lerp between equal values
 // returns the value).  Everything else (triad LUT, masks, persistence, stores) is shared
 // with the general fused kernel (crt_fused.cuh).  ~25 KB static shared memory, no dynamic.
+// Two variants: k_fused_ps2 (plain loads) and k_fused_ps2_pipe (tile input and state by TMA, below).
 #pragma once
 #include "crt_fused.cuh"
 #include "crt_tma.cuh"
@@ -33,7 +34,17 @@ CRT_HD bool fused_ps2_supported(const Dev& d, bool glitch_on) {
 template <bool BLOOM, bool FAST, typename BloomFn>
 __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, const MaskTabs& mt, const float* s_fwd, const float* s_inv,
                                                const int (*s_sel)[12], float* __restrict__ state, uint8_t* __restrict__ out, float* __restrict__ q_out, int has_prev,
-                                               int ox0, int oy0, int ox1, int oy1, int xb, int y0, const float (&t1)[2][3], BloomFn&& bloom) {
+                                               int ox0, int oy0, int ox1, int oy1, int xb, int y0, const float (&t1)[2][3], BloomFn&& bloom,
+                                               const float* s_prev = nullptr) {
+    // s_prev: the patch's previous state in shared memory (row pitch P2_TW * 3 floats) when a TMA copy fetched it
+    auto finish = [&](int r, int y, auto&& pixel) {
+        if (s_prev) {
+            const float4* sp = reinterpret_cast<const float4*>(s_prev + r * (P2_TW * 3));
+            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel, true, sp[0], sp[1], sp[2]);
+        } else {
+            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
+        }
+    };
     const bool fast = FAST && ox0 >= d.comp_x0 && ox1 <= d.comp_x1;        // block-uniform
     if (fast) {
         float cvig[4], cscan[4];
@@ -73,7 +84,7 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
                 v.z = __saturatef(s_fwd[lut_index_fast(__saturatef(v.z)) + off[k][2]] * m);
                 return v;
             };
-            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
+            finish(r, y, pixel);
         }
     } else {
 #pragma unroll
@@ -85,7 +96,7 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
                 if (BLOOM) v = add_bloom(d, v, bloom(r, k));
                 return after_bloom_fast(d, f, v, yy, x, s_fwd, s_inv, mt, yy - oy0, x - ox0);
             };
-            finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
+            finish(r, y, pixel);
         }
     }
 }
@@ -243,72 +254,67 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_ps2(Dev d, FrameDev f, co
 }
 
 
-// ---- TMA variant ---------------------------------------------------------------------------------
-// Same arithmetic; the persistence state tile is fetched with one bulk asynchronous copy per row
-// (cp.async.bulk, completion on an mbarrier) issued before any other work, so the 12 B/px state read
-// overlaps the block grading; results are staged in shared memory and leave with bulk stores (state
-// rows and packed uint8 rows).  No thread issues a global load/store for state or output.
-// Requires W % 16 == 0 (16-byte multiples for the uint8 rows).
-// MEASURED (round 1, run 18): correct, but SLOWER than the LDGSTS variant below — 8 193 vs 12 657
-// frames/s on the default chain at 4K — because a tile issues 96 row-sized (768 B / 192 B) 1-D bulk
-// copies that serialise in the copy engine.  Kept opt-in (CRT_TMA=1) as the base for a 2-D
-// tensor-map version (one copy per tile); not the default path.
-constexpr int P2_STATE_BYTES = P2_TH * P2_TW * 3 * 4, P2_OUT_BYTES = P2_TH * P2_TW * 3, P2_US_BYTES = 3 * P2_BH * (P2_BW + 2) * 4;
+// ---- TMA-pipelined variant ----------------------------------------------------------------------
+// Same arithmetic as k_fused_ps2; what changes is how a tile's data reaches the SM.  The plain kernel is
+// latency bound (ncu, run 28/30: issue slots 46 % busy, long-scoreboard stalls on the first use of the
+// input bytes and of the persistence state; removing instructions did not shorten it).  Here
+//   * the tile's input bytes — the 18 even rows x 224 bytes a tile's blocks read — arrive by ONE tiled
+//     tensor-map copy (TMA) per tile into a double buffer, issued one tile ahead (for the first tile:
+//     at kernel entry, before the previous frame's kernel has finished — see launch_pdl);
+//   * the tile's previous state (32 rows x 768 bytes) arrives by one TMA copy issued at the top of the
+//     tile's iteration and is consumed after the grading phase; the blend reads it from shared memory;
+// so no thread waits on a global load: the copies are in flight while the CTA (and the other CTAs of the
+// SM) compute.  Results still leave with plain 16-byte stores.  Tiles on the left / right frame edge,
+// where chromatic aberration wraps around (np.roll), read their bytes with the plain loads.
+// (Round 1, run 18: a first variant with one 1-D bulk copy per tile ROW was slower than plain loads —
+// 96 copies per tile serialise in the copy engine; hence one tensor-map copy per tile.)
+// Requires W % 8 == 0, |aberration| <= 3, 16-byte aligned clip / state pointers.
+constexpr int P2_RAW_W = 224, P2_RAW_BYTES = 4096;           // input buffer: 18 rows x 224 bytes (padded to 4 KB)
+constexpr int P2_ST_BYTES = P2_TH * P2_TW * 3 * 4;            // state tile: 32 x 192 float32
+constexpr int P2_PIPE_SMEM = P2_ST_BYTES + 2 * P2_RAW_BYTES;
 
-template <typename PixelFn>
-__device__ __forceinline__ void finish_quad_smem(const Dev& d, float* __restrict__ srow, uint8_t* __restrict__ orow, bool to_u8, int has_prev,
-                                                 int y, int xb, PixelFn&& pixel) {
-    const float pp = d.persist, pq = d.persist_q;
-    float4* sp = reinterpret_cast<float4*>(srow);
-    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa, pc = pa;
-    if (has_prev) { pa = sp[0]; pb = sp[1]; pc = sp[2]; }
-    const float prev[12] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, pc.x, pc.y, pc.z, pc.w};
-    float res[12];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        F3 v = pixel(y, xb + k, k);
-        if (has_prev) { v.x = blend_fast(prev[k * 3], v.x, pp, pq); v.y = blend_fast(prev[k * 3 + 1], v.y, pp, pq); v.z = blend_fast(prev[k * 3 + 2], v.z, pp, pq); }
-        res[k * 3] = v.x; res[k * 3 + 1] = v.y; res[k * 3 + 2] = v.z;
-    }
-    sp[0] = make_float4(res[0], res[1], res[2], res[3]);
-    sp[1] = make_float4(res[4], res[5], res[6], res[7]);
-    sp[2] = make_float4(res[8], res[9], res[10], res[11]);
-    if (to_u8) {
-        uint32_t* op = reinterpret_cast<uint32_t*>(orow);
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-            op[j] = pack4(res[j * 4], res[j * 4 + 1], res[j * 4 + 2], res[j * 4 + 3]);
-    }
-}
+struct Ps2Maps {                 // host-encoded tensor maps (crt_abi.cu)
+    CUtensorMap in;              // uint8 [frames][H/2 even rows][W*3], box 224 x 18 x 1
+    CUtensorMap st;              // float32 [H][W*3], box 192 x 32
+    int frame;                   // index of this launch's frame inside `in`
+    int use_state;               // 0: no previous state to fetch (first frame / first pass of the two-pass path)
+};
 
 template <bool BLOOM, bool FAST>
-__global__ void __launch_bounds__(P2_NT) k_fused_ps2_tma(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
-                                                         float* __restrict__ state, float* __restrict__ q_out, int has_prev) {
+__global__ void __launch_bounds__(P2_NT, 3) k_fused_ps2_pipe(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                          float* __restrict__ state, float* __restrict__ q_out, int has_prev,
+                                                          const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_st,
+                                                          int frame) {
     extern __shared__ __align__(128) unsigned char dsm[];
-    float* s_state = reinterpret_cast<float*>(dsm);                               // [TH][TW*3] float32
-    uint8_t* s_out = dsm + P2_STATE_BYTES;                                          // [TH][TW*3] uint8
-    float (*Us)[P2_BH][P2_BW + 2] = reinterpret_cast<float (*)[P2_BH][P2_BW + 2]>(dsm + P2_STATE_BYTES + P2_OUT_BYTES);
-    float (*Ss)[P2_BH][P2_BW + 2] = reinterpret_cast<float (*)[P2_BH][P2_BW + 2]>(dsm + P2_STATE_BYTES + P2_OUT_BYTES + P2_US_BYTES);
-    __shared__ __align__(16) float s_fwd[1028], s_inv[1028];
+    float* s_state = reinterpret_cast<float*>(dsm);                                 // [TH][TW*3]
+    uint8_t* s_raw = dsm + P2_ST_BYTES;                                               // [2][18][224]
+    __shared__ __align__(16) float s_lut[2 * 1028];
+    __shared__ __align__(16) int s_sel[3][12];
+    float* const s_fwd = s_lut;
+    float* const s_inv = s_lut + 1028;
     __shared__ float s_unit[256];
     __shared__ __align__(16) float s_pow[POW_TAB_FLOATS];
     __shared__ float s_rows[2 * P2_TH], s_cols[2 * P2_TW];
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(16) float Us[3][P2_BH][P2_BW + 2];
+    __shared__ __align__(16) float Ss[3][P2_BH][P2_BW + 2];
+    __shared__ __align__(8) uint64_t bar_in[2], bar_st;
     const int tid = threadIdx.x;
-    const int ox0 = blockIdx.x * P2_TW, oy0 = blockIdx.y * P2_TH;
-    const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + P2_TH, d.H) - 1;
-    const int rows = oy1 - oy0 + 1, tw = ox1 - ox0 + 1;
-    float* gdst = q_out ? q_out : state;                    // float rows written at the end (pre-warp image in the two-pass path)
-    const bool load_prev = has_prev && !q_out;
-
-    if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
-    __syncthreads();
-    if (load_prev && tid < 32) {                            // warp 0: one bulk copy per tile row, all in flight at once
-        if (tid == 0) mbar_expect_tx(&s_bar, (uint32_t)(rows * tw * 12));
-        __syncwarp();
-        if (tid < rows) bulk_g2s(s_state + tid * (P2_TW * 3), state + ((size_t)(oy0 + tid) * d.W + ox0) * 3, (uint32_t)(tw * 12), &s_bar);
+    griddep_launch_dependents();
+    const bool use_state = has_prev && !q_out;
+    const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
+    const int as = a0 > (d.W >> 1) ? a0 - d.W : a0;                         // signed shift (aberr_mod is taken modulo W)
+    const int aa = as < 0 ? -as : as;
+    const int tiles_x = (d.W + P2_TW - 1) / P2_TW, ntiles = tiles_x * ((d.H + P2_TH - 1) / P2_TH);
+    const int step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;
+    int tby = blockIdx.x / tiles_x, tbx = blockIdx.x - tby * tiles_x;
+    if (tid == 0) {
+        mbar_init(&bar_in[0], 1); mbar_init(&bar_in[1], 1); mbar_init(&bar_st, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&map_in); tma_prefetch_desc(&map_st);
+        // first tile's input: independent of the previous kernel
+        mbar_expect_tx(&bar_in[0], P2_RAW_W * P2_BH);
+        tma_load_3d(s_raw, &map_in, 6 * ((tbx * P2_TW >> 1) - 1) - 3 * aa, (tby * P2_TH >> 1) - 1, frame, &bar_in[0]);
     }
-
     const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
     const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
     if (d.triad_mode >= 2) {
@@ -317,118 +323,147 @@ __global__ void __launch_bounds__(P2_NT) k_fused_ps2_tma(Dev d, FrameDev f, cons
         if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
     }
     s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
+    ps2_fill_sel(s_sel, tid);
     if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += blockDim.x) s_pow[i] = d.pow_tab[i];
     MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
-    if (tid < P2_TH) {
-        const int y = oy0 + tid;
-        if (d.scan_mode == 1) mt.row_scan[tid] = scan_row(d, f, y);
-        else if (d.scan_mode == 2) { double t = ((double)y + f.phase) * d.scan_inv_period; mt.row_scan[tid] = (float)(t - floor(t)); }
-        if (d.vig_mode == 1) { const float ny = ((float)y - d.vig_cy) * d.vig_iry; mt.row_vig[tid] = ny * ny; }
-    } else if (tid >= 64 && tid < 64 + P2_TW) {
-        const int c = tid - 64, x = ox0 + c;
-        if (d.scan_mode == 2) { double t = (d.scan_tan * (double)x) * d.scan_inv_period; mt.col_scan[c] = (float)(t - floor(t)); }
-        if (d.vig_mode == 1) { const float nx = ((float)x - d.vig_cx) * d.vig_irx; mt.col_vig[c] = nx * nx; }
-    }
-    __syncthreads();
-
-    // ---- phase 1: one graded value per 2x2 block ----
-    const int gbx0 = (ox0 >> 1) - 1, gby0 = (oy0 >> 1) - 1;
-    for (int u = tid; u < P2_BW * P2_BH; u += P2_NT) {
-        const int bj = u / P2_BW, bi = u - bj * P2_BW;
-        const int gbi = imin(imax(gbx0 + bi, 0), d.hw - 1), gbj = imin(imax(gby0 + bj, 0), d.hh - 1);
-        const F3 v1 = graded_source_lut(d, in, 2 * gbj, 2 * gbi, 2 * gbj, 2 * gbi, s_unit, s_pow);
-        Us[0][bj][bi] = v1.x; Us[1][bj][bi] = v1.y; Us[2][bj][bi] = v1.z;
-        if (BLOOM && d.thr_on) {
-            const F3 sv = bloom_src(d, v1);
-            Ss[0][bj][bi] = sv.x; Ss[1][bj][bi] = sv.y; Ss[2][bj][bi] = sv.z;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int ox0 = tbx * P2_TW, oy0 = tby * P2_TH;
+        const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + P2_TH, d.H) - 1;
+        const int gbx0 = (ox0 >> 1) - 1, gby0 = (oy0 >> 1) - 1;
+        // next tile of this CTA
+        int nbx = tbx + step_x, nby = tby + step_y;
+        if (nbx >= tiles_x) { nbx -= tiles_x; ++nby; }
+        if (tid == 0) {
+            if (it > 0 && use_state) {           // this tile's state (the previous tile's tail has finished with the buffer)
+                mbar_expect_tx(&bar_st, P2_ST_BYTES);
+                tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st);
+            }
+            if (tile + (int)gridDim.x < ntiles) {      // next tile's input into the other buffer (last read two barriers ago)
+                mbar_expect_tx(&bar_in[buf ^ 1], P2_RAW_W * P2_BH);
+                tma_load_3d(s_raw + (buf ^ 1) * P2_RAW_BYTES, &map_in, 6 * ((nbx * P2_TW >> 1) - 1) - 3 * aa, (nby * P2_TH >> 1) - 1, frame,
+                            &bar_in[buf ^ 1]);
+            }
         }
-    }
-    __syncthreads();
-    if (load_prev) mbar_wait(&s_bar, 0);                    // state tile has landed
+        if (tid < P2_TH) {
+            const int y = oy0 + tid;
+            if (d.scan_mode == 1) mt.row_scan[tid] = scan_row(d, f, y);
+            else if (d.scan_mode == 2) { double t = ((double)y + f.phase) * d.scan_inv_period; mt.row_scan[tid] = (float)(t - floor(t)); }
+            if (d.vig_mode == 1) { const float ny = ((float)y - d.vig_cy) * d.vig_iry; mt.row_vig[tid] = ny * ny; }
+        } else if (tid >= 64 && tid < 64 + P2_TW) {
+            const int c = tid - 64, x = ox0 + c;
+            if (d.scan_mode == 2) { double t = (d.scan_tan * (double)x) * d.scan_inv_period; mt.col_scan[c] = (float)(t - floor(t)); }
+            if (d.vig_mode == 1) { const float nx = ((float)x - d.vig_cx) * d.vig_irx; mt.col_vig[c] = nx * nx; }
+        }
+        __syncthreads();        // tables staged (first tile); mask tables visible
 
-    // ---- phase 4 ----
-    const int tx = tid & 15, ty = tid >> 4;
-    const int xb = ox0 + 4 * tx, y0 = oy0 + 2 * ty;
-    if (xb <= ox1 && y0 <= oy1) {
-        const int bi = 2 * tx + 1, bj = ty + 1;
-        float bl[2][4][3];
-        float t1[2][3];
+        // ---- phase 1: one graded value per 2x2 block ----
+        mbar_wait(&bar_in[buf], (it >> 1) & 1);                 // this tile's input bytes have landed
+        {
+            constexpr int NIT = (P2_BW * P2_BH + P2_NT - 1) / P2_NT;
+            const bool x_inside = 2 * gbx0 - aa >= 0 && 2 * (gbx0 + P2_BW - 1) + aa < d.W;       // tile-uniform
+            const uint8_t* rawb = s_raw + buf * P2_RAW_BYTES;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            t1[0][ch] = Us[ch][bj][bi]; t1[1][ch] = Us[ch][bj][bi + 1];
-            if (BLOOM) {
-                const float (*src)[P2_BW + 2] = d.thr_on ? Ss[ch] : Us[ch];
-                float h[3][4];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const float2 ca = *reinterpret_cast<const float2*>(&src[bj - 1 + r][bi - 1]);
-                    const float2 cb = *reinterpret_cast<const float2*>(&src[bj - 1 + r][bi + 1]);
-                    const float d01 = fsub(ca.y, ca.x), d12 = fsub(cb.x, ca.y), d23 = fsub(cb.y, cb.x);
-                    h[r][0] = ffma(d01, 0.75f, ca.x); h[r][1] = ffma(d12, 0.25f, ca.y);
-                    h[r][2] = ffma(d12, 0.75f, ca.y); h[r][3] = ffma(d23, 0.25f, cb.x);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    bl[0][k][ch] = ffma(fsub(h[1][k], h[0][k]), 0.75f, h[0][k]);
-                    bl[1][k][ch] = ffma(fsub(h[2][k], h[1][k]), 0.25f, h[1][k]);
+            for (int i = 0; i < NIT; ++i) {
+                const int u = tid + i * P2_NT;
+                if (u < P2_BW * P2_BH) {
+                    const int bj = u / P2_BW, bi = u - bj * P2_BW;
+                    uint32_t r0, r1, r2;
+                    if (x_inside) {
+                        // buffer row of the (clamped) block row; byte 0 of the buffer is byte 6 gbx0 - 3 aa of the frame row
+                        const uint8_t* p = rawb + (imin(imax(gby0 + bj, 0), d.hh - 1) - gby0) * P2_RAW_W + 6 * bi + 3 * aa;
+                        r0 = p[-3 * as]; r1 = p[1]; r2 = p[3 * as + 2];
+                    } else {
+                        const int sx = 2 * imin(imax(gbx0 + bi, 0), d.hw - 1), sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
+                        const uint8_t* row = in + (size_t)sy * d.W * 3;
+                        r0 = row[wrap(sx - a0, d.W) * 3 + 0]; r1 = row[sx * 3 + 1]; r2 = row[wrap(sx + a0, d.W) * 3 + 2];
+                    }
+                    const F3 v1 = colour(d, mk3(s_unit[r0], s_unit[r1], s_unit[r2]), s_pow);
+                    Us[0][bj][bi] = v1.x; Us[1][bj][bi] = v1.y; Us[2][bj][bi] = v1.z;
+                    if (BLOOM && d.thr_on) {
+                        const F3 sv = bloom_src(d, v1);
+                        Ss[0][bj][bi] = sv.x; Ss[1][bj][bi] = sv.y; Ss[2][bj][bi] = sv.z;
+                    }
                 }
             }
         }
-        const bool fast = FAST && ox0 >= d.comp_x0 && ox1 <= d.comp_x1;
-        float cvig[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* tab[4][3];
-        const int ph0 = xb - 3 * (int)__umulhi((unsigned)xb, 0x55555556u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (fast && d.vig_mode) cvig[k] = mt.col_vig[xb - ox0 + k];
-            const int ph = (ph0 + k) % 3;
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) tab[k][ch] = ph == ch ? s_fwd : s_inv;
-        }
-        const float vs = d.vig_mode ? d.vig_strength : 0.f;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int y = y0 + r;
-            if (y > oy1) break;
-            float* srow = s_state + (y - oy0) * (P2_TW * 3) + 12 * tx;
-            uint8_t* orow = s_out + (y - oy0) * (P2_TW * 3) + 12 * tx;
-            if (fast) {
-                const float rfac = (d.scan_mode ? mt.row_scan[y - oy0] : 1.0f) * (f.flicker_on ? f.flicker : 1.0f);
-                const float rvig = d.vig_mode ? mt.row_vig[y - oy0] : 0.f;
-                auto pixel = [&](int, int, int k) -> F3 {
-                    F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
-                    if (BLOOM) v = add_bloom(d, v, mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]));
-                    const float m = rfac * __fmaf_rn(-vs, __saturatef(rvig + cvig[k]), 1.0f);
-                    v.x = __saturatef(tab[k][0][lut_index(v.x)] * m);
-                    v.y = __saturatef(tab[k][1][lut_index(v.y)] * m);
-                    v.z = __saturatef(tab[k][2][lut_index(v.z)] * m);
-                    return v;
-                };
-                finish_quad_smem(d, srow, orow, !q_out, load_prev, y, xb, pixel);
-            } else {
-                auto pixel = [&](int yy, int x, int k) -> F3 {
-                    F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
-                    if (BLOOM) v = add_bloom(d, v, mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]));
-                    return after_bloom_fast(d, f, v, yy, x, s_fwd, s_inv, mt, yy - oy0, x - ox0);
-                };
-                finish_quad_smem(d, srow, orow, !q_out, load_prev, y, xb, pixel);
+        __syncthreads();
+        griddep_wait();         // previous kernel of the stream complete: state / pre-warp image / noise may be touched from here on
+        if (use_state) {
+            if (it == 0 && tid == 0) {           // first tile: the state may only be fetched now
+                mbar_expect_tx(&bar_st, P2_ST_BYTES);
+                tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st);
             }
+            mbar_wait(&bar_st, it & 1);
         }
-    }
-    fence_proxy_async();                                    // results in shared memory -> visible to the bulk-copy engine
-    __syncthreads();
-    if (tid < rows) {
-        if (gdst) bulk_s2g(gdst + ((size_t)(oy0 + tid) * d.W + ox0) * 3, s_state + tid * (P2_TW * 3), (uint32_t)(tw * 12));
-        if (!q_out) bulk_s2g(out + ((size_t)(oy0 + tid) * d.W + ox0) * 3, s_out + tid * (P2_TW * 3), (uint32_t)(tw * 3));
-        bulk_commit();
-        bulk_wait_read();
+
+        // ---- phase 4 ----
+        const int tx = tid & 15, ty = tid >> 4;
+        const int xb = ox0 + 4 * tx, y0 = oy0 + 2 * ty;
+        if (xb <= ox1 && y0 <= oy1) {
+            const int bi = 2 * tx + 1, bj = ty + 1;
+            float bl[2][4][3];
+            float t1[2][3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                t1[0][ch] = Us[ch][bj][bi]; t1[1][ch] = Us[ch][bj][bi + 1];
+                if (BLOOM) {
+                    const float (*src)[P2_BW + 2] = d.thr_on ? Ss[ch] : Us[ch];
+                    float h[3][4];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const float2 ca = *reinterpret_cast<const float2*>(&src[bj - 1 + r][bi - 1]);
+                        const float2 cb = *reinterpret_cast<const float2*>(&src[bj - 1 + r][bi + 1]);
+                        const float d01 = fsub(ca.y, ca.x), d12 = fsub(cb.x, ca.y), d23 = fsub(cb.y, cb.x);
+                        h[r][0] = ffma(d01, 0.75f, ca.x); h[r][1] = ffma(d12, 0.25f, ca.y);
+                        h[r][2] = ffma(d12, 0.75f, ca.y); h[r][3] = ffma(d23, 0.25f, cb.x);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        bl[0][k][ch] = ffma(fsub(h[1][k], h[0][k]), 0.75f, h[0][k]);
+                        bl[1][k][ch] = ffma(fsub(h[2][k], h[1][k]), 0.25f, h[1][k]);
+                    }
+                }
+            }
+            ps2_patch_tail<BLOOM, FAST>(d, f, mt, s_fwd, s_inv, s_sel, state, out, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
+                                        [&](int r, int k) { return mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]); },
+                                        use_state ? s_state + (y0 - oy0) * (P2_TW * 3) + 12 * tx : nullptr);
+        }
+        __syncthreads();        // everyone is done with this tile's tables, block values and state tile
+        tbx = nbx; tby = nby;
     }
 }
 
+inline bool fused_ps2_pipe_supported(const Dev& d) {
+    const int a0 = d.aberr != 0 ? d.aberr_mod : 0, as = a0 > (d.W >> 1) ? a0 - d.W : a0;
+    return (d.W & 7) == 0 && as >= -3 && as <= 3 && env_int("CRT_PIPE", 1) != 0;
+}
+
 inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
-                         cudaStream_t st, int* launches, bool pdl = false) {
+                         cudaStream_t st, int* launches, bool pdl = false, const Ps2Maps* maps = nullptr) {
     dim3 grid((d.W + P2_TW - 1) / P2_TW, (d.H + P2_TH - 1) / P2_TH);
     const int ntiles = (int)(grid.x * grid.y);
+    const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1 && !d.noise_on;
+    if (maps) {                                                  // TMA-pipelined variant, 3 CTAs per SM
+        static int resident3 = 0;
+        if (!resident3) {
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaFuncSetAttribute(k_fused_ps2_pipe<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM);
+            cudaFuncSetAttribute(k_fused_ps2_pipe<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM);
+            cudaFuncSetAttribute(k_fused_ps2_pipe<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM);
+            cudaFuncSetAttribute(k_fused_ps2_pipe<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM);
+            resident3 = sms * 3;
+        }
+        auto kern = d.bloom_mode == 1 ? (fast ? k_fused_ps2_pipe<true, true> : k_fused_ps2_pipe<true, false>)
+                                      : (fast ? k_fused_ps2_pipe<false, true> : k_fused_ps2_pipe<false, false>);
+        const cudaError_t e = launch_pdl(kern, dim3(ntiles < resident3 ? ntiles : resident3), dim3(P2_NT), (size_t)P2_PIPE_SMEM, st, pdl,
+                                         d, f, in, out, state, q_out, has_prev, maps->in, maps->st, maps->frame);
+        ++*launches;
+        return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
+    }
     static int resident = 0;                                     // CTAs the GPU holds at once: SMs x MINB (launch bounds)
     static const int minb = env_int("CRT_PS2_MINB", 4);
     if (!resident) {
@@ -438,28 +473,7 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
         resident = sms * (minb == 3 ? 3 : 4) * env_int("CRT_PS2_WAVES", 1);
         if (env_int("CRT_PS2_PERSIST", 1) == 0) resident = 1 << 30;
     }
-    const dim3 pgrid(ntiles < resident ? ntiles : resident);       // persistent 1-D grid (the TMA variant keeps the 2-D grid)
-    const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1 && !d.noise_on;
-    if ((d.W & 15) == 0 && env_int("CRT_TMA", 0)) {      // bulk-copy variant: opt-in, measured slower (see header note)
-        const size_t smem = P2_STATE_BYTES + P2_OUT_BYTES + P2_US_BYTES * ((d.bloom_mode == 1 && d.thr_on) ? 2 : 1);
-        static bool configured = false;
-        if (!configured) {
-            cudaFuncSetAttribute(k_fused_ps2_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            cudaFuncSetAttribute(k_fused_ps2_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            cudaFuncSetAttribute(k_fused_ps2_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            cudaFuncSetAttribute(k_fused_ps2_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            configured = true;
-        }
-        if (d.bloom_mode == 1) {
-            if (fast) k_fused_ps2_tma<true, true><<<grid, P2_NT, smem, st>>>(d, f, in, out, state, q_out, has_prev);
-            else k_fused_ps2_tma<true, false><<<grid, P2_NT, smem, st>>>(d, f, in, out, state, q_out, has_prev);
-        } else {
-            if (fast) k_fused_ps2_tma<false, true><<<grid, P2_NT, smem, st>>>(d, f, in, out, state, q_out, has_prev);
-            else k_fused_ps2_tma<false, false><<<grid, P2_NT, smem, st>>>(d, f, in, out, state, q_out, has_prev);
-        }
-        ++*launches;
-        return cudaGetLastError() == cudaSuccess ? 0 : 2;
-    }
+    const dim3 pgrid(ntiles < resident ? ntiles : resident);       // persistent 1-D grid
     auto kern = d.bloom_mode == 1 ? (fast ? (minb == 3 ? k_fused_ps2<true, true, 3> : k_fused_ps2<true, true, 4>) : k_fused_ps2<true, false, 4>)
                                   : (fast ? k_fused_ps2<false, true, 4> : k_fused_ps2<false, false, 4>);
     const cudaError_t e = launch_pdl(kern, pgrid, dim3(P2_NT), 0, st, pdl, d, f, in, out, state, q_out, has_prev);

@@ -1,7 +1,9 @@
-// crt_tma.cuh — thin wrappers over the sm_90+/sm_100 bulk asynchronous copy ("TMA 1-D") and
-// mbarrier PTX used by the fused kernels to move whole tile rows between HBM and shared memory
-// without tying up registers or load/store instructions (SASS: UBLKCP / SYNCS).
+// crt_tma.cuh — thin wrappers over the sm_90+/sm_100 bulk asynchronous copies (TMA: 1-D bulk and
+// tiled tensor-map copies) and mbarrier PTX used by the block kernels to move whole tiles between
+// HBM and shared memory without tying up registers or load/store instructions
+// (SASS: UBLKCP / UTMALDG / SYNCS), plus the host-side tensor-map encoder.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -46,5 +48,44 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 // wait until the bulk stores of this thread have finished READING shared memory
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// Tiled tensor-map loads (one instruction per tile): coordinates are element indices, innermost first;
+// out-of-range elements are filled with zeros; completion (box bytes) is signalled on the mbarrier.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
 #endif
+
+// Host: encode a tiled tensor map (no swizzle, no interleave, zero fill) through the driver entry point
+// (no link-time dependency on libcuda).  dims / box innermost first; strides in bytes for dims 1.. (rank - 1 entries).
+inline bool tma_encode(CUtensorMap* map, CUtensorMapDataType type, int rank, const void* base, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn fn = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_fn>(p);
+    }
+    if (!fn) return false;
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bd[5], es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bd[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+    return fn(map, type, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bd, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace crt
