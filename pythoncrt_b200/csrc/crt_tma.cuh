@@ -29,10 +29,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol error must trap (CUDA error), never hang the GPU.
+// Bounded wait: a protocol error must trap (CUDA error) within about a second, never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
-        if (it > (1u << 26)) __trap();
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > 2000000000LL) __trap();
 }
 
 // global -> shared, completion signalled on an mbarrier (bytes and both addresses multiples of 16)
@@ -50,6 +52,8 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 
 // Tiled tensor-map loads (one instruction per tile): coordinates are element indices, innermost first;
 // out-of-range elements are filled with zeros; completion (box bytes) is signalled on the mbarrier.
+// The innermost coordinate must address a 16-byte aligned element (measured on the B200: an unaligned
+// start raises an illegal-instruction exception), the shared-memory destination 128-byte aligned.
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
