@@ -58,8 +58,8 @@ struct crt_ctx {
     Dev dev{};
     bool dev_ok = false;
     int policy = 0;
-    Ps2Maps maps{};                     // tensor map of the TMA-pipelined block kernel, valid for the state buffer maps_st
-    const void* maps_st = nullptr;
+    Ps2Maps maps{};                     // tensor maps of the TMA-pipelined block kernel, valid for (maps_in, maps_frames, maps_st)
+    const void* maps_in = nullptr; const void* maps_st = nullptr; int maps_frames = 0;
     FusedPlan plan{};                   // single-pass fused kernel
     FusedPlan plan_q{};                 // two-pass: fused first pass without warp/glitch/text-after, then k_gather
     Dev dev_q{};                        // parameter block of that first pass
@@ -200,16 +200,21 @@ int run_staged(crt_ctx* ctx, const FrameDev& f, const uint8_t* d_in, uint8_t* d_
     return CRT_OK;
 }
 
-// Tensor map for k_fused_ps2_pipe: the persistence state as float32 [H][W*3] (box 192 x 32).
-// Returns false when the variant cannot be used.
-bool prepare_ps2_maps(crt_ctx* ctx, const Dev& d, const float* d_state) {
-    if (!d_state || !fused_ps2_pipe_supported(d) || ((uintptr_t)d_state & 15)) return false;
-    if (ctx->maps_st == d_state) return true;
+// Tensor maps for k_fused_ps2_pipe: the clip as uint8 [frames * H/2 even rows][W*3] (box 256 x 18) and the
+// persistence state as float32 [H][W*3] (box 192 x 32).  Returns false when the variant cannot be used.
+bool prepare_ps2_maps(crt_ctx* ctx, const Dev& d, const uint8_t* d_in, int n_frames, const float* d_state) {
+    if (!d_state || !fused_ps2_pipe_supported(d)) return false;
+    if (((uintptr_t)d_in & 15) || ((uintptr_t)d_state & 15)) return false;
+    if (ctx->maps_in == d_in && ctx->maps_frames == n_frames && ctx->maps_st == d_state) return true;
     const uint64_t W3 = (uint64_t)d.W * 3;
+    // even rows of all frames as one 2-D tensor: the frame pitch W3 * H is (H / 2) row pitches of 2 * W3
+    const uint64_t in_dims[2] = {W3, (uint64_t)(d.H / 2) * n_frames}, in_strides[1] = {2 * W3};
+    const uint32_t in_box[2] = {(uint32_t)P2_RAW_W, (uint32_t)P2_BH};
+    if (!tma_encode(&ctx->maps.in, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d_in, in_dims, in_strides, in_box)) return false;
     const uint64_t st_dims[2] = {W3, (uint64_t)d.H}, st_strides[1] = {W3 * 4};
     const uint32_t st_box[2] = {(uint32_t)P2_TW * 3, (uint32_t)P2_TH};
     if (!tma_encode(&ctx->maps.st, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_state, st_dims, st_strides, st_box)) return false;
-    ctx->maps_st = d_state;
+    ctx->maps_in = d_in; ctx->maps_frames = n_frames; ctx->maps_st = d_state;
     return true;
 }
 
@@ -233,8 +238,8 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         return fail(ctx, CRT_ERR_UNSUPPORTED, std::string("fused kernel not available: ") + ctx->plan.why);
     if (want_two_pass && !ctx->scratch.q) CU(cudaMalloc((void**)&ctx->scratch.q, frame_px * 3 * sizeof(float)));
     static const bool use_pdl = env_int("CRT_PDL", 1) != 0;
-    // TMA-pipelined block kernel: needs a tensor map of this call's state buffer
-    const bool pipe = want_fused && ctx->plan.ps2 && !ctx->plan.gauss_k && persist && prepare_ps2_maps(ctx, d, d_state);
+    // TMA-pipelined block kernel: needs tensor maps of this call's clip and state buffers
+    const bool pipe = want_fused && ctx->plan.ps2 && !ctx->plan.gauss_k && persist && prepare_ps2_maps(ctx, d, d_in, n_frames, d_state);
     for (int i = 0; i < n_frames; ++i) {
         const crt_frame& fr = frames[i];
         FrameDev f = derive_frame(p, fr);
@@ -276,6 +281,7 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         // Frames after the first may overlap the previous frame's kernel tail (launch_pdl, crt_fused.cuh).  Never frame 0:
         // its input may come from the caller's immediately preceding kernel.
         const bool pdl = i > 0 && use_pdl;
+        ctx->maps.frame = i;
         int rc;
         if (want_fused) {
             prof_mark(ctx, st, false);

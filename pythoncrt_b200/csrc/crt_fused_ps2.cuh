@@ -255,33 +255,47 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_ps2(Dev d, FrameDev f, co
 
 
 // ---- TMA-pipelined variant ----------------------------------------------------------------------
-// Same arithmetic as k_fused_ps2; what changes is how a tile's previous state reaches the SM.  The plain
-// kernel is latency bound (ncu, run 28/30: issue slots 46 % busy, long-scoreboard stalls on the first use
-// of the input bytes and of the persistence state; removing instructions did not shorten it).  Here the
-// tile's previous state (32 rows x 768 bytes) arrives by ONE tiled tensor-map copy (TMA) issued at the top
-// of the tile's iteration, is consumed after the grading phase, and the blend reads it from shared memory:
-// no thread waits on a state load, and 24 KB per CTA are in flight while the CTA (and the other CTAs of the
-// SM) compute.  Results still leave with plain 16-byte stores.
-// Measured (round 1): 66.0 vs 70.7 us per 4K frame with 4 CTAs per SM (run 35); with 3 CTAs per SM the
-// gain is lost (72.5 us, run 33).  Fetching the tile's INPUT bytes the same way (2-D map over the even rows,
-// 256 x 18 box one tile ahead, LDS.U8 in the grading phase) was slower than the batched byte loads
-// (62.5 vs 59.7 us without state, run 35) and is not done.  A first variant with one 1-D bulk copy per tile
-// ROW (run 18) was slower than plain loads — 96 copies per tile serialise in the copy engine.
-// Requires W % 4 == 0 and a 16-byte aligned state pointer; used when every CTA has several tiles.
+// Same arithmetic as k_fused_ps2; what changes is how a tile's data reaches the SM.  The plain kernel is
+// latency bound (ncu, run 28/30: issue slots 46 % busy, long-scoreboard stalls on the first use of the
+// input bytes and of the persistence state; removing instructions did not shorten it).  Here
+//   * the tile's input bytes — 18 even rows x 256 bytes around what the tile's blocks read — arrive by ONE
+//     tiled tensor-map copy (TMA) per tile into a double buffer, issued one tile ahead (for the first tile:
+//     at kernel entry, before the previous frame's kernel has finished — see launch_pdl);
+//   * the tile's previous state (32 rows x 768 bytes) arrives by one TMA copy issued at the top of the
+//     tile's iteration and is consumed after the grading phase; the blend reads it from shared memory;
+// so no thread waits on a global load: the copies are in flight while the CTA (and the other CTAs of the
+// SM) compute.  Results still leave with plain 16-byte stores.  Tiles on the left / right frame edge,
+// where chromatic aberration wraps around (np.roll), read their bytes with the plain loads.
+// Measured (round 1, default chain at 4K): 66.0 us per frame against 70.7 us for the plain kernel with
+// 4 CTAs per SM (run 35).  Each half alone does not pay: state by TMA with the input on batched byte loads
+// 70.3 us (run 36); input by TMA without a state to fetch 62.5 vs 59.7 us (first pass of the two-pass path,
+// run 35); with 3 CTAs per SM 72.5 us (run 33).  A first variant with one 1-D bulk copy per tile ROW
+// (run 18) was slower still — 96 copies per tile serialise in the copy engine.
+// TMA facts measured with tests/_probe/tma_probe.cu: the innermost start coordinate must be 16-byte
+// aligned (else: illegal-instruction exception), out-of-range and negative coordinates are zero-filled
+// and count towards the barrier's byte count, a [frames][rows][bytes] map with a box of 1 frame never
+// completed — hence one 2-D map over the even rows of all frames (the frame pitch is H/2 row pitches).
+// Requires W % 8 == 0, |aberration| <= 6, 16-byte aligned clip / state pointers; used when there is a
+// state to fetch and every CTA walks over several tiles.
+constexpr int P2_RAW_W = 256, P2_RAW_BYTES = P2_RAW_W * P2_BH;   // input buffer: 18 rows x 256 bytes (the box starts 16-byte aligned)
 constexpr int P2_ST_BYTES = P2_TH * P2_TW * 3 * 4;            // state tile: 32 x 192 float32
-constexpr int P2_PIPE_SMEM = P2_ST_BYTES;
+constexpr int P2_PIPE_SMEM = P2_ST_BYTES + 2 * P2_RAW_BYTES;
 
-struct Ps2Maps {                 // host-encoded tensor map (crt_abi.cu)
+struct Ps2Maps {                 // host-encoded tensor maps (crt_abi.cu)
+    CUtensorMap in;              // uint8 [frames * H/2 even rows][W*3] (row pitch 2 W*3), box 256 x 18
     CUtensorMap st;              // float32 [H][W*3], box 192 x 32
+    int frame;                   // index of this launch's frame inside `in`
 };
 
 // THR: the bloom threshold is on (a second block array for the thresholded source; 3 CTAs per SM instead of 4)
 template <bool BLOOM, bool FAST, bool THR>
 __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                           float* __restrict__ state, float* __restrict__ q_out, int has_prev,
-                                                          const __grid_constant__ CUtensorMap map_st) {
+                                                          const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_st,
+                                                          int frame) {
     extern __shared__ __align__(128) unsigned char dsm[];
     float* s_state = reinterpret_cast<float*>(dsm);                                 // [TH][TW*3]
+    uint8_t* s_raw = dsm + P2_ST_BYTES;                                               // [2][18][256]
     __shared__ __align__(16) float s_lut[2 * 1028];
     __shared__ __align__(16) int s_sel[3][12];
     float* const s_fwd = s_lut;
@@ -291,14 +305,23 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, Fr
     __shared__ float s_rows[2 * P2_TH], s_cols[2 * P2_TW];
     __shared__ __align__(16) float Us[3][P2_BH][P2_BW + 2];
     __shared__ __align__(16) float Ss[THR ? 3 : 1][THR ? P2_BH : 1][P2_BW + 2];
-    __shared__ __align__(8) uint64_t bar_st;
+    __shared__ __align__(8) uint64_t bar_in[2], bar_st;
     const int tid = threadIdx.x;
     griddep_launch_dependents();
     const bool use_state = has_prev && !q_out;
+    const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
+    const int as = a0 > (d.W >> 1) ? a0 - d.W : a0;                         // signed shift (aberr_mod is taken modulo W)
+    const int aa = as < 0 ? -as : as;
     const int tiles_x = (d.W + P2_TW - 1) / P2_TW, ntiles = tiles_x * ((d.H + P2_TH - 1) / P2_TH);
     const int step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;
     int tby = blockIdx.x / tiles_x, tbx = blockIdx.x - tby * tiles_x;
-    if (tid == 0) { mbar_init(&bar_st, 1); fence_mbar_init(); }
+    if (tid == 0) {
+        mbar_init(&bar_in[0], 1); mbar_init(&bar_in[1], 1); mbar_init(&bar_st, 1);
+        fence_mbar_init();
+        // first tile's input: independent of the previous kernel
+        mbar_expect_tx(&bar_in[0], P2_RAW_BYTES);
+        tma_load_2d(s_raw, &map_in, (6 * ((tbx * P2_TW >> 1) - 1) - 3 * aa) & ~15, frame * d.hh + (tby * P2_TH >> 1) - 1, &bar_in[0]);
+    }
     const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
     const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
     if (d.triad_mode >= 2) {
@@ -318,9 +341,17 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, Fr
         // next tile of this CTA
         int nbx = tbx + step_x, nby = tby + step_y;
         if (nbx >= tiles_x) { nbx -= tiles_x; ++nby; }
-        if (tid == 0 && it > 0 && use_state) {   // this tile's state (the previous tile's tail has finished with the buffer)
-            mbar_expect_tx(&bar_st, P2_ST_BYTES);
-            tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st);
+        const int buf = it & 1;
+        if (tid == 0) {
+            if (it > 0 && use_state) {           // this tile's state (the previous tile's tail has finished with the buffer)
+                mbar_expect_tx(&bar_st, P2_ST_BYTES);
+                tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st);
+            }
+            if (tile + (int)gridDim.x < ntiles) {      // next tile's input into the other buffer (last read two barriers ago)
+                mbar_expect_tx(&bar_in[buf ^ 1], P2_RAW_BYTES);
+                tma_load_2d(s_raw + (buf ^ 1) * P2_RAW_BYTES, &map_in, (6 * ((nbx * P2_TW >> 1) - 1) - 3 * aa) & ~15,
+                            frame * d.hh + (nby * P2_TH >> 1) - 1, &bar_in[buf ^ 1]);
+            }
         }
         if (tid < P2_TH) {
             const int y = oy0 + tid;
@@ -334,49 +365,29 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, Fr
         }
         __syncthreads();        // tables staged (first tile); mask tables visible
 
-    // ---- phase 1: one graded value per 2x2 block (tile + one halo block, clamped = cv2's edge rule) ----
+        // ---- phase 1: one graded value per 2x2 block ----
+        mbar_wait(&bar_in[buf], (it >> 1) & 1);                 // this tile's input bytes have landed
         {
-            constexpr int NIT = (P2_BW * P2_BH + P2_NT - 1) / P2_NT;          // 3 blocks per thread at most
-            uint32_t raw[NIT][3];                                 // 32-bit: a byte array would live in local memory
-            const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
-            // all loads first: their latencies overlap.  Tiles away from the left / right frame edge need neither the
-            // block clamp nor the aberration wrap in x: one 32-bit offset per block, byte offsets per channel.
-            const int as = a0 > (d.W >> 1) ? a0 - d.W : a0;                     // signed shift (aberr_mod is taken modulo W)
-            const int aa = as < 0 ? -as : as;
-            if (2 * gbx0 - aa >= 0 && 2 * (gbx0 + P2_BW - 1) + aa < d.W) {      // tile-uniform
-                const int W3 = d.W * 3;
-#pragma unroll
-                for (int i = 0; i < NIT; ++i) {
-                    const int u = tid + i * P2_NT;
-                    if (u < P2_BW * P2_BH) {
-                        const int bj = u / P2_BW, bi = u - bj * P2_BW;
-                        const int sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
-                        const uint8_t* p = in + (unsigned)(sy * W3 + 6 * (gbx0 + bi));      // < 2^31 (checked by plan_fused)
-                        raw[i][0] = p[-3 * as];
-                        raw[i][1] = p[1];
-                        raw[i][2] = p[3 * as + 2];
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < NIT; ++i) {
-                    const int u = tid + i * P2_NT;
-                    if (u < P2_BW * P2_BH) {
-                        const int bj = u / P2_BW, bi = u - bj * P2_BW;
-                        const int sx = 2 * imin(imax(gbx0 + bi, 0), d.hw - 1), sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
-                        const uint8_t* row = in + (size_t)sy * d.W * 3;
-                        raw[i][0] = row[wrap(sx - a0, d.W) * 3 + 0];
-                        raw[i][1] = row[sx * 3 + 1];
-                        raw[i][2] = row[wrap(sx + a0, d.W) * 3 + 2];
-                    }
-                }
-            }
+            constexpr int NIT = (P2_BW * P2_BH + P2_NT - 1) / P2_NT;
+            const bool x_inside = 2 * gbx0 - aa >= 0 && 2 * (gbx0 + P2_BW - 1) + aa < d.W;       // tile-uniform
+            const uint8_t* rawb = s_raw + buf * P2_RAW_BYTES;
+            const int xoff = 6 * gbx0 - ((6 * gbx0 - 3 * aa) & ~15);
 #pragma unroll
             for (int i = 0; i < NIT; ++i) {
                 const int u = tid + i * P2_NT;
                 if (u < P2_BW * P2_BH) {
                     const int bj = u / P2_BW, bi = u - bj * P2_BW;
-                    const F3 v1 = colour(d, mk3(s_unit[raw[i][0]], s_unit[raw[i][1]], s_unit[raw[i][2]]), s_pow);
+                    uint32_t r0, r1, r2;
+                    if (x_inside) {
+                        // buffer row of the (clamped) block row; byte 0 of the buffer is byte (6 gbx0 - 3 aa) & ~15 of the frame row
+                        const uint8_t* p = rawb + (imin(imax(gby0 + bj, 0), d.hh - 1) - gby0) * P2_RAW_W + 6 * bi + xoff;
+                        r0 = p[-3 * as]; r1 = p[1]; r2 = p[3 * as + 2];
+                    } else {
+                        const int sx = 2 * imin(imax(gbx0 + bi, 0), d.hw - 1), sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
+                        const uint8_t* row = in + (size_t)sy * d.W * 3;
+                        r0 = row[wrap(sx - a0, d.W) * 3 + 0]; r1 = row[sx * 3 + 1]; r2 = row[wrap(sx + a0, d.W) * 3 + 2];
+                    }
+                    const F3 v1 = colour(d, mk3(s_unit[r0], s_unit[r1], s_unit[r2]), s_pow);
                     Us[0][bj][bi] = v1.x; Us[1][bj][bi] = v1.y; Us[2][bj][bi] = v1.z;
                     if (BLOOM && THR) {
                         const F3 sv = bloom_src(d, v1);
@@ -432,7 +443,10 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, Fr
     }
 }
 
-inline bool fused_ps2_pipe_supported(const Dev& d) { return (d.W & 3) == 0 && env_int("CRT_PIPE", 1) != 0; }
+inline bool fused_ps2_pipe_supported(const Dev& d) {
+    const int a0 = d.aberr != 0 ? d.aberr_mod : 0, as = a0 > (d.W >> 1) ? a0 - d.W : a0;
+    return (d.W & 7) == 0 && as >= -6 && as <= 6 && env_int("CRT_PIPE", 1) != 0;
+}
 
 inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
                          cudaStream_t st, int* launches, bool pdl = false, const Ps2Maps* maps = nullptr) {
@@ -461,7 +475,7 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
         }
         const int resident_pipe = sms * (thr ? 3 : 4);
         const cudaError_t e = launch_pdl(kern, dim3(ntiles < resident_pipe ? ntiles : resident_pipe), dim3(P2_NT), (size_t)P2_PIPE_SMEM, st, pdl,
-                                         d, f, in, out, state, q_out, has_prev, maps->st);
+                                         d, f, in, out, state, q_out, has_prev, maps->in, maps->st, maps->frame);
         ++*launches;
         return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
     }
