@@ -156,7 +156,10 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_ps2(Dev d, FrameDev f, co
         if (d.scan_mode == 2) { double t = (d.scan_tan * (double)x) * d.scan_inv_period; mt.col_scan[c] = (float)(t - floor(t)); }
         if (d.vig_mode == 1) { const float nx = ((float)x - d.vig_cx) * d.vig_irx; mt.col_vig[c] = nx * nx; }
     }
-    __syncthreads();        // tables ready (and, from the second tile on, the previous tile's block values are dead)
+    // The LUT / u8->float tables staged before the loop must be visible before the first grading phase.  Later tiles
+    // need no barrier here: the mask tables written above are read after the next barrier, and the previous tile's
+    // block values died at the barrier that ended its iteration.
+    if (tile == (int)blockIdx.x) __syncthreads();
 
     // ---- phase 1: one graded value per 2x2 block (tile + one halo block, clamped = cv2's edge rule) ----
     const int gbx0 = (ox0 >> 1) - 1, gby0 = (oy0 >> 1) - 1;
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, Fr
             if (d.scan_mode == 2) { double t = (d.scan_tan * (double)x) * d.scan_inv_period; mt.col_scan[c] = (float)(t - floor(t)); }
             if (d.vig_mode == 1) { const float nx = ((float)x - d.vig_cx) * d.vig_irx; mt.col_vig[c] = nx * nx; }
         }
-        __syncthreads();        // tables staged (first tile); mask tables visible
+        if (it == 0) __syncthreads();      // tables staged before the loop; later tiles need no barrier here (see k_fused_ps2)
 
         // ---- phase 1: one graded value per 2x2 block ----
         mbar_wait(&bar_in[buf], (it >> 1) & 1);                 // this tile's input bytes have landed
