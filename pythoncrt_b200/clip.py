@@ -20,6 +20,56 @@ from .params import CrtParams
 EIGHTH_LSB = 1.0 / 2040.0
 
 
+def iter_rawvideo(stream, width: int, height: int):
+    """Frames of an `rgb24` rawvideo byte stream, as FFmpegPipeReader.iter_frames yields them
+    (/root/reference/crt_filter.py:494-502): W*H*3 bytes per frame, a short read ends the clip."""
+    import numpy as np
+    frame_size = width * height * 3
+    while True:
+        buf = stream.read(frame_size)
+        if not buf or len(buf) < frame_size:
+            break
+        yield np.frombuffer(buf, dtype=np.uint8).reshape((height, width, 3))
+
+
+def process_rawvideo(engine, src, dst, *, fps: float = 30.0, first_index: int = 0, chunk_frames: int = 0, pinned: bool = True) -> int:
+    """Stream an `rgb24` rawvideo clip (the byte format of the reference's ffmpeg pipes: reader
+    /root/reference/crt_filter.py:484-502, writer write_frame :1101) through a configured
+    CrtEngine: `src.read` -> pinned host chunk -> crt_process_host (copies and kernels overlap
+    inside the library) -> `dst.write`.  The persistence state is carried across chunks on the
+    device, frame indices continue from `first_index`.  Returns the number of frames written."""
+    import numpy as np
+    h, w = engine.height, engine.width
+    fbytes = h * w * 3
+    if chunk_frames <= 0:
+        chunk_frames = max(1, min(256, (192 << 20) // fbytes))
+    if pinned:
+        import torch
+        h_in = torch.empty((chunk_frames, h, w, 3), dtype=torch.uint8).pin_memory().numpy()
+        h_out = torch.empty((chunk_frames, h, w, 3), dtype=torch.uint8).pin_memory().numpy()
+    else:
+        h_in = np.empty((chunk_frames, h, w, 3), np.uint8)
+        h_out = np.empty_like(h_in)
+    engine.reset_state()
+    done = 0
+    frames = iter_rawvideo(src, w, h)
+    while True:
+        n = 0
+        for fr in frames:
+            h_in[n] = fr
+            n += 1
+            if n == chunk_frames:
+                break
+        if n == 0:
+            break
+        engine.process_host(h_in[:n], h_out[:n], fps=fps, first_index=first_index + done)
+        dst.write(h_out[:n].tobytes() if not hasattr(dst, "write_frames") else h_out[:n])
+        done += n
+        if n < chunk_frames:
+            break
+    return done
+
+
 def halo_frames(persistence: float, eps: float = EIGHTH_LSB) -> int:
     """Warm-up frames K with persistence^K <= eps (0 when persistence is off)."""
     p = float(persistence)

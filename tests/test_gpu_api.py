@@ -74,6 +74,24 @@ def test_host_buffer_path_equals_device_path():
     assert np.array_equal(eng.process_host(frames[:2], fps=case.fps), out[:2])   # pageable memory works too
 
 
+def test_rawvideo_stream_equals_device_path():
+    """clip.process_rawvideo (rgb24 pipe format of the reference, crt_filter.py:484-502 / :1101) against
+    the device-resident path, chunked so that the state crosses chunk boundaries."""
+    import io
+    import torch
+    import host_emu
+    from pythoncrt_b200 import CrtEngine, clip
+    case = CASES_BY_NAME["cfg1_cli_default"]
+    frames = np.stack(case_frames(case) * 4)                         # 12 frames
+    eng = CrtEngine(case.w, case.h).configure(host_emu.oracle_to_product_params(case.params))
+    dev, _ = eng.process(torch.from_numpy(frames).cuda(), fps=case.fps)
+    dst = io.BytesIO()
+    n = clip.process_rawvideo(eng, io.BytesIO(frames.tobytes() + b"\x00" * 100), dst, fps=case.fps, chunk_frames=5)
+    assert n == 12
+    got = np.frombuffer(dst.getvalue(), np.uint8).reshape(frames.shape)
+    assert np.array_equal(got, dev.cpu().numpy())
+
+
 def test_device_generators():
     import torch
     from pythoncrt_b200 import CrtEngine, CrtParams

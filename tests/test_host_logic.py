@@ -175,3 +175,31 @@ def test_fused_tile_planner_on_every_case():
                 assert pl["cap_px"] >= min(64, case.w) * min(pl["th"], case.h)   # (the packed gaussian and pixel_size-2 block kernels size their own buffers: cap_px == 0)
     big = host_emu.plan(CrtParams(noise_strength=0.0, warp_strength=0.15, scanline_angle=3.0), 3840, 2160)
     assert big["ok"] and big["smem"] <= 110 * 1024          # BASELINE configs[2] keeps two CTAs per SM
+
+
+def test_rawvideo_streaming_chunks_and_short_read():
+    """clip.process_rawvideo: rgb24 framing as the reference's pipe reader (:494-502) — a trailing
+    partial frame is dropped, chunks carry consecutive frame indices, every frame is written once."""
+    import io
+    from pythoncrt_b200 import clip
+
+    class FakeEngine:
+        height, width = 4, 6
+        def __init__(self): self.calls = []; self.resets = 0
+        def reset_state(self): self.resets += 1
+        def process_host(self, a, out, fps, first_index):
+            self.calls.append((a.shape[0], first_index, fps))
+            out[...] = 255 - a
+            return out
+
+    fb = 4 * 6 * 3
+    rng = np.random.default_rng(5)
+    data = rng.integers(0, 256, 7 * fb + 11, dtype=np.uint8).tobytes()        # 7 frames + a partial one
+    frames = list(clip.iter_rawvideo(io.BytesIO(data), 6, 4))
+    assert len(frames) == 7 and frames[3].shape == (4, 6, 3)
+    eng, dst = FakeEngine(), io.BytesIO()
+    n = clip.process_rawvideo(eng, io.BytesIO(data), dst, fps=24.0, first_index=10, chunk_frames=3, pinned=False)
+    assert n == 7 and eng.resets == 1
+    assert eng.calls == [(3, 10, 24.0), (3, 13, 24.0), (1, 16, 24.0)]
+    want = (255 - np.frombuffer(data[:7 * fb], np.uint8)).tobytes()
+    assert dst.getvalue() == want
