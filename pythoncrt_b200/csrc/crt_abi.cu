@@ -299,7 +299,7 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
                : pq.gauss_k ? run_fused_gauss(pq.th, pq.nt, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
                             : run_fused(pq, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches);
             prof_mark(ctx, st, true);
-            if (!rc) rc = run_gather(d, f, ctx->scratch.q, out_i, state_i, has_prev, st, &launches, use_pdl);
+            if (!rc) rc = run_gather(d, f, ctx->scratch.q, out_i, state_i, has_prev, st, &launches);
             fused_used = 2;
         }
         else rc = run_staged(ctx, f, in_i, out_i, state_i, has_prev, img_i, st, &launches);

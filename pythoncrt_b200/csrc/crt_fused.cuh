@@ -584,59 +584,48 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused(Dev d, FrameDev f, cons
 // Second pass of the two-pass path: glitch shift, 4-tap warp gather from the pre-warp image
 // written by the first pass (global memory, L2-resident for the most part), text layer,
 // persistence, quantise.  Handles every gather the single-pass kernel declines.
-constexpr int GATHER_TH = 64, GATHER_ROWS = 256 / FROW_THREADS;      // a thread walks down its 4-pixel column: 4 rows per thread
+// ncu (run 41, 4K): 78 us, 187 thread-instructions per pixel, issue slots 60 % busy, 40 registers, 67 %
+// occupancy, long-scoreboard stalls on the twelve 4-byte tap loads per pixel.  Tried and measured slower
+// on cfg3 (runs 42-44, 7 560 frames/s as it stands): column coordinates hoisted over 4 rows per thread
+// (58 registers, 7 170), an all-taps-inside fast path (48 registers, 7 400; capped at 40 registers 7 380),
+// programmatic dependent launch of this kernel.  Next step: stage the tile's footprint in shared memory.
+constexpr int GATHER_TH = 16;
 template <bool WARP>
 __global__ void __launch_bounds__(256) k_gather(Dev d, FrameDev f, const float* __restrict__ qimg, uint8_t* __restrict__ out,
                                                 float* __restrict__ state, int has_prev) {
     const int tid = threadIdx.x;
-    const int y_first = blockIdx.y * GATHER_TH + tid / FROW_THREADS, xb = blockIdx.x * FTW + (tid % FROW_THREADS) * 4;
-    const int y_end = imin(d.H, (blockIdx.y + 1) * GATHER_TH);
-    griddep_launch_dependents();        // the next frame's first pass may begin its state-independent phases (see launch_pdl)
-    if (xb >= d.W) return;
-    const bool glitch = f.goffs != nullptr;
-    float xn0[4] = {0.f, 0.f, 0.f, 0.f};            // normalised column coordinates: one exact division per column, reused down the rows
-    if (WARP && !glitch) {
+    const int y = blockIdx.y * GATHER_TH + tid / FROW_THREADS, xb = blockIdx.x * FTW + (tid % FROW_THREADS) * 4;
+    if (y >= d.H || xb >= d.W) return;
+    const float yn = WARP ? warp_norm((float)y, d.warp_cy, d.warp_dy) : 0.f;
+    auto pixel = [&](int yy, int x, int k) -> F3 {
+        const int gx = glitch_src_x(d, f, yy, x);
+        F3 v = mk3(0.f, 0.f, 0.f);
+        if (WARP) {
+            const Taps t = warp_taps_n(d, warp_norm((float)gx, d.warp_cx, d.warp_dx), yn);
+            F3 a[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) xn0[k] = warp_norm((float)(xb + k), d.warp_cx, d.warp_dx);
-    }
-    griddep_wait();                     // the first pass has written the whole pre-warp image
-    for (int y = y_first; y < y_end; y += GATHER_ROWS) {
-        const float yn = WARP ? warp_norm((float)y, d.warp_cy, d.warp_dy) : 0.f;
-        auto pixel = [&](int yy, int x, int k) -> F3 {
-            const int gx = glitch ? glitch_src_x(d, f, yy, x) : x;
-            F3 v = mk3(0.f, 0.f, 0.f);
-            if (WARP) {
-                const Taps t = warp_taps_n(d, glitch ? warp_norm((float)gx, d.warp_cx, d.warp_dx) : xn0[k], yn);
-                F3 a[4];
-                if ((unsigned)t.ix < (unsigned)(d.W - 1) && (unsigned)t.iy < (unsigned)(d.H - 1)) {     // all four taps inside the image
-                    const float* p = qimg + ((size_t)t.iy * d.W + t.ix) * 3;
-                    a[0] = load_f3(p); a[1] = load_f3(p + 3); a[2] = load_f3(p + (size_t)d.W * 3); a[3] = load_f3(p + (size_t)d.W * 3 + 3);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int ty = t.iy + (j >> 1), tx = t.ix + (j & 1);
-                        const bool ok = ty >= 0 && ty < d.H && tx >= 0 && tx < d.W;
-                        a[j] = ok ? load_f3(qimg + ((size_t)ty * d.W + tx) * 3) : mk3(0.f, 0.f, 0.f);
-                    }
-                }
-                v = mk3(gather4_fast(a[0].x, a[1].x, a[2].x, a[3].x, t), gather4_fast(a[0].y, a[1].y, a[2].y, a[3].y, t),
-                        gather4_fast(a[0].z, a[1].z, a[2].z, a[3].z, t));
-            } else {
-                v = load_f3(qimg + ((size_t)yy * d.W + gx) * 3);
+            for (int j = 0; j < 4; ++j) {
+                const int ty = t.iy + (j >> 1), tx = t.ix + (j & 1);
+                const bool ok = ty >= 0 && ty < d.H && tx >= 0 && tx < d.W;
+                a[j] = ok ? load_f3(qimg + ((size_t)ty * d.W + tx) * 3) : mk3(0.f, 0.f, 0.f);
             }
-            if (d.text_mode == 2) v = text_blend(d, v, yy, gx);
-            return v;
-        };
-        finish_quad(d, state, out, nullptr, has_prev, y, xb, imin(4, d.W - xb), pixel);
-    }
+            v = mk3(gather4_fast(a[0].x, a[1].x, a[2].x, a[3].x, t), gather4_fast(a[0].y, a[1].y, a[2].y, a[3].y, t),
+                    gather4_fast(a[0].z, a[1].z, a[2].z, a[3].z, t));
+        } else {
+            v = load_f3(qimg + ((size_t)yy * d.W + gx) * 3);
+        }
+        if (d.text_mode == 2) v = text_blend(d, v, yy, gx);
+        return v;
+    };
+    finish_quad(d, state, out, nullptr, has_prev, y, xb, imin(4, d.W - xb), pixel);
 }
 
-inline int run_gather(const Dev& d, const FrameDev& f, const float* qimg, uint8_t* out, float* state, int has_prev, cudaStream_t st, int* launches,
-                      bool pdl = false) {
+inline int run_gather(const Dev& d, const FrameDev& f, const float* qimg, uint8_t* out, float* state, int has_prev, cudaStream_t st, int* launches) {
     dim3 grid((d.W + FTW - 1) / FTW, (d.H + GATHER_TH - 1) / GATHER_TH);
-    const cudaError_t e = launch_pdl(d.warp_on ? k_gather<true> : k_gather<false>, grid, dim3(256), 0, st, pdl, d, f, qimg, out, state, has_prev);
+    if (d.warp_on) k_gather<true><<<grid, 256, 0, st>>>(d, f, qimg, out, state, has_prev);
+    else k_gather<false><<<grid, 256, 0, st>>>(d, f, qimg, out, state, has_prev);
     ++*launches;
-    return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
 #endif  // __CUDACC__
