@@ -48,7 +48,7 @@ struct crt_ctx {
     std::vector<Lerp1> h_dn_x, h_dn_y, h_up_x, h_up_y;     // host copies of the fast-bloom coordinate tables
     Lerp1 *dn_x = nullptr, *dn_y = nullptr, *up_x = nullptr, *up_y = nullptr, *nz_x = nullptr, *nz_y = nullptr;
     int nz_grain = 0;
-    Scratch scratch{nullptr, nullptr, nullptr, nullptr};
+    Scratch scratch{nullptr, nullptr, nullptr};
     float* noise_buf = nullptr;
     int32_t* glitch_buf = nullptr;
     size_t glitch_cap = 0;
@@ -238,12 +238,6 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         return fail(ctx, CRT_ERR_UNSUPPORTED, std::string("fused kernel not available: ") + ctx->plan.why);
     if (want_two_pass && !ctx->scratch.q) CU(cudaMalloc((void**)&ctx->scratch.q, frame_px * 3 * sizeof(float)));
     static const bool use_pdl = env_int("CRT_PDL", 1) != 0;
-    // split gaussian block path: scratch for the block images
-    static const bool use_split = env_int("CRT_SPLIT", 1) != 0;
-    const FusedPlan& blk = want_fused ? ctx->plan : ctx->plan_q;
-    const bool split = use_split && (want_fused || want_two_pass) && blk.ps2 && blk.gauss_k;
-    if (split && !ctx->scratch.gs) CU(cudaMalloc((void**)&ctx->scratch.gs, fused_gauss_ps2_scratch_floats(d) * sizeof(float)));
-    float* gs = split ? ctx->scratch.gs : nullptr;
     // TMA-pipelined block kernel: needs tensor maps of this call's clip and state buffers
     const bool pipe = want_fused && ctx->plan.ps2 && !ctx->plan.gauss_k && persist && prepare_ps2_maps(ctx, d, d_in, n_frames, d_state);
     for (int i = 0; i < n_frames; ++i) {
@@ -291,7 +285,7 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         int rc;
         if (want_fused) {
             prof_mark(ctx, st, false);
-            rc = (ctx->plan.ps2 && ctx->plan.gauss_k) ? run_fused_gauss_ps2(d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches, pdl, gs)
+            rc = (ctx->plan.ps2 && ctx->plan.gauss_k) ? run_fused_gauss_ps2(d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches, pdl)
                : ctx->plan.ps2 ? run_fused_ps2(d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches, pdl, pipe ? &ctx->maps : nullptr)
                : ctx->plan.gauss_k ? run_fused_gauss(ctx->plan.th, ctx->plan.nt, d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches)
                                    : run_fused(ctx->plan, d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches);
@@ -300,7 +294,7 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         } else if (want_two_pass) {
             const FusedPlan& pq = ctx->plan_q;
             prof_mark(ctx, st, false);
-            rc = (pq.ps2 && pq.gauss_k) ? run_fused_gauss_ps2(ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl, gs)
+            rc = (pq.ps2 && pq.gauss_k) ? run_fused_gauss_ps2(ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl)
                : pq.ps2 ? run_fused_ps2(ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl)
                : pq.gauss_k ? run_fused_gauss(pq.th, pq.nt, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
                             : run_fused(pq, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches);
@@ -361,7 +355,6 @@ int crt_destroy(crt_ctx* ctx) {
     if (ctx->scratch.ds) cudaFree(ctx->scratch.ds);
     if (ctx->scratch.bl) cudaFree(ctx->scratch.bl);
     if (ctx->scratch.q) cudaFree(ctx->scratch.q);
-    if (ctx->scratch.gs) cudaFree(ctx->scratch.gs);
     if (ctx->noise_buf) cudaFree(ctx->noise_buf);
     if (ctx->glitch_buf) cudaFree(ctx->glitch_buf);
     if (ctx->state) cudaFree(ctx->state);

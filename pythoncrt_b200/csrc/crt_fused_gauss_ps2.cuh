@@ -17,13 +17,12 @@
 // The per-pixel tail (triad LUT, masks, persistence, stores) is ps2_patch_tail (crt_fused_ps2.cuh).
 // Shared memory: ~31 KB dynamic + ~11 KB static for K = 9 -> three 256-thread CTAs per SM at 80 registers.
 //
-// SPLIT (default): the grading of the blocks runs in its own kernel, k_grade_blocks, once per block of the
-// frame (no halo recomputation: 1.0 instead of 1.41 evaluations per block, and straight-line arithmetic
-// at a high issue rate), writing planar block images G (graded) and S (thresholded bloom source) that stay
-// in L2 (2 x 6 MB at 1080p); the tile kernel then fills Sb with coalesced loads.  The grading kernel does
-// not depend on the persistence state, so with programmatic dependent launch it overlaps the previous
-// frame's tile kernel: it computes its blocks into registers, and only then waits for that kernel to finish
-// (which also makes overwriting G / S safe) before storing.
+// Measured and NOT adopted (round 1, runs 47-49): grading the blocks in a kernel of its own, once per block of
+// the frame (no halo recomputation; 12 us at 70 % issue rate, block images in L2) with this kernel reading the
+// block images.  Correct, but 33 650 vs 37 060 frames/s on BASELINE configs[1]: the tile kernel keeps 150 of
+// its 256 thread-instructions per pixel and, without the arithmetic of the grading phase to cover its loads,
+// issues at 36 % instead of 50 %; the two kernels of a frame form a serial chain (the grading kernel only gets
+// SM slots when the previous frame's tile kernel drains), so the sum, not the overlap, is what is paid.
 #pragma once
 #include "crt_fused_gauss.cuh"
 #include "crt_fused_ps2.cuh"
@@ -55,46 +54,9 @@ CRT_HD bool fused_gauss_ps2_supported(const Dev& d, bool glitch_on) {
 
 #if defined(__CUDACC__)
 
-// Stages 0-4 + bloom threshold once per 2x2 block of the frame: G[ch][by][bx] graded value, S[ch][by][bx] thresholded
-// bloom source (only when the threshold is on).  NB blocks per thread, all computed before the dependency wait.
-template <int NB>
-__global__ void __launch_bounds__(256) k_grade_blocks(Dev d, const uint8_t* __restrict__ in, float* __restrict__ G, float* __restrict__ S) {
-    __shared__ float s_unit[256];
-    __shared__ __align__(16) float s_pow[POW_TAB_FLOATS];
-    const int tid = threadIdx.x;
-    griddep_launch_dependents();        // the tile kernel of this frame may stage its tables meanwhile
-    s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
-    if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += 256) s_pow[i] = d.pow_tab[i];
-    __syncthreads();
-    const int nblk = d.hw * d.hh;
-    const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
-    const int base = blockIdx.x * (256 * NB) + tid;
-    F3 g[NB], sv[NB];
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-        const int u = imin(base + j * 256, nblk - 1);               // surplus threads repeat the last block (stores are guarded)
-        const int by = u / d.hw, bx = u - by * d.hw;
-        const int sx = 2 * bx;
-        const uint8_t* row = in + (size_t)(2 * by) * d.W * 3;
-        const uint32_t r0 = row[wrap(sx - a0, d.W) * 3 + 0], r1 = row[sx * 3 + 1], r2 = row[wrap(sx + a0, d.W) * 3 + 2];
-        g[j] = colour(d, mk3(s_unit[r0], s_unit[r1], s_unit[r2]), s_pow);
-        sv[j] = bloom_src(d, g[j]);
-    }
-    griddep_wait();                     // the previous frame's tile kernel has finished (it reads G / S)
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-        const int u = base + j * 256;
-        if (u < nblk) {
-            G[u] = g[j].x; G[nblk + u] = g[j].y; G[2 * nblk + u] = g[j].z;
-            if (d.thr_on) { S[u] = sv[j].x; S[nblk + u] = sv[j].y; S[2 * nblk + u] = sv[j].z; }
-        }
-    }
-}
-
-template <int K, bool FAST, bool SPLIT>
-__global__ void __launch_bounds__(P2_NT, 3) k_fused_gauss_ps2(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
-                                                           float* __restrict__ state, float* __restrict__ q_out, int has_prev,
-                                                           const float* __restrict__ G, const float* __restrict__ S) {
+template <int K, bool FAST, int MINB>
+__global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                           float* __restrict__ state, float* __restrict__ q_out, int has_prev) {
     constexpr int R = K / 2, HB = (R + 1) / 2, OFF = R & 1;
     constexpr int NBX = P2_TW / 2 + 2 * HB, NBY = P2_TH / 2 + 2 * HB;
     constexpr int PITCH = (NBY & 3) == 2 ? NBY : NBY + 2;
@@ -120,11 +82,9 @@ __global__ void __launch_bounds__(P2_NT, 3) k_fused_gauss_ps2(Dev d, FrameDev f,
         reinterpret_cast<float4*>(s_inv)[tid] = reinterpret_cast<const float4*>(lut_b)[tid];
         if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
     }
-    if (!SPLIT) {                                   // grading tables (k_grade_blocks has its own)
-        s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
-        if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += blockDim.x) s_pow[i] = d.pow_tab[i];
-    }
+    s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
     ps2_fill_sel(s_sel, tid);
+    if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += blockDim.x) s_pow[i] = d.pow_tab[i];
     float taps[K];                                  // the kernel is symmetric: R + 1 registers
 #pragma unroll
     for (int i = 0; i <= R; ++i) { taps[R + i] = d.taps[R + i]; taps[R - i] = taps[R + i]; }
@@ -149,17 +109,7 @@ __global__ void __launch_bounds__(P2_NT, 3) k_fused_gauss_ps2(Dev d, FrameDev f,
 
         // ---- phase 1: graded value + bloom source per block of tile + halo (clamped block index = REPLICATE) ----
         const int gbx0 = (ox0 >> 1) - HB, gby0 = (oy0 >> 1) - HB;
-        if (SPLIT) {
-            griddep_wait();             // k_grade_blocks of this frame (and with it the previous frame's tile kernel) has finished
-            const float* __restrict__ src = d.thr_on ? S : G;
-            const int nblk = d.hw * d.hh;
-            for (int u = tid; u < 3 * NBX * NBY; u += P2_NT) {             // bx fastest: coalesced rows of NBX floats
-                const int ch = u / (NBX * NBY), r = u - ch * (NBX * NBY);
-                const int bj = r / NBX, bi = r - bj * NBX;
-                const int gx = imin(imax(gbx0 + bi, 0), d.hw - 1), gy = imin(imax(gby0 + bj, 0), d.hh - 1);
-                Sb[(ch * NBX + bi) * PITCH + bj] = src[ch * nblk + gy * d.hw + gx];
-            }
-        } else {
+        {
             constexpr int NIT = (NBX * NBY + P2_NT - 1) / P2_NT;
             uint32_t raw[NIT][3];                                 // 32-bit: a byte array would live in local memory
             const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
@@ -232,7 +182,7 @@ __global__ void __launch_bounds__(P2_NT, 3) k_fused_gauss_ps2(Dev d, FrameDev f,
             *reinterpret_cast<float4*>(o0 + P2_TW) = make_float4(r[0].y, r[1].y, r[2].y, r[3].y);
         }
         __syncthreads();
-        if (!SPLIT) griddep_wait();     // previous kernel of the stream complete: state / pre-warp image / noise may be touched from here on
+        griddep_wait();         // previous kernel of the stream complete: state / pre-warp image / noise may be touched from here on
 
         // ---- phase 3 + 4: column pass in registers, then the per-pixel tail for a 4 x 2 patch ----
         const int tx = tid & 15, ty = tid >> 4;
@@ -242,8 +192,7 @@ __global__ void __launch_bounds__(P2_NT, 3) k_fused_gauss_ps2(Dev d, FrameDev f,
             float t1[2][3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const float2 tv = SPLIT ? *reinterpret_cast<const float2*>(G + (size_t)(ch * d.hh + (oy0 >> 1) + ty) * d.hw + (ox0 >> 1) + 2 * tx)
-                                        : *reinterpret_cast<const float2*>(T1 + (ch * (P2_TH / 2) + ty) * (P2_TW / 2) + 2 * tx);
+                const float2 tv = *reinterpret_cast<const float2*>(T1 + (ch * (P2_TH / 2) + ty) * (P2_TW / 2) + 2 * tx);
                 t1[0][ch] = tv.x; t1[1][ch] = tv.y;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {                                   // pixel pairs (xb, xb+1), (xb+2, xb+3)
@@ -271,66 +220,48 @@ __global__ void __launch_bounds__(P2_NT, 3) k_fused_gauss_ps2(Dev d, FrameDev f,
     }
 }
 
-// gs: scratch for the block images, 2 planes sets of [3][hh][hw] floats (G, S), or null: grading inside the tile kernel
-template <int K>
+template <int K, int MINB>
 inline int launch_fused_gauss_ps2_t(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
-                                    int has_prev, cudaStream_t st, bool pdl, float* gs, int* launches) {
+                                    int has_prev, cudaStream_t st, bool pdl) {
     static bool configured[64] = {};
     static int resident = 0;
     const size_t smem = fused_gauss_ps2_smem(K);
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        if (cudaFuncSetAttribute(k_fused_gauss_ps2<K, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
-        if (cudaFuncSetAttribute(k_fused_gauss_ps2<K, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
-        if (cudaFuncSetAttribute(k_fused_gauss_ps2<K, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
-        if (cudaFuncSetAttribute(k_fused_gauss_ps2<K, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+        if (cudaFuncSetAttribute(k_fused_gauss_ps2<K, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+        if (cudaFuncSetAttribute(k_fused_gauss_ps2<K, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
         configured[dev & 63] = true;
     }
     if (!resident) {
-        int sms = 148, per_sm = 3;
+        int sms = 148, per_sm = 4;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_gauss_ps2<K, true, false>, P2_NT, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_gauss_ps2<K, true, MINB>, P2_NT, smem);
         resident = sms * (per_sm > 0 ? per_sm : 1);
         if (env_int("CRT_PS2_PERSIST", 1) == 0) resident = 1 << 30;
     }
     const int ntiles = ((d.W + P2_TW - 1) / P2_TW) * ((d.H + P2_TH - 1) / P2_TH);
     const dim3 grid(ntiles < resident ? ntiles : resident);
     const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1 && !d.noise_on;
-    cudaError_t e;
-    if (gs) {
-        constexpr int NB = 2;
-        const int nblk = d.hw * d.hh;
-        float* G = gs;
-        float* S = gs + (size_t)3 * nblk;
-        e = launch_pdl(k_grade_blocks<NB>, dim3((nblk + 256 * NB - 1) / (256 * NB)), dim3(256), 0, st, pdl, d, in, G, S);
-        ++*launches;
-        // the tile kernel follows this library's own kernel: always a programmatic dependent launch
-        if (e == cudaSuccess)
-            e = launch_pdl(fast ? k_fused_gauss_ps2<K, true, true> : k_fused_gauss_ps2<K, false, true>, grid, dim3(P2_NT), smem, st, true,
-                           d, f, in, out, state, q_out, has_prev, (const float*)G, (const float*)S);
-    } else {
-        e = launch_pdl(fast ? k_fused_gauss_ps2<K, true, false> : k_fused_gauss_ps2<K, false, false>, grid, dim3(P2_NT), smem, st, pdl,
-                       d, f, in, out, state, q_out, has_prev, (const float*)nullptr, (const float*)nullptr);
-    }
-    ++*launches;
+    const cudaError_t e = launch_pdl(fast ? k_fused_gauss_ps2<K, true, MINB> : k_fused_gauss_ps2<K, false, MINB>, grid, dim3(P2_NT), smem, st, pdl,
+                                     d, f, in, out, state, q_out, has_prev);
     return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
 }
 
-inline size_t fused_gauss_ps2_scratch_floats(const Dev& d) { return (size_t)6 * d.hw * d.hh; }
-
 inline int run_fused_gauss_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
-                               cudaStream_t st, int* launches, bool pdl = false, float* gs = nullptr) {
+                               cudaStream_t st, int* launches, bool pdl = false) {
     int rc = 4;
+    static const int minb = env_int("CRT_GPS2_MINB", 3);        // CTAs per SM the kernel is compiled for (64 vs 80 registers)
     switch (d.ksize) {
-        case 5: rc = launch_fused_gauss_ps2_t<5>(d, f, in, out, state, q_out, has_prev, st, pdl, gs, launches); break;
-        case 7: rc = launch_fused_gauss_ps2_t<7>(d, f, in, out, state, q_out, has_prev, st, pdl, gs, launches); break;
-        case 9: rc = launch_fused_gauss_ps2_t<9>(d, f, in, out, state, q_out, has_prev, st, pdl, gs, launches); break;
-        case 11: rc = launch_fused_gauss_ps2_t<11>(d, f, in, out, state, q_out, has_prev, st, pdl, gs, launches); break;
-        case 13: rc = launch_fused_gauss_ps2_t<13>(d, f, in, out, state, q_out, has_prev, st, pdl, gs, launches); break;
-        case 25: rc = launch_fused_gauss_ps2_t<25>(d, f, in, out, state, q_out, has_prev, st, pdl, gs, launches); break;
+        case 5: rc = minb == 3 ? launch_fused_gauss_ps2_t<5, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<5, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 7: rc = minb == 3 ? launch_fused_gauss_ps2_t<7, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<7, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 9: rc = minb == 3 ? launch_fused_gauss_ps2_t<9, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<9, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 11: rc = minb == 3 ? launch_fused_gauss_ps2_t<11, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<11, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 13: rc = minb == 3 ? launch_fused_gauss_ps2_t<13, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<13, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 25: rc = minb == 3 ? launch_fused_gauss_ps2_t<25, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<25, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
         default: break;
     }
+    ++*launches;
     return rc;
 }
 

@@ -12,7 +12,6 @@ struct Scratch {
     float* ds;      // fast bloom: half-size plane [hh][hw][3]
     float* bl;      // gaussian bloom: blurred plane [H][W][3]
     float* q;       // pre-warp processed image [H][W][3] (only when warp is on)
-    float* gs;      // block images of the split gaussian path: G [3][hh][hw] and S [3][hh][hw] (crt_fused_gauss_ps2.cuh)
 };
 
 // ---- fast bloom: 2x down-scale cell (cv2.resize INTER_LINEAR, crt_filter.py:606) ----
