@@ -224,7 +224,9 @@ def main() -> int:
     if not args.no_e2e:
         import psutil
         need = 2 * N * H * W * 3
-        n_e2e = N if psutil.virtual_memory().available > need * 1.5 + (8 << 30) else max(8, N // 8)
+        n_e2e = N if psutil.virtual_memory().available > need * 1.5 * world + (8 << 30) else max(8, N // 8)
+        if world > 1:                   # every rank pins its own host buffers: keep the total bounded on a shared host
+            n_e2e = min(n_e2e, max(150, N // world))
         h_in = torch.empty((n_e2e, H, W, 3), dtype=torch.uint8).pin_memory()
         h_out = torch.empty((n_e2e, H, W, 3), dtype=torch.uint8).pin_memory()
         h_in.copy_(frames[halo:halo + n_e2e].cpu())
