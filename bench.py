@@ -64,6 +64,28 @@ def alg_bytes_per_px(persistence: float) -> int:
     return 30 if persistence > 0.0 else 6
 
 
+def bind_near_gpu(index: int):
+    """Pin this process to the CPUs NVML reports as local to the GPU (same NUMA node / PCIe root), so that the pinned
+    host buffers of the e2e leg are first-touched on that node.  Best effort: any failure leaves the affinity alone."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(index).uuid)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        near = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(near & allowed)
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+        return {"near": len(near), "allowed": len(allowed), "bound": len(cpus) if cpus and len(cpus) < len(allowed) else 0}
+    except Exception as e:  # noqa: BLE001
+        return {"error": type(e).__name__}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -163,6 +185,7 @@ def main() -> int:
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
+    numa = bind_near_gpu(local) if os.environ.get("CRT_BENCH_BIND", "1") != "0" else None
     dev = torch.device(f"cuda:{local}")
     W, H, N, fps = wl["w"], wl["h"], wl["frames"], wl["fps"]
     p = product_params(wl["over"])
@@ -245,7 +268,7 @@ def main() -> int:
         same = bool(torch.equal(h_out[:4].to(dev), out[halo:halo + 4])) if rank == 0 else True
         e2e = {"value": world * n_e2e * e2e_steps / float(dt.item()), "unit": "frames/s", "h2d_bytes_per_step": n_e2e * H * W * 3,
                "d2h_bytes_per_step": n_e2e * H * W * 3, "frames_per_step": n_e2e, "steps": e2e_steps, "api": "crt_process_host",
-               "matches_device_path": same}
+               "matches_device_path": same, "cpu_binding": numa}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
