@@ -595,6 +595,7 @@ __global__ void __launch_bounds__(256) k_gather(Dev d, FrameDev f, const float* 
                                                 float* __restrict__ state, int has_prev) {
     const int tid = threadIdx.x;
     const int y = blockIdx.y * GATHER_TH + tid / FROW_THREADS, xb = blockIdx.x * FTW + (tid % FROW_THREADS) * 4;
+    griddep_launch_dependents();        // the next frame's first pass may fill this kernel's last wave (it waits before it writes)
     if (y >= d.H || xb >= d.W) return;
     const float yn = WARP ? warp_norm((float)y, d.warp_cy, d.warp_dy) : 0.f;
     auto pixel = [&](int yy, int x, int k) -> F3 {
