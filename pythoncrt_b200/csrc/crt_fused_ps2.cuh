@@ -36,6 +36,8 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
                                                const int (*s_sel)[12], float* __restrict__ state, uint8_t* __restrict__ out, float* __restrict__ q_out, int has_prev,
                                                int ox0, int oy0, int ox1, int oy1, int xb, int y0, const float (&t1)[2][3], BloomFn&& bloom,
                                                const float* s_prev = nullptr) {
+    // Both rows of the patch are inside the frame (even frame height, even y0), so the two rows' arithmetic is one
+    // straight-line block the scheduler can interleave.
     // s_prev: the patch's previous state in shared memory (row pitch P2_TW * 3 floats) when a TMA copy fetched it
     auto finish = [&](int r, int y, auto&& pixel) {
         if (s_prev) {
@@ -63,7 +65,6 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int y = y0 + r;
-            if (y > oy1) break;
             const float rscan = d.scan_mode ? mt.row_scan[y - oy0] : 1.0f;         // mask (mode 1) or phase fraction (mode 2)
             const float flick = f.flicker_on ? f.flicker : 1.0f;
             const float rfac = (d.scan_mode == 2 ? 1.0f : rscan) * flick;
@@ -90,7 +91,6 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int y = y0 + r;
-            if (y > oy1) break;
             auto pixel = [&](int yy, int x, int k) -> F3 {
                 F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
                 if (BLOOM) v = add_bloom(d, v, bloom(r, k));
