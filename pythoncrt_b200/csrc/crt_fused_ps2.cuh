@@ -461,13 +461,14 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
     static const int pipe_min_tiles = env_int("CRT_PIPE_MIN_TILES", 2 * 148 * 4);
     if (maps && has_prev && !q_out && ntiles >= pipe_min_tiles) {
         static int sms = 0;
+        static bool configured[64] = {};                         // the opt-in shared-memory size is a per-device attribute
         const bool thr = d.bloom_mode == 1 && d.thr_on;
         auto kern = !thr ? (d.bloom_mode == 1 ? (fast ? k_fused_ps2_pipe<true, true, false> : k_fused_ps2_pipe<true, false, false>)
                                               : (fast ? k_fused_ps2_pipe<false, true, false> : k_fused_ps2_pipe<false, false, false>))
                          : (fast ? k_fused_ps2_pipe<true, true, true> : k_fused_ps2_pipe<true, false, true>);
-        if (!sms) {
-            int dev = 0;
-            cudaGetDevice(&dev);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!configured[dev & 63]) {
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             cudaFuncSetAttribute(k_fused_ps2_pipe<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM);
             cudaFuncSetAttribute(k_fused_ps2_pipe<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM);
@@ -475,6 +476,7 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
             cudaFuncSetAttribute(k_fused_ps2_pipe<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM);
             cudaFuncSetAttribute(k_fused_ps2_pipe<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM);
             cudaFuncSetAttribute(k_fused_ps2_pipe<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM);
+            configured[dev & 63] = true;
         }
         const int resident_pipe = sms * (thr ? 3 : 4);
         const cudaError_t e = launch_pdl(kern, dim3(ntiles < resident_pipe ? ntiles : resident_pipe), dim3(P2_NT), (size_t)P2_PIPE_SMEM, st, pdl,
