@@ -35,12 +35,34 @@ template <bool BLOOM, bool FAST, typename BloomFn>
 __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, const MaskTabs& mt, const float* s_fwd, const float* s_inv,
                                                const int (*s_sel)[12], float* __restrict__ state, uint8_t* __restrict__ out, float* __restrict__ q_out, int has_prev,
                                                int ox0, int oy0, int ox1, int oy1, int xb, int y0, const float (&t1)[2][3], BloomFn&& bloom,
-                                               const float* s_prev = nullptr) {
+                                               float* s_prev = nullptr, bool state_in_smem = false) {
     // Both rows of the patch are inside the frame (even frame height, even y0), so the two rows' arithmetic is one
     // straight-line block the scheduler can interleave.
     // s_prev: the patch's previous state in shared memory (row pitch P2_TW * 3 floats) when a TMA copy fetched it
     auto finish = [&](int r, int y, auto&& pixel) {
-        if (s_prev) {
+        if (s_prev && state_in_smem) {
+            // previous state read from, and the new state written back to, the tile buffer in shared memory (it leaves
+            // with one TMA store per tile); only the packed uint8 pixels are stored from here
+            float4* sp = reinterpret_cast<float4*>(s_prev + r * (P2_TW * 3));
+            const float4 pa = sp[0], pb = sp[1], pc = sp[2];
+            const float prev[12] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, pc.x, pc.y, pc.z, pc.w};
+            float res[12];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                F3 v = pixel(y, xb + k, k);
+                v.x = blend_fast(prev[k * 3], v.x, d.persist, d.persist_q);
+                v.y = blend_fast(prev[k * 3 + 1], v.y, d.persist, d.persist_q);
+                v.z = blend_fast(prev[k * 3 + 2], v.z, d.persist, d.persist_q);
+                res[k * 3] = v.x; res[k * 3 + 1] = v.y; res[k * 3 + 2] = v.z;
+            }
+            sp[0] = make_float4(res[0], res[1], res[2], res[3]);
+            sp[1] = make_float4(res[4], res[5], res[6], res[7]);
+            sp[2] = make_float4(res[8], res[9], res[10], res[11]);
+            uint32_t* op = reinterpret_cast<uint32_t*>(out + (y * d.W + xb) * 3);
+            op[0] = pack4(res[0], res[1], res[2], res[3]);
+            op[1] = pack4(res[4], res[5], res[6], res[7]);
+            op[2] = pack4(res[8], res[9], res[10], res[11]);
+        } else if (s_prev) {
             const float4* sp = reinterpret_cast<const float4*>(s_prev + r * (P2_TW * 3));
             finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel, true, sp[0], sp[1], sp[2]);
         } else {
@@ -267,7 +289,10 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_ps2(Dev d, FrameDev f, co
 //   * the tile's previous state (32 rows x 768 bytes) arrives by one TMA copy issued at the top of the
 //     tile's iteration and is consumed after the grading phase; the blend reads it from shared memory;
 // so no thread waits on a global load: the copies are in flight while the CTA (and the other CTAs of the
-// SM) compute.  Results still leave with plain 16-byte stores.  Tiles on the left / right frame edge,
+// SM) compute.  The new state is written back into the same shared-memory tile and leaves with ONE TMA
+// store per tile (fully coalesced; the 16-byte per-thread stores of the plain kernel reach 3.3 TB/s on
+// their own, coalesced stores 5.4 TB/s: tests/_probe/store_probe.cu); the packed uint8 pixels (3 B/px) are
+// still stored by the threads.  Tiles on the left / right frame edge,
 // where chromatic aberration wraps around (np.roll), read their bytes with the plain loads.
 // Measured (round 1, default chain at 4K): 66.0 us per frame against 70.7 us for the plain kernel with
 // 4 CTAs per SM (run 35).  Each half alone does not pay: state by TMA with the input on batched byte loads
@@ -346,7 +371,8 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, Fr
         if (nbx >= tiles_x) { nbx -= tiles_x; ++nby; }
         const int buf = it & 1;
         if (tid == 0) {
-            if (it > 0 && use_state) {           // this tile's state (the previous tile's tail has finished with the buffer)
+            if (it > 0 && use_state) {           // this tile's state: the previous tile's TMA store must have drained the buffer
+                bulk_wait_read();
                 mbar_expect_tx(&bar_st, P2_ST_BYTES);
                 tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st);
             }
@@ -439,11 +465,17 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, Fr
             }
             ps2_patch_tail<BLOOM, FAST>(d, f, mt, s_fwd, s_inv, s_sel, state, out, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
                                         [&](int r, int k) { return mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]); },
-                                        use_state ? s_state + (y0 - oy0) * (P2_TW * 3) + 12 * tx : nullptr);
+                                        use_state ? s_state + (y0 - oy0) * (P2_TW * 3) + 12 * tx : nullptr, use_state);
         }
+        if (use_state) fence_proxy_async();     // the new state in shared memory -> visible to the TMA engine
         __syncthreads();        // everyone is done with this tile's tables, block values and state tile
+        if (use_state && tid == 0) {            // the tile's new state leaves with one coalesced TMA store (rows outside the frame are clipped)
+            tma_store_2d(&map_st, s_state, ox0 * 3, oy0);
+            bulk_commit();
+        }
         tbx = nbx; tby = nby;
     }
+    if (use_state && tid == 0) bulk_wait_all();     // the last tile's store has completed before the CTA exits
 }
 
 inline bool fused_ps2_pipe_supported(const Dev& d) {
