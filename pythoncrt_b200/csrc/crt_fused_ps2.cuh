@@ -31,11 +31,13 @@ CRT_HD bool fused_ps2_supported(const Dev& d, bool glitch_on) {
 
 // Stages 5-10, persistence and stores for a thread's 4 x 2 pixel patch (two 2x2 blocks side by side).
 // t1 = graded value of the two blocks, bloom(r, k) = blurred bloom source of pixel k of row r.
-template <bool BLOOM, bool FAST, typename BloomFn>
+struct NoRowHook { __device__ __forceinline__ void operator()(int) const {} };
+template <bool BLOOM, bool FAST, typename BloomFn, typename RowFn = NoRowHook>
 __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, const MaskTabs& mt, const float* s_fwd, const float* s_inv,
                                                const int (*s_sel)[12], float* __restrict__ state, uint8_t* __restrict__ out, float* __restrict__ q_out, int has_prev,
                                                int ox0, int oy0, int ox1, int oy1, int xb, int y0, const float (&t1)[2][3], BloomFn&& bloom,
-                                               float* s_prev = nullptr, bool state_in_smem = false) {
+                                               float* s_prev = nullptr, bool state_in_smem = false, RowFn&& row_begin = RowFn()) {
+    // row_begin(r) runs before row r of the patch is evaluated (e.g. to compute that row's bloom values only then)
     // Both rows of the patch are inside the frame (even frame height, even y0), so the two rows' arithmetic is one
     // straight-line block the scheduler can interleave.
     // s_prev: the patch's previous state in shared memory (row pitch P2_TW * 3 floats) when a TMA copy fetched it
@@ -87,6 +89,7 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int y = y0 + r;
+            row_begin(r);
             const float rscan = d.scan_mode ? mt.row_scan[y - oy0] : 1.0f;         // mask (mode 1) or phase fraction (mode 2)
             const float flick = f.flicker_on ? f.flicker : 1.0f;
             const float rfac = (d.scan_mode == 2 ? 1.0f : rscan) * flick;
@@ -113,6 +116,7 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int y = y0 + r;
+            row_begin(r);
             auto pixel = [&](int yy, int x, int k) -> F3 {
                 F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
                 if (BLOOM) v = add_bloom(d, v, bloom(r, k));
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_ps2(Dev d, FrameDev f, co
 // and count towards the barrier's byte count, a [frames][rows][bytes] map with a box of 1 frame never
 // completed — hence one 2-D map over the even rows of all frames (the frame pitch is H/2 row pitches).
 // Requires W % 8 == 0, |aberration| <= 6, 16-byte aligned clip / state pointers; used when there is a
-// state to fetch and every CTA walks over several tiles.
+// state to fetch and the frame has at least ~500 tiles (run 68: 1080p 51 700 vs 44 900 frames/s, VGA neutral).
 constexpr int P2_RAW_W = 256, P2_RAW_BYTES = P2_RAW_W * P2_BH;   // input buffer: 18 rows x 256 bytes (the box starts 16-byte aligned)
 constexpr int P2_ST_BYTES = P2_TH * P2_TW * 3 * 4;            // state tile: 32 x 192 float32
 constexpr int P2_PIPE_SMEM = P2_ST_BYTES + 2 * P2_RAW_BYTES;
@@ -440,32 +444,34 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, Fr
         const int xb = ox0 + 4 * tx, y0 = oy0 + 2 * ty;
         if (xb <= ox1 && y0 <= oy1) {
             const int bi = 2 * tx + 1, bj = ty + 1;
-            float bl[2][4][3];
+            float blr[4][3];                                     // bloom of the row being evaluated
             float t1[2][3];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                t1[0][ch] = Us[ch][bj][bi]; t1[1][ch] = Us[ch][bj][bi + 1];
-                if (BLOOM) {
+            for (int ch = 0; ch < 3; ++ch) { t1[0][ch] = Us[ch][bj][bi]; t1[1][ch] = Us[ch][bj][bi + 1]; }
+            // The bloom of a patch row is computed when that row is evaluated (two block rows, x-lerps, one y-lerp):
+            // holding both rows' 24 values across the first row's arithmetic does not fit in 64 registers (ncu run 65:
+            // 12 spill stores + 12 reloads per thread and tile, reloads stalling on the long scoreboard).
+            auto row_begin = [&](int r) {
+#pragma unroll
+                for (int ch = 0; ch < (BLOOM ? 3 : 0); ++ch) {
                     const float (*src)[P2_BW + 2] = THR ? Ss[THR ? ch : 0] : Us[ch];
-                    float h[3][4];
+                    float h[2][4];
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        const float2 ca = *reinterpret_cast<const float2*>(&src[bj - 1 + r][bi - 1]);
-                        const float2 cb = *reinterpret_cast<const float2*>(&src[bj - 1 + r][bi + 1]);
+                    for (int q = 0; q < 2; ++q) {
+                        const float2 ca = *reinterpret_cast<const float2*>(&src[bj - 1 + r + q][bi - 1]);
+                        const float2 cb = *reinterpret_cast<const float2*>(&src[bj - 1 + r + q][bi + 1]);
                         const float d01 = fsub(ca.y, ca.x), d12 = fsub(cb.x, ca.y), d23 = fsub(cb.y, cb.x);
-                        h[r][0] = ffma(d01, 0.75f, ca.x); h[r][1] = ffma(d12, 0.25f, ca.y);
-                        h[r][2] = ffma(d12, 0.75f, ca.y); h[r][3] = ffma(d23, 0.25f, cb.x);
+                        h[q][0] = ffma(d01, 0.75f, ca.x); h[q][1] = ffma(d12, 0.25f, ca.y);
+                        h[q][2] = ffma(d12, 0.75f, ca.y); h[q][3] = ffma(d23, 0.25f, cb.x);
                     }
+                    const float w = r == 0 ? 0.75f : 0.25f;      // y = 2j: lerp(row j-1, row j, 0.75); y = 2j + 1: lerp(row j, row j+1, 0.25)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        bl[0][k][ch] = ffma(fsub(h[1][k], h[0][k]), 0.75f, h[0][k]);
-                        bl[1][k][ch] = ffma(fsub(h[2][k], h[1][k]), 0.25f, h[1][k]);
-                    }
+                    for (int k = 0; k < 4; ++k) blr[k][ch] = ffma(fsub(h[1][k], h[0][k]), w, h[0][k]);
                 }
-            }
+            };
             ps2_patch_tail<BLOOM, FAST>(d, f, mt, s_fwd, s_inv, s_sel, state, out, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
-                                        [&](int r, int k) { return mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]); },
-                                        use_state ? s_state + (y0 - oy0) * (P2_TW * 3) + 12 * tx : nullptr, use_state);
+                                        [&](int, int k) { return mk3(blr[k][0], blr[k][1], blr[k][2]); },
+                                        use_state ? s_state + (y0 - oy0) * (P2_TW * 3) + 12 * tx : nullptr, use_state, row_begin);
         }
         if (use_state) fence_proxy_async();     // the new state in shared memory -> visible to the TMA engine
         __syncthreads();        // everyone is done with this tile's tables, block values and state tile
@@ -490,7 +496,7 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
     const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1 && !d.noise_on;
     // TMA-pipelined variant (4 CTAs per SM, 3 with the bloom threshold on): pays off when there is a state to fetch and
     // every CTA walks over several tiles
-    static const int pipe_min_tiles = env_int("CRT_PIPE_MIN_TILES", 2 * 148 * 4);
+    static const int pipe_min_tiles = env_int("CRT_PIPE_MIN_TILES", 512);      // measured: wins at 1080p (1020 tiles) and 4K, neutral at VGA (150)
     if (maps && has_prev && !q_out && ntiles >= pipe_min_tiles) {
         static int sms = 0;
         static bool configured[64] = {};                         // the opt-in shared-memory size is a per-device attribute
