@@ -247,34 +247,35 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_ps2(Dev d, FrameDev f, co
     const int xb = ox0 + 4 * tx, y0 = oy0 + 2 * ty;
     if (xb <= ox1 && y0 <= oy1) {
     const int bi = 2 * tx + 1, bj = ty + 1;                 // first of the two blocks, in halo coordinates
-    float bl[2][4][3];                                      // bloom of the 8 pixels
+    float blr[4][3];                                        // bloom of the patch row being evaluated
     float t1[2][3];                                         // graded value of the two blocks
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        t1[0][ch] = Us[ch][bj][bi]; t1[1][ch] = Us[ch][bj][bi + 1];
-        if (BLOOM) {
+    for (int ch = 0; ch < 3; ++ch) { t1[0][ch] = Us[ch][bj][bi]; t1[1][ch] = Us[ch][bj][bi + 1]; }
+    // The bloom of a patch row is computed when that row is evaluated: cells bi-1 .. bi+2 of two block rows
+    // (bi - 1 is even: 8-byte aligned pairs), cv2's x-lerps, one y-lerp.  Holding both rows' 24 values across the
+    // first row's arithmetic does not fit in 64 registers (they were spilled and reloaded).
+    auto row_begin = [&](int r) {
+#pragma unroll
+        for (int ch = 0; ch < (BLOOM ? 3 : 0); ++ch) {
             const float (*src)[P2_BW + 2] = d.thr_on ? Ss[ch] : Us[ch];
-            float h[3][4];
+            float h[2][4];
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                // cells bi-1 .. bi+2 of block row bj-1+r (bi - 1 is even: 8-byte aligned pairs)
-                const float2 ca = *reinterpret_cast<const float2*>(&src[bj - 1 + r][bi - 1]);
-                const float2 cb = *reinterpret_cast<const float2*>(&src[bj - 1 + r][bi + 1]);
+            for (int q = 0; q < 2; ++q) {
+                const float2 ca = *reinterpret_cast<const float2*>(&src[bj - 1 + r + q][bi - 1]);
+                const float2 cb = *reinterpret_cast<const float2*>(&src[bj - 1 + r + q][bi + 1]);
                 const float d01 = fsub(ca.y, ca.x), d12 = fsub(cb.x, ca.y), d23 = fsub(cb.y, cb.x);
-                h[r][0] = ffma(d01, 0.75f, ca.x);           // x = 2i     : lerp(c[i-1], c[i], 0.75)
-                h[r][1] = ffma(d12, 0.25f, ca.y);           // x = 2i + 1 : lerp(c[i], c[i+1], 0.25)
-                h[r][2] = ffma(d12, 0.75f, ca.y);           // x = 2i + 2 : lerp(c[i], c[i+1], 0.75)
-                h[r][3] = ffma(d23, 0.25f, cb.x);           // x = 2i + 3 : lerp(c[i+1], c[i+2], 0.25)
+                h[q][0] = ffma(d01, 0.75f, ca.x);           // x = 2i     : lerp(c[i-1], c[i], 0.75)
+                h[q][1] = ffma(d12, 0.25f, ca.y);           // x = 2i + 1 : lerp(c[i], c[i+1], 0.25)
+                h[q][2] = ffma(d12, 0.75f, ca.y);           // x = 2i + 2 : lerp(c[i], c[i+1], 0.75)
+                h[q][3] = ffma(d23, 0.25f, cb.x);           // x = 2i + 3 : lerp(c[i+1], c[i+2], 0.25)
             }
+            const float w = r == 0 ? 0.75f : 0.25f;         // y = 2j: lerp(row j-1, row j, 0.75); y = 2j + 1: lerp(row j, row j+1, 0.25)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                bl[0][k][ch] = ffma(fsub(h[1][k], h[0][k]), 0.75f, h[0][k]);     // y = 2j     : lerp(row j-1, row j, 0.75)
-                bl[1][k][ch] = ffma(fsub(h[2][k], h[1][k]), 0.25f, h[1][k]);     // y = 2j + 1 : lerp(row j, row j+1, 0.25)
-            }
+            for (int k = 0; k < 4; ++k) blr[k][ch] = ffma(fsub(h[1][k], h[0][k]), w, h[0][k]);
         }
-    }
+    };
     ps2_patch_tail<BLOOM, FAST>(d, f, mt, s_fwd, s_inv, s_sel, state, out, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
-                                [&](int r, int k) { return mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]); });
+                                [&](int, int k) { return mk3(blr[k][0], blr[k][1], blr[k][2]); }, nullptr, false, row_begin);
     }                       // this thread's patch
     __syncthreads();        // everyone is done with this tile's tables / block values
     tbx += step_x; tby += step_y;
