@@ -239,7 +239,8 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
     if (want_two_pass && !ctx->scratch.q) CU(cudaMalloc((void**)&ctx->scratch.q, frame_px * 3 * sizeof(float)));
     static const bool use_pdl = env_int("CRT_PDL", 1) != 0;
     // TMA-pipelined block kernel: needs tensor maps of this call's clip and state buffers
-    const bool pipe = want_fused && ctx->plan.ps2 && !ctx->plan.gauss_k && persist && prepare_ps2_maps(ctx, d, d_in, n_frames, d_state);
+    const bool pipe = (want_fused && ctx->plan.ps2 && !ctx->plan.gauss_k && persist && prepare_ps2_maps(ctx, d, d_in, n_frames, d_state)) ||
+                      (want_two_pass && ctx->plan_q.ps2 && !ctx->plan_q.gauss_k && prepare_ps2_maps(ctx, ctx->dev_q, d_in, n_frames, ctx->scratch.q));
     for (int i = 0; i < n_frames; ++i) {
         const crt_frame& fr = frames[i];
         FrameDev f = derive_frame(p, fr);
@@ -295,7 +296,7 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
             const FusedPlan& pq = ctx->plan_q;
             prof_mark(ctx, st, false);
             rc = (pq.ps2 && pq.gauss_k) ? run_fused_gauss_ps2(ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl)
-               : pq.ps2 ? run_fused_ps2(ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl)
+               : pq.ps2 ? run_fused_ps2(ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl, pipe ? &ctx->maps : nullptr)
                : pq.gauss_k ? run_fused_gauss(pq.th, pq.nt, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
                             : run_fused(pq, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches);
             prof_mark(ctx, st, true);

@@ -43,27 +43,33 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
     // s_prev: the patch's previous state in shared memory (row pitch P2_TW * 3 floats) when a TMA copy fetched it
     auto finish = [&](int r, int y, auto&& pixel) {
         if (s_prev && state_in_smem) {
-            // previous state read from, and the new state written back to, the tile buffer in shared memory (it leaves
-            // with one TMA store per tile); only the packed uint8 pixels are stored from here
+            // previous state read from (single-pass), and the new state / pre-warp image written back to, the tile buffer
+            // in shared memory (it leaves with one TMA store per tile); only the packed uint8 pixels are stored from here
             float4* sp = reinterpret_cast<float4*>(s_prev + r * (P2_TW * 3));
-            const float4 pa = sp[0], pb = sp[1], pc = sp[2];
+            const bool blend = has_prev && !q_out;
+            float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa, pc = pa;
+            if (blend) { pa = sp[0]; pb = sp[1]; pc = sp[2]; }
             const float prev[12] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, pc.x, pc.y, pc.z, pc.w};
             float res[12];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 F3 v = pixel(y, xb + k, k);
-                v.x = blend_fast(prev[k * 3], v.x, d.persist, d.persist_q);
-                v.y = blend_fast(prev[k * 3 + 1], v.y, d.persist, d.persist_q);
-                v.z = blend_fast(prev[k * 3 + 2], v.z, d.persist, d.persist_q);
+                if (blend) {
+                    v.x = blend_fast(prev[k * 3], v.x, d.persist, d.persist_q);
+                    v.y = blend_fast(prev[k * 3 + 1], v.y, d.persist, d.persist_q);
+                    v.z = blend_fast(prev[k * 3 + 2], v.z, d.persist, d.persist_q);
+                }
                 res[k * 3] = v.x; res[k * 3 + 1] = v.y; res[k * 3 + 2] = v.z;
             }
             sp[0] = make_float4(res[0], res[1], res[2], res[3]);
             sp[1] = make_float4(res[4], res[5], res[6], res[7]);
             sp[2] = make_float4(res[8], res[9], res[10], res[11]);
-            uint32_t* op = reinterpret_cast<uint32_t*>(out + (y * d.W + xb) * 3);
-            op[0] = pack4(res[0], res[1], res[2], res[3]);
-            op[1] = pack4(res[4], res[5], res[6], res[7]);
-            op[2] = pack4(res[8], res[9], res[10], res[11]);
+            if (!q_out) {
+                uint32_t* op = reinterpret_cast<uint32_t*>(out + (y * d.W + xb) * 3);
+                op[0] = pack4(res[0], res[1], res[2], res[3]);
+                op[1] = pack4(res[4], res[5], res[6], res[7]);
+                op[2] = pack4(res[8], res[9], res[10], res[11]);
+            }
         } else if (s_prev) {
             const float4* sp = reinterpret_cast<const float4*>(s_prev + r * (P2_TW * 3));
             finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel, true, sp[0], sp[1], sp[2]);
@@ -316,7 +322,7 @@ constexpr int P2_PIPE_SMEM = P2_ST_BYTES + 2 * P2_RAW_BYTES;
 
 struct Ps2Maps {                 // host-encoded tensor maps (crt_abi.cu)
     CUtensorMap in;              // uint8 [frames * H/2 even rows][W*3] (row pitch 2 W*3), box 256 x 18
-    CUtensorMap st;              // float32 [H][W*3], box 192 x 32
+    CUtensorMap st;              // float32 [H][W*3], box 192 x 32: the state buffer, or the pre-warp image in the two-pass path
     int frame;                   // index of this launch's frame inside `in`
 };
 
@@ -341,7 +347,8 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, Fr
     __shared__ __align__(8) uint64_t bar_in[2], bar_st;
     const int tid = threadIdx.x;
     griddep_launch_dependents();
-    const bool use_state = has_prev && !q_out;
+    const bool use_state = has_prev && !q_out;      // a previous state to fetch
+    const bool tile_out = use_state || q_out;       // the result (new state, or the pre-warp image of the two-pass path) leaves through the tile
     const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
     const int as = a0 > (d.W >> 1) ? a0 - d.W : a0;                         // signed shift (aberr_mod is taken modulo W)
     const int aa = as < 0 ? -as : as;
@@ -376,10 +383,9 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, Fr
         if (nbx >= tiles_x) { nbx -= tiles_x; ++nby; }
         const int buf = it & 1;
         if (tid == 0) {
-            if (it > 0 && use_state) {           // this tile's state: the previous tile's TMA store must have drained the buffer
+            if (it > 0 && tile_out) {            // the previous tile's TMA store must have drained the buffer; then fetch this tile's state
                 bulk_wait_read();
-                mbar_expect_tx(&bar_st, P2_ST_BYTES);
-                tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st);
+                if (use_state) { mbar_expect_tx(&bar_st, P2_ST_BYTES); tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st); }
             }
             if (tile + (int)gridDim.x < ntiles) {      // next tile's input into the other buffer (last read two barriers ago)
                 mbar_expect_tx(&bar_in[buf ^ 1], P2_RAW_BYTES);
@@ -472,17 +478,17 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, Fr
             };
             ps2_patch_tail<BLOOM, FAST>(d, f, mt, s_fwd, s_inv, s_sel, state, out, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
                                         [&](int, int k) { return mk3(blr[k][0], blr[k][1], blr[k][2]); },
-                                        use_state ? s_state + (y0 - oy0) * (P2_TW * 3) + 12 * tx : nullptr, use_state, row_begin);
+                                        tile_out ? s_state + (y0 - oy0) * (P2_TW * 3) + 12 * tx : nullptr, tile_out, row_begin);
         }
-        if (use_state) fence_proxy_async();     // the new state in shared memory -> visible to the TMA engine
+        if (tile_out) fence_proxy_async();      // the new state in shared memory -> visible to the TMA engine
         __syncthreads();        // everyone is done with this tile's tables, block values and state tile
-        if (use_state && tid == 0) {            // the tile's new state leaves with one coalesced TMA store (rows outside the frame are clipped)
+        if (tile_out && tid == 0) {            // the tile's new state leaves with one coalesced TMA store (rows outside the frame are clipped)
             tma_store_2d(&map_st, s_state, ox0 * 3, oy0);
             bulk_commit();
         }
         tbx = nbx; tby = nby;
     }
-    if (use_state && tid == 0) bulk_wait_all();     // the last tile's store has completed before the CTA exits
+    if (tile_out && tid == 0) bulk_wait_all();      // the last tile's store has completed before the CTA exits
 }
 
 inline bool fused_ps2_pipe_supported(const Dev& d) {
@@ -498,7 +504,7 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
     // TMA-pipelined variant (4 CTAs per SM, 3 with the bloom threshold on): pays off when there is a state to fetch and
     // every CTA walks over several tiles
     static const int pipe_min_tiles = env_int("CRT_PIPE_MIN_TILES", 512);      // measured: wins at 1080p (1020 tiles) and 4K, neutral at VGA (150)
-    if (maps && has_prev && !q_out && ntiles >= pipe_min_tiles) {
+    if (maps && (q_out || has_prev) && ntiles >= pipe_min_tiles) {
         static int sms = 0;
         static bool configured[64] = {};                         // the opt-in shared-memory size is a per-device attribute
         const bool thr = d.bloom_mode == 1 && d.thr_on;
