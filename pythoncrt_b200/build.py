@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcrt_b200.so")
 SOURCES = ["crt_abi.cu"]
-DEPS = ["crt_abi.cu", "crt_math.cuh", "crt_stages.cuh", "crt_kernels.cuh", "crt_fused.cuh", "crt_fused_gauss.cuh", "crt_fused_ps2.cuh", "crt_fused_gauss_ps2.cuh", "crt_tma.cuh", "crt_pow_tables.h", "crt_derive.h",
+DEPS = ["crt_abi.cu", "crt_math.cuh", "crt_stages.cuh", "crt_kernels.cuh", "crt_fused.cuh", "crt_fused_gauss.cuh", "crt_fused_ps2.cuh", "crt_fused_gauss_ps2.cuh", "crt_gather_tile.cuh", "crt_tma.cuh", "crt_pow_tables.h", "crt_derive.h",
         os.path.join("..", "..", "include", "crt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]

@@ -16,6 +16,7 @@
 #include "crt_fused_gauss.cuh"
 #include "crt_fused_ps2.cuh"
 #include "crt_fused_gauss_ps2.cuh"
+#include "crt_gather_tile.cuh"
 
 using namespace crt;
 
@@ -58,6 +59,8 @@ struct crt_ctx {
     Dev dev{};
     bool dev_ok = false;
     int policy = 0;
+    CUtensorMap map_gather{};           // float32 [H][W*3] map of the state buffer with the gather kernel's 192 x 16 box
+    const void* map_gather_ptr = nullptr;
     Ps2Maps maps{};                     // tensor maps of the TMA-pipelined block kernel, valid for (maps_in, maps_frames, maps_st)
     const void* maps_in = nullptr; const void* maps_st = nullptr; int maps_frames = 0;
     FusedPlan plan{};                   // single-pass fused kernel
@@ -238,6 +241,18 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         return fail(ctx, CRT_ERR_UNSUPPORTED, std::string("fused kernel not available: ") + ctx->plan.why);
     if (want_two_pass && !ctx->scratch.q) CU(cudaMalloc((void**)&ctx->scratch.q, frame_px * 3 * sizeof(float)));
     static const bool use_pdl = env_int("CRT_PDL", 1) != 0;
+    // second pass of the two-pass path with the state moved by TMA: needs a tensor map of the state buffer (192 x 16 box)
+    static const bool use_gather_tile = env_int("CRT_GATHER_TILE", 1) != 0;
+    const CUtensorMap* gather_map = nullptr;
+    if (want_two_pass && use_gather_tile && d_state && !((uintptr_t)d_state & 15) && !(d.W & 3)) {
+        if (ctx->map_gather_ptr != d_state) {
+            const uint64_t W3 = (uint64_t)d.W * 3;
+            const uint64_t dims[2] = {W3, (uint64_t)d.H}, strides[1] = {W3 * 4};
+            const uint32_t box[2] = {(uint32_t)FTW * 3, (uint32_t)GATHER_TH};
+            if (tma_encode(&ctx->map_gather, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_state, dims, strides, box)) ctx->map_gather_ptr = d_state;
+        }
+        if (ctx->map_gather_ptr == d_state) gather_map = &ctx->map_gather;
+    }
     // TMA-pipelined block kernel: needs tensor maps of this call's clip and state buffers
     const bool pipe = (want_fused && ctx->plan.ps2 && !ctx->plan.gauss_k && persist && prepare_ps2_maps(ctx, d, d_in, n_frames, d_state)) ||
                       (want_two_pass && ctx->plan_q.ps2 && !ctx->plan_q.gauss_k && prepare_ps2_maps(ctx, ctx->dev_q, d_in, n_frames, ctx->scratch.q));
@@ -300,7 +315,7 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
                : pq.gauss_k ? run_fused_gauss(pq.th, pq.nt, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
                             : run_fused(pq, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches);
             prof_mark(ctx, st, true);
-            if (!rc) rc = run_gather(d, f, ctx->scratch.q, out_i, state_i, has_prev, st, &launches);
+            if (!rc) rc = run_gather_any(d, f, ctx->scratch.q, out_i, state_i, has_prev, st, &launches, gather_map);
             fused_used = 2;
         }
         else rc = run_staged(ctx, f, in_i, out_i, state_i, has_prev, img_i, st, &launches);
