@@ -109,3 +109,20 @@ def test_device_generators():
     top = (noisy[:, :300].float() - clean[:, :300].float())
     assert 0.5 < float(top.std()) < 4.0 and abs(float(top.mean())) < 0.5    # ~N(0, 3/255) before masks and persistence
     assert not torch.equal(noisy[:, 400:], clean[:, 400:])
+
+
+def test_unaligned_buffers_are_rejected_not_faulted():
+    """crt_process validates buffer alignment (16-byte state, 4-byte output) instead of faulting in a kernel."""
+    import torch
+    from pythoncrt_b200 import CrtEngine, CrtParams
+    from pythoncrt_b200.cabi import CrtError
+    eng = CrtEngine(128, 96).configure(CrtParams(noise_strength=0.0))
+    frames = torch.randint(0, 256, (2, 96, 128, 3), dtype=torch.uint8, device="cuda")
+    out = torch.empty_like(frames)
+    raw = torch.zeros(96 * 128 * 3 + 4, dtype=torch.float32, device="cuda")
+    bad_state = raw[1:1 + 96 * 128 * 3].view(96, 128, 3)             # 4-byte offset: not 16-byte aligned
+    assert bad_state.data_ptr() % 16 != 0
+    with pytest.raises(CrtError, match="aligned"):
+        eng.process(frames, out, state=bad_state, state_valid=False)
+    good, _ = eng.process(frames)                                     # the engine is still usable
+    assert good.shape == frames.shape
