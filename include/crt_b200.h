@@ -153,9 +153,9 @@ int crt_set_policy(crt_ctx* ctx, int policy);
  *   state_valid  0 = "state_prev is None" (first frame, no blend, :687 / :1086)
  *   frames host array of n_frames per-frame records
  *   stream cudaStream_t (NULL = legacy default stream)
- * d_state must be 16-byte and d_out 4-byte aligned (CRT_ERR_INVALID otherwise; cudaMalloc /
- * torch allocations are); with d_in 16-byte aligned as well the block kernels move their
- * tiles with TMA.
+ * When W % 4 == 0, d_state must be 16-byte and d_out 4-byte aligned (CRT_ERR_INVALID
+ * otherwise; cudaMalloc / torch allocations are); with d_in 16-byte aligned as well the
+ * block kernels move their tiles with TMA.
  * Replaces n_frames calls of apply_crt_effect (:531-699), or of
  * apply_static_effects (:702-861) + the blend/quantise block (:1086-1098).
  */

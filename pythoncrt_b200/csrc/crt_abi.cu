@@ -232,8 +232,9 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
     const bool persist = p.persistence > 0.0 && !d_img;
     if (persist && !d_state) return fail(ctx, CRT_ERR_INVALID, "persistence > 0 needs a state buffer");
     // the kernels move the state with 16-byte and the pixels with 4-byte accesses (device allocations are aligned far beyond that)
-    if (((uintptr_t)d_state & 15) || ((uintptr_t)d_out & 3) || ((uintptr_t)d_img & 15))
-        return fail(ctx, CRT_ERR_INVALID, "state / image buffers must be 16-byte aligned, the output clip 4-byte aligned");
+    // (frames whose width is not a multiple of 4 take scalar accesses and have no such requirement)
+    if ((d.W & 3) == 0 && (((uintptr_t)d_state & 15) || ((uintptr_t)d_out & 3)))
+        return fail(ctx, CRT_ERR_INVALID, "the state buffer must be 16-byte aligned, the output clip 4-byte aligned");
     CU(cudaSetDevice(ctx->device));
     const size_t frame_px = (size_t)d.W * d.H;
     const GlitchGeom gg = glitch_geom(p, d.W, d.H);
