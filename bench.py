@@ -38,6 +38,7 @@ WORKLOADS = {
     "cfg1": dict(desc="CLI default chain, noise off, 640x480", w=640, h=480, frames=64, fps=30.0, over={}, cpu_frames=640),
     "default4k": dict(desc="CLI default chain (scanline+triad+aberration+fast bloom+vignette+persistence, noise off) at 4K — the north_star target chain",
                       w=3840, h=2160, frames=300, fps=30.0, over={}, cpu_frames=24),
+    "default720": dict(desc="CLI default chain (as default4k) at 720p", w=1280, h=720, frames=600, fps=30.0, over={}, cpu_frames=96),
     "default1080": dict(desc="CLI default chain (as default4k) at 1080p", w=1920, h=1080, frames=600, fps=30.0, over={}, cpu_frames=96),
     "cfg2": dict(desc="1080p full chain, gaussian bloom sigma 1.5 thr 0.7 + colour grading", w=1920, h=1080, frames=600, fps=30.0,
                  over={**GAUSS, **GRADE}, cpu_frames=96),

@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_ps2(Dev d, FrameDev f, co
 // and count towards the barrier's byte count, a [frames][rows][bytes] map with a box of 1 frame never
 // completed — hence one 2-D map over the even rows of all frames (the frame pitch is H/2 row pitches).
 // Requires W % 8 == 0, |aberration| <= 6, 16-byte aligned clip / state pointers; used when there is a
-// state to fetch and the frame has at least ~500 tiles (run 68: 1080p 51 700 vs 44 900 frames/s, VGA neutral).
+// state to fetch and the frame has at least ~250 tiles (run 68: 1080p 51 700 vs 44 900 frames/s, VGA neutral).
 constexpr int P2_RAW_W = 256, P2_RAW_BYTES = P2_RAW_W * P2_BH;   // input buffer: 18 rows x 256 bytes (the box starts 16-byte aligned)
 constexpr int P2_ST_BYTES = P2_TH * P2_TW * 3 * 4;            // state tile: 32 x 192 float32
 constexpr int P2_PIPE_SMEM = P2_ST_BYTES + 2 * P2_RAW_BYTES;
@@ -503,7 +503,7 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
     const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1 && !d.noise_on;
     // TMA-pipelined variant (4 CTAs per SM, 3 with the bloom threshold on): pays off when there is a state to fetch and
     // every CTA walks over several tiles
-    static const int pipe_min_tiles = env_int("CRT_PIPE_MIN_TILES", 512);      // measured: wins at 1080p (1020 tiles) and 4K, neutral at VGA (150)
+    static const int pipe_min_tiles = env_int("CRT_PIPE_MIN_TILES", 256);      // measured: wins at 720p (460 tiles, +1.5 %), 1080p (+15 %) and 4K, neutral at VGA (150)
     if (maps && (q_out || has_prev) && ntiles >= pipe_min_tiles) {
         static int sms = 0;
         static bool configured[64] = {};                         // the opt-in shared-memory size is a per-device attribute

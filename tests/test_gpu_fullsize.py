@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 FULL = [
     Case("full_cfg1_vga", 480, 640, BASE, frames=4),
     Case("full_cfg2_1080p", 1080, 1920, BASE.but(**GAUSS, **GRADE), frames=2),
+    Case("full_default_720p", 720, 1280, BASE, frames=3),           # smallest frame class that takes the TMA-pipelined kernel
     Case("full_default_4k", 2160, 3840, BASE, frames=3),           # north_star chain: TMA-pipelined block kernel from frame 1 on
     Case("full_default_4k_thr", 2160, 3840, BASE.but(bloom_threshold=0.5, flicker_strength=0.3, flicker_hz=50.0), frames=3, source="structured"),
     Case("full_cfg3_4k", 2160, 3840, BASE.but(**WARP), frames=2),
