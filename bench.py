@@ -9,8 +9,12 @@ gaussian bloom + colour grading, 600 frames, 1 B200").  Prints ONE JSON line
 (contract in the task brief): value = whole-job frames/s with inputs in HBM,
 e2e = the same through the host-buffer C-ABI call (pinned host memory in and
 out, copies inside the timed region), roofline = achieved algorithmic GB/s of
-the dominant kernel against the measured HBM peak, cpu_baseline = the oracle
-port of the reference's CPU path timed on this box's host cores.
+all kernels of a frame against the measured HBM peak, cpu_baseline = the
+reference's CPU path (the unmodified module staged under baseline/_ref when it
+is importable, else the oracle port) timed on this box's host cores.  `also` =
+short runs of the other BASELINE configurations (default chain at 4K = the
+north_star target, cfg3; cfg4 at N > 1; cfg5 at N = 8) with whole-frame kernel
+times.
 
 Multi-GPU (torchrun, one rank per GPU): the clip is sharded temporally, every
 rank owns a chunk of `frames` frames preceded by its persistence warm-up halo
@@ -130,9 +134,19 @@ def oracle_params(over):
     return ChainParams(noise_strength=0.0).but(**over)
 
 
+def make_config(workload: str, wl: dict, world: int) -> dict:
+    """`config` of the JSON line — identical for our arm and the reference arm (the latter adds `sampled_frames`)."""
+    persistence = wl["over"].get("persistence", 0.2)          # CLI default 0.2 (crt_filter.py:1171); no product import on the reference arm
+    return {"workload": workload, "desc": wl["desc"], "width": wl["w"], "height": wl["h"], "frames_per_gpu": wl["frames"], "fps": wl["fps"],
+            "parallelism": f"temporal-shards x{world}", "rng": "device counter-based (noise/glitch generated)",
+            "l2": "clip (in+out) is larger than L2; no flush needed", "alg_bytes_per_px": alg_bytes_per_px(persistence)}
+
+
 def run_reference_arm(args, wl):
-    """--impl reference: the reference's CPU path (oracle port, same numpy/cv2 passes, export-like
-    2-worker loop) on this box's host cores; each step is a bounded sample of the workload."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores — the UNMODIFIED
+    reference module (staged under baseline/_ref by oracle/install_ref.py, imported by oracle/ref_loader.py) driven through
+    process_video's export loop (2-worker pool + ordered drain, crt_filter.py:1015-1131) when it is importable, else the
+    oracle port of the same loop.  Each step is a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -147,52 +161,34 @@ def run_reference_arm(args, wl):
         secs += info["seconds"]
     fps = n * args.steps / secs
     sample = f"{n} frames of {wl['w']}x{wl['h']} per step ({wl['frames']}-frame workload sampled; CPU path ~{fps:.2f} fps)"
+    cfg = make_config(args.workload, wl, max(1, args.gpus))
+    cfg["sampled_frames"] = n
     line = {"impl": "reference", "metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": wl["desc"], "width": wl["w"], "height": wl["h"], "frames": wl["frames"]},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": info["cpu_count"], "kind": "port", "sample": sample,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": info["cpu_count"], "kind": info["kind"], "sample": sample,
                              "worker_threads": info["workers"], "cv2_threads": info["cv2_threads"], "numpy": info["numpy"], "cv2": info["cv2"]},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
 
 
-def main() -> int:
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=0, help="override frames per clip (debug)")
-    ap.add_argument("--policy", default="auto", choices=["auto", "staged", "fused"])
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--time-every", type=int, default=8, help="CUDA events around one kernel launch in this many (1 = every launch)")
-    args = ap.parse_args()
-    wl = dict(WORKLOADS[args.workload])
-    if args.frames:
-        wl["frames"] = args.frames
-    if args.impl == "reference":
-        return run_reference_arm(args, wl)
+PATHS = {0: "staged", 1: "fused", 2: "two-pass"}
+KERNELS = {0: "staged kernels (bloom + pre-warp + output)", 1: "fused tile kernel", 2: "fused first pass + gather (+ generators)"}
 
-    import numpy as np
+
+def measure(workload: str, wl: dict, steps: int, warmup: int, policy: str, time_every: int, ctx: dict, keep: bool = False):
+    """One device-resident measurement of `workload` on this rank's GPU: W warm-up steps, K timed steps between CUDA
+    events, max over ranks.  The kernel time is the duration of ALL kernels of a frame (generators, first pass, gather),
+    from CUDA events on the launch stream around one frame in `time_every` (an event pair around every frame would remove
+    the frame-to-frame overlap of programmatic dependent launch from `value`).  Returns a dict."""
     import torch
     import torch.distributed as dist
     from pythoncrt_b200 import CrtEngine, clip
-
-    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    torch.cuda.set_device(local)
-    numa = bind_near_gpu(local) if os.environ.get("CRT_BENCH_BIND", "1") != "0" else None
-    dev = torch.device(f"cuda:{local}")
+    rank, world, local, dev = ctx["rank"], ctx["world"], ctx["local"], ctx["dev"]
     W, H, N, fps = wl["w"], wl["h"], wl["frames"], wl["fps"]
     p = product_params(wl["over"])
-    rng_modes = dict(noise_mode="generate", glitch_mode="generate", seed=1234)
-    eng = CrtEngine(W, H, local).configure(p, variant="export", policy=args.policy, **rng_modes)
-
+    eng = CrtEngine(W, H, local).configure(p, variant="export", policy=policy, noise_mode="generate", glitch_mode="generate", seed=1234)
     # this rank's chunk of the global clip: frames [rank*N, (rank+1)*N) preceded by the persistence halo
     halo = clip.halo_frames(p.persistence) if rank > 0 else 0
     first = rank * N - halo
@@ -210,16 +206,16 @@ def main() -> int:
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, warmup)):
         step()
     sync_all()
     launches0 = eng.kernels_launched
     sampler = ClockSampler(local)
     sampler.start()
-    eng.profile_begin(min(16384, (N + halo) * args.steps), every=args.time_every)
+    eng.profile_begin(min(16384, (N + halo) * steps), every=time_every)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record()
     sync_all()
@@ -229,17 +225,67 @@ def main() -> int:
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    launches = eng.kernels_launched - launches0
     fused = int(eng.last_info.fused)
-    value = world * N * args.steps / (total_ms * 1e-3)
+    value = world * N * steps / (total_ms * 1e-3)
     bpp = alg_bytes_per_px(p.persistence)
     peak, peak_src = hbm_peak()
     kern_avg_ms = kern_ms / max(1, kern_n)
     achieved = (W * H * bpp) / (kern_avg_ms * 1e-3) / 1e9 if kern_n else None
-    traffic = None
+    sustained = value / world * W * H * bpp / 1e9
+    res = {"value": value, "ms_per_step": total_ms / steps, "total_ms": total_ms, "halo": halo, "fused": fused, "bpp": bpp,
+           "launches": eng.kernels_launched - launches0, "clocks": clocks, "effective_gbs": value * W * H * bpp / 1e9,
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                        "traffic": None, "peak_source": peak_src, "kernel": KERNELS.get(fused), "scope": "all kernels of one frame, timed alone (event-fenced)",
+                        "kernel_avg_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "kernel_timed_every": time_every,
+                        "kernel_share_of_step": (kern_ms * time_every / total_ms) if total_ms else None,
+                        "frac_sustained": sustained / peak, "sustained_note": "per-GPU frames/s x algorithmic bytes / peak: consecutive frames overlap (PDL)"}}
+    if keep:
+        res.update(eng=eng, frames=frames, out=out)
+    else:
+        eng.close()
+        del frames, out, state
+        torch.cuda.empty_cache()
+    return res
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=0, help="override frames per clip (debug)")
+    ap.add_argument("--policy", default="auto", choices=["auto", "staged", "fused"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the short runs of the other BASELINE configurations")
+    ap.add_argument("--time-every", type=int, default=8, help="CUDA events around the kernels of one frame in this many (1 = every frame)")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.frames:
+        wl["frames"] = args.frames
+    if args.impl == "reference":
+        return run_reference_arm(args, wl)
+
+    import numpy as np  # noqa: F401
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    numa = bind_near_gpu(local) if os.environ.get("CRT_BENCH_BIND", "1") != "0" else None
+    dev = torch.device(f"cuda:{local}")
+    ctx = dict(rank=rank, world=world, local=local, dev=dev)
+    W, H, N, fps = wl["w"], wl["h"], wl["frames"], wl["fps"]
+
+    m = measure(args.workload, wl, args.steps, args.warmup, args.policy, args.time_every, ctx, keep=True)
+    eng, frames, out, halo = m.pop("eng"), m.pop("frames"), m.pop("out"), m["halo"]
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(args.workload)
+            m["roofline"]["traffic"] = json.load(f).get(args.workload)
     except Exception:
         pass
 
@@ -257,7 +303,9 @@ def main() -> int:
         e2e_steps = max(1, min(args.steps, 3))
         eng.reset_state()
         eng.process_host(h_in.numpy(), h_out.numpy(), fps=fps, first_index=rank * N)       # warm-up (allocates the ring)
-        sync_all()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             eng.reset_state()
@@ -270,35 +318,61 @@ def main() -> int:
         e2e = {"value": world * n_e2e * e2e_steps / float(dt.item()), "unit": "frames/s", "h2d_bytes_per_step": n_e2e * H * W * 3,
                "d2h_bytes_per_step": n_e2e * H * W * 3, "frames_per_step": n_e2e, "steps": e2e_steps, "api": "crt_process_host",
                "matches_device_path": same, "cpu_binding": numa}
+        ceiling = pcie_ceiling(world)
+        if ceiling:
+            e2e["ceiling_fps"] = ceiling["gbs_each_way"] * 1e9 / (H * W * 3)
+            e2e["ceiling"] = ceiling
+        del h_in, h_out
+    eng.close()
+    del frames, out
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configurations, short runs on the same box ----
+    also = None
+    if not args.no_also and args.workload == "cfg2":
+        also = {}
+        names = ["default4k", "cfg3"] + (["cfg4"] if world > 1 else []) + (["cfg5"] if world >= 8 else [])
+        for name in names:
+            w2 = dict(WORKLOADS[name])
+            w2["frames"] = min(w2["frames"], {"default4k": 200, "cfg3": 200, "cfg4": 120, "cfg5": 40}[name])
+            r = measure(name, w2, 3, 3, "auto", args.time_every, ctx)
+            if rank == 0:
+                also[name] = {"value": r["value"], "unit": "frames/s", "ms_per_step": r["ms_per_step"], "steps": 3, "warmup": 3,
+                              "config": make_config(name, w2, world), "path": PATHS.get(r["fused"]), "kernel_avg_ms": r["roofline"]["kernel_avg_ms"],
+                              "frac": r["roofline"]["frac"], "roofline": r["roofline"], "gpu_launches": r["launches"], "clocks": r["clocks"]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import cpu_bench
         info = cpu_bench.time_cpu_path(H, W, oracle_params(wl["over"]), fps, wl["cpu_frames"])
-        cpu = {"value": info["fps"], "unit": "frames/s", "cores": info["cpu_count"], "kind": "port",
+        cpu = {"value": info["fps"], "unit": "frames/s", "cores": info["cpu_count"], "kind": info["kind"],
                "sample": f"{info['frames']} frames of {W}x{H} through the export-like 2-worker loop, {info['seconds']:.1f} s",
                "worker_threads": info["workers"], "cv2_threads": info["cv2_threads"], "numpy": info["numpy"], "cv2": info["cv2"]}
 
     if rank == 0:
         line = {
-            "metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": args.workload, "desc": wl["desc"], "width": W, "height": H, "frames_per_gpu": N, "halo_frames": halo,
-                       "fps": fps, "parallelism": f"temporal-shards x{world}", "path": {0: "staged", 1: "fused", 2: "two-pass"}.get(fused, str(fused)),
-                       "rng": "device counter-based (noise/glitch generated)", "l2": "clip (in+out) is larger than L2; no flush needed",
-                       "alg_bytes_per_px": bpp},
-            "effective_gbs": value * W * H * bpp / 1e9,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": {0: "k_output (staged)", 1: "fused tile kernel", 2: "fused first pass (two-pass path)"}.get(fused),
-                         "kernel_avg_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "kernel_timed_every": args.time_every,
-                         "kernel_share_of_step": (kern_ms * args.time_every / total_ms) if total_ms else None},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "metric": "frames_per_sec", "value": m["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": make_config(args.workload, wl, world), "path": PATHS.get(m["fused"]), "halo_frames_rank_gt0": None,
+            "effective_gbs": m["effective_gbs"], "roofline": m["roofline"],
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": m["launches"], "clocks": m["clocks"], "also": also,
         }
+        from pythoncrt_b200 import clip as _clip
+        line["halo_frames_rank_gt0"] = _clip.halo_frames(product_params(wl["over"]).persistence)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def pcie_ceiling(world: int):
+    """Aggregate pinned host<->device copy ceiling measured for `world` concurrent ranks (profiles/pcie_ceiling.json, written
+    by profiles/tools/pcie_probe.py on the same pool); None when no measurement for this rank count is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "pcie_ceiling.json")) as f:
+            return json.load(f).get(str(world))
+    except Exception:
+        return None
 
 
 if __name__ == "__main__":

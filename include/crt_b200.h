@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CRT_B200_ABI_VERSION 1
+#define CRT_B200_ABI_VERSION 2
 
 typedef struct crt_ctx crt_ctx;
 
@@ -44,6 +44,7 @@ typedef enum crt_status {
 /* Which of the reference's two chains is being replaced: they differ only in
  * the glitch offset generator (:664-679 vs :835-853). */
 typedef enum crt_variant { CRT_VARIANT_GUI = 0, CRT_VARIANT_EXPORT = 1 } crt_variant;
+typedef enum crt_channel_order { CRT_ORDER_RGB = 0, CRT_ORDER_BGR = 1 } crt_channel_order;
 
 /*
  * Scalar effect parameters = the scalar arguments of apply_crt_effect
@@ -83,7 +84,9 @@ typedef struct crt_params {
     double warp_strength;
     /* glitch :664-686 / :835-859.  glitch_mode: 0 = offsets injected per frame
      * (crt_frame.d_glitch_offs, made on the host from numpy's PCG64 exactly as the
-     * reference does), 1 = generated on the device from the counter-based RNG */
+     * reference does), 1 = generated on the device from the counter-based RNG, keyed on the reference's own seed
+     * (int(|phase_px| * k) + (W << 10) + (H << 1), k = 0.05 gui :670 / 2.0 export :841) so that a pattern is held
+     * for exactly as many frames as the reference holds it */
     int32_t glitch_amp_px;
     double glitch_height_frac;
     int32_t glitch_mode;
@@ -92,7 +95,14 @@ typedef struct crt_params {
     /* persistence :687-694 / :1086-1096 */
     double persistence;
     int32_t variant;          /* crt_variant */
-    int32_t reserved[7];
+    /* Channel order of the frames (and of the float state / image): the reference's arithmetic is defined by channel
+     * INDEX with index 0 = R (luma weights :289, temperature gains :296-297, aberration :573-575, triad phase :224).
+     * CRT_ORDER_RGB feeds index 0 to those rules like the reference; CRT_ORDER_BGR (e.g. OpenCV capture buffers before
+     * the reference's COLOR_BGR2RGB, :1336) applies the R rules to index 2 and the B rules to index 0, so the result
+     * equals the reference's on the channel-swapped frame, swapped back, bit for bit.  Host tables (triad columns, text
+     * layer) are always given in the reference's RGB order. */
+    int32_t channel_order;    /* crt_channel_order */
+    int32_t reserved[6];
 } crt_params;
 
 /* Host-built tables.  The host side (pythoncrt_b200/tables.py) builds them with
@@ -181,8 +191,9 @@ int crt_process_host(crt_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, const cr
 int crt_reset_state(crt_ctx* ctx);
 
 /* Timing hooks for bench.py: while enabled, CUDA events are recorded (on the
- * launch stream) around the dominant kernel of every frame, up to max_samples.
- * crt_profile_end synchronises them and returns the summed duration and count. */
+ * launch stream) around ALL kernels of a frame (generators, first pass, gather),
+ * up to max_samples frames.  crt_profile_end synchronises them and returns the
+ * summed duration and the number of frames timed. */
 int crt_profile_begin(crt_ctx* ctx, int max_samples);
 int crt_profile_end(crt_ctx* ctx, double* total_ms, int* samples);
 /* Time only one launch in `every` (default 1 = all).  An event between two frames' kernels

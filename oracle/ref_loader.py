@@ -8,9 +8,11 @@ packages (with a real `__spec__`, otherwise `importlib.util.find_spec` raises
 and `ensure_deps` takes the pip branch, crt_filter.py:22-25) and make
 `subprocess.run` refuse to run while the module body executes.
 
-Only the pure numpy/cv2 functions of the reference are used afterwards.  The
-reference does not exist on the GPU box: `available()` is False there and every
-caller must cope (tests skip, golden fixtures are used instead).
+Only the pure numpy/cv2 functions of the reference are used afterwards.
+/root/reference does not exist on the GPU box; the copy staged under
+baseline/_ref by oracle/install_ref.py (git-ignored, shipped with the gpurun
+snapshot) is used there by `bench.py --impl reference`.  Tests never rely on
+it: they skip when `available()` is False and use the golden fixtures.
 """
 from __future__ import annotations
 
@@ -21,7 +23,11 @@ import subprocess
 import sys
 import types
 
-REFERENCE_PATH = os.environ.get("CRT_REFERENCE_PATH", "/root/reference/crt_filter.py")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the read-only checkout in the build container, else the copy staged by oracle/install_ref.py (travels to the GPU box)
+_CANDIDATES = [os.environ.get("CRT_REFERENCE_PATH", ""), "/root/reference/crt_filter.py",
+               os.path.join(os.path.dirname(_HERE), "baseline", "_ref", "crt_filter.py")]
+REFERENCE_PATH = next((c for c in _CANDIDATES if c and os.path.isfile(c)), _CANDIDATES[1])
 
 _STUBS = {
     "moviepy": {},

@@ -12,10 +12,11 @@ import os
 LIB_NAME = "libcrt_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 (TABLE_TRIAD_COLS, TABLE_LUT_FWD, TABLE_LUT_INV, TABLE_GAUSS_TAPS, TABLE_PIXELATE_X, TABLE_PIXELATE_Y,
  TABLE_VIGNETTE_PLANE, TABLE_TEXT_RGBA) = range(8)
 VARIANT_GUI, VARIANT_EXPORT = 0, 1
+ORDER_RGB, ORDER_BGR = 0, 1
 POLICY_AUTO, POLICY_STAGED, POLICY_FUSED = 0, 1, 2
 
 # every symbol include/crt_b200.h declares
@@ -44,7 +45,8 @@ class CrtParamsC(C.Structure):
         ("text_mode", C.c_int32),
         ("persistence", C.c_double),
         ("variant", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("channel_order", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 

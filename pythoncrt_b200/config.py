@@ -12,8 +12,10 @@ from .params import CrtParams
 
 def build_config(params: CrtParams, W: int, H: int, *, variant: str = "export", triad_cols="auto", vignette="auto",
                  text_rgba: Optional[np.ndarray] = None, text_after: bool = True, noise_mode: str = "inject",
-                 glitch_mode: str = "inject", seed: int = 0) -> Tuple[cabi.CrtParamsC, Dict[int, np.ndarray]]:
+                 glitch_mode: str = "inject", seed: int = 0, channel_order: str = "rgb") -> Tuple[cabi.CrtParamsC, Dict[int, np.ndarray]]:
     """Return (crt_params struct, {crt_table id: contiguous ndarray}).  See CrtEngine.configure."""
+    if channel_order not in ("rgb", "bgr"):
+        raise ValueError("channel_order must be 'rgb' (index 0 = R, like the reference) or 'bgr'")
     tabs: Dict[int, np.ndarray] = {}
     p = params
     c = cabi.CrtParamsC()
@@ -31,6 +33,7 @@ def build_config(params: CrtParams, W: int, H: int, *, variant: str = "export", 
     c.noise_mode = 1 if noise_mode == "generate" else 0
     c.glitch_mode = 1 if glitch_mode == "generate" else 0
     c.noise_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    c.channel_order = cabi.ORDER_BGR if channel_order == "bgr" else cabi.ORDER_RGB
 
     # triad column table + LUTs
     if isinstance(triad_cols, str):

@@ -11,12 +11,8 @@
 
 #include "../../include/crt_b200.h"
 #include "crt_derive.h"
-#include "crt_kernels.cuh"
-#include "crt_fused.cuh"
-#include "crt_fused_gauss.cuh"
-#include "crt_fused_ps2.cuh"
-#include "crt_fused_gauss_ps2.cuh"
-#include "crt_gather_tile.cuh"
+#include "crt_fused_ps2.cuh"      // types and constants only: the kernels are instantiated in the crt_tu_*.cu units
+#include "crt_launch.h"
 
 using namespace crt;
 
@@ -59,6 +55,7 @@ struct crt_ctx {
     Dev dev{};
     bool dev_ok = false;
     int policy = 0;
+    LaunchEnv env;                      // per-context launch state (SM count, configured kernels): no process-wide statics
     CUtensorMap map_gather{};           // float32 [H][W*3] map of the state buffer with the gather kernel's 192 x 16 box
     const void* map_gather_ptr = nullptr;
     Ps2Maps maps{};                     // tensor maps of the TMA-pipelined block kernel, valid for (maps_in, maps_frames, maps_st)
@@ -160,16 +157,23 @@ int ensure_scratch(crt_ctx* ctx) {
     return CRT_OK;
 }
 
+// Key of the generated glitch pattern: the reference's own seed formula (gui crt_filter.py:670, export :841), so that the
+// pattern changes exactly when the reference's does (the GUI holds a pattern for 20 phase-px, the export for 0.5).
+uint64_t glitch_key(const crt_params& p, int W, int H, const crt_frame& fr) {
+    const double k = p.variant == CRT_VARIANT_EXPORT ? 2.0 : 0.05;
+    return (uint64_t)(((long long)(fabs(fr.phase_px) * k) + ((long long)W << 10) + ((long long)H << 1)) & 0xFFFFFFFFll);
+}
+
 int gen_glitch(crt_ctx* ctx, const crt_frame& fr, const GlitchGeom& g, int32_t* d_offs, cudaStream_t st) {
     if (g.rows <= 0) return CRT_OK;
     if (g.rows > 12000) return fail(ctx, CRT_ERR_UNSUPPORTED, "glitch band taller than 12000 rows");
-    k_glitch_gen<<<1, GLITCH_THREADS, (size_t)g.rows * sizeof(float), st>>>(d_offs, g.rows, g.nseg, ctx->p.variant == CRT_VARIANT_EXPORT ? 1 : 0,
-                                                                           (float)ctx->p.glitch_amp_px, ctx->p.noise_seed ^ 0x9E3779B97F4A7C15ull, fr.frame_index);
-    CU(cudaGetLastError());
+    if (launch_glitch_gen(d_offs, g.rows, g.nseg, ctx->p.variant == CRT_VARIANT_EXPORT ? 1 : 0, (float)ctx->p.glitch_amp_px,
+                          ctx->p.noise_seed ^ 0x9E3779B97F4A7C15ull, glitch_key(ctx->p, ctx->W, ctx->H, fr), st))
+        return fail(ctx, CRT_ERR_CUDA, std::string("glitch generator launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     return CRT_OK;
 }
 
-// bench.py timing hook: events around the dominant kernel of a frame
+// bench.py timing hook: events around ALL kernels of a frame (generators, first pass, gather), one frame in prof_every
 void prof_mark(crt_ctx* ctx, cudaStream_t st, bool stop) {
     if (!ctx->prof_on || ctx->prof_n >= ctx->prof_cap) return;
     if (!stop) ctx->prof_open = (ctx->prof_tick++ % ctx->prof_every) == 0;
@@ -181,26 +185,8 @@ void prof_mark(crt_ctx* ctx, cudaStream_t st, bool stop) {
 // One frame through the staged kernels.
 int run_staged(crt_ctx* ctx, const FrameDev& f, const uint8_t* d_in, uint8_t* d_out, float* d_state, int has_prev, float* d_img,
                cudaStream_t st, int* launches) {
-    const Dev& d = ctx->dev;
     int rc = ensure_scratch(ctx); if (rc) return rc;
-    dim3 blk(32, 8);
-    if (d.bloom_mode == 1) {
-        dim3 grd((d.hw + 31) / 32, (d.hh + 7) / 8);
-        k_bloom_down<<<grd, blk, 0, st>>>(d, d_in, ctx->scratch.ds); ++*launches;
-    } else if (d.bloom_mode == 2) {
-        const int r = d.ksize / 2;
-        size_t smem = ((size_t)(GAUSS_TH + 2 * r) * (GAUSS_TW + 2 * r) + (size_t)(GAUSS_TH + 2 * r) * GAUSS_TW) * 3 * sizeof(float);
-        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_bloom_gauss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grd((d.W + GAUSS_TW - 1) / GAUSS_TW, (d.H + GAUSS_TH - 1) / GAUSS_TH);
-        k_bloom_gauss<<<grd, blk, smem, st>>>(d, d_in, ctx->scratch.bl); ++*launches;
-    }
-    dim3 grd((d.W + 31) / 32, (d.H + 7) / 8);
-    if (d.warp_on) { k_pre_warp<<<grd, blk, 0, st>>>(d, f, d_in, ctx->scratch); ++*launches; }
-    prof_mark(ctx, st, false);
-    k_output<<<grd, blk, 0, st>>>(d, f, d_in, ctx->scratch, has_prev, d_state, d_out, d_img); ++*launches;
-    prof_mark(ctx, st, true);
-    CU(cudaGetLastError());
-    return CRT_OK;
+    return launch_staged(ctx->env, ctx->dev, f, d_in, d_out, d_state, has_prev, d_img, ctx->scratch, st, launches);
 }
 
 // Tensor maps for k_fused_ps2_pipe: the clip as uint8 [frames * H/2 even rows][W*3] (box 256 x 18) and the
@@ -233,14 +219,16 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
     if (persist && !d_state) return fail(ctx, CRT_ERR_INVALID, "persistence > 0 needs a state buffer");
     // the kernels move the state with 16-byte and the pixels with 4-byte accesses (device allocations are aligned far beyond that)
     // (frames whose width is not a multiple of 4 take scalar accesses and have no such requirement)
-    if ((d.W & 3) == 0 && (((uintptr_t)d_state & 15) || ((uintptr_t)d_out & 3)))
-        return fail(ctx, CRT_ERR_INVALID, "the state buffer must be 16-byte aligned, the output clip 4-byte aligned");
+    if ((d.W & 3) == 0 && (((uintptr_t)d_state & 15) || ((uintptr_t)d_out & 3) || ((uintptr_t)d_img & 15)))
+        return fail(ctx, CRT_ERR_INVALID, "the state / float image buffer must be 16-byte aligned, the output clip 4-byte aligned");
     CU(cudaSetDevice(ctx->device));
     const size_t frame_px = (size_t)d.W * d.H;
     const GlitchGeom gg = glitch_geom(p, d.W, d.H);
     int launches = 0, fused_used = 0;
-    const bool want_fused = ctx->policy != 1 && ctx->plan.ok && !d_img;
-    const bool want_two_pass = ctx->policy != 1 && !want_fused && ctx->plan_q.ok && !d_img;
+    // crt_process_static (d_img) takes the same kernels: the float image leaves through the path the pre-warp image of the
+    // two-pass path takes (q_out), or is what the gather writes as "state" when no previous state is blended in
+    const bool want_fused = ctx->policy != 1 && ctx->plan.ok;
+    const bool want_two_pass = ctx->policy != 1 && !want_fused && ctx->plan_q.ok;
     if (ctx->policy == 2 && !want_fused && !want_two_pass)
         return fail(ctx, CRT_ERR_UNSUPPORTED, std::string("fused kernel not available: ") + ctx->plan.why);
     if (want_two_pass && !ctx->scratch.q) CU(cudaMalloc((void**)&ctx->scratch.q, frame_px * 3 * sizeof(float)));
@@ -248,7 +236,7 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
     // second pass of the two-pass path with the state moved by TMA: needs a tensor map of the state buffer (192 x 16 box)
     static const bool use_gather_tile = env_int("CRT_GATHER_TILE", 1) != 0;
     const CUtensorMap* gather_map = nullptr;
-    if (want_two_pass && use_gather_tile && d_state && !((uintptr_t)d_state & 15) && !(d.W & 3)) {
+    if (want_two_pass && use_gather_tile && !d_img && d_state && !((uintptr_t)d_state & 15) && !(d.W & 3)) {
         if (ctx->map_gather_ptr != d_state) {
             const uint64_t W3 = (uint64_t)d.W * 3;
             const uint64_t dims[2] = {W3, (uint64_t)d.H}, strides[1] = {W3 * 4};
@@ -263,13 +251,14 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
     for (int i = 0; i < n_frames; ++i) {
         const crt_frame& fr = frames[i];
         FrameDev f = derive_frame(p, fr);
+        prof_mark(ctx, st, false);          // whole frame: generators + every pass
         if (d.noise_on) {
             f.noise = fr.d_noise;
             if (!f.noise) {
                 if (p.noise_mode != 1) return fail(ctx, CRT_ERR_INVALID, "noise_strength > 0 with noise_mode 0 needs crt_frame.d_noise");
                 if (!ctx->noise_buf) CU(cudaMalloc((void**)&ctx->noise_buf, frame_px * sizeof(float)));
-                const int cells = d.gh * d.gw;
-                k_noise_gen<<<((cells + 3) / 4 + 255) / 256, 256, 0, st>>>(ctx->noise_buf, cells, p.noise_seed, fr.frame_index); ++launches;
+                if (launch_noise_gen(ctx->noise_buf, d.gh * d.gw, p.noise_seed, fr.frame_index, st)) return fail(ctx, CRT_ERR_CUDA, "noise generator launch failed");
+                ++launches;
                 f.noise = ctx->noise_buf;
             }
         }
@@ -298,31 +287,30 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         uint8_t* out_i = d_out ? d_out + (size_t)i * frame_px * 3 : nullptr;
         float* img_i = d_img ? d_img + (size_t)i * frame_px * 3 : nullptr;
         float* state_i = (persist || (d_state && !d_img)) ? d_state : nullptr;
+        float* q_i = nullptr;               // single-pass kernels: where the float image goes instead of out / state
+        if (d_img) { if (want_two_pass) state_i = img_i; else q_i = img_i; }
         // Frames after the first may overlap the previous frame's kernel tail (launch_pdl, crt_fused.cuh).  Never frame 0:
         // its input may come from the caller's immediately preceding kernel.
         const bool pdl = i > 0 && use_pdl;
         ctx->maps.frame = i;
         int rc;
         if (want_fused) {
-            prof_mark(ctx, st, false);
-            rc = (ctx->plan.ps2 && ctx->plan.gauss_k) ? run_fused_gauss_ps2(d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches, pdl)
-               : ctx->plan.ps2 ? run_fused_ps2(d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches, pdl, pipe ? &ctx->maps : nullptr)
-               : ctx->plan.gauss_k ? run_fused_gauss(ctx->plan.th, ctx->plan.nt, d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches)
-                                   : run_fused(ctx->plan, d, f, in_i, out_i, state_i, nullptr, has_prev, st, &launches);
+            rc = (ctx->plan.ps2 && ctx->plan.gauss_k) ? launch_fused_gauss_ps2(ctx->env, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches, pdl)
+               : ctx->plan.ps2 ? launch_fused_ps2(ctx->env, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches, pdl, pipe ? &ctx->maps : nullptr)
+               : ctx->plan.gauss_k ? launch_fused_gauss(ctx->env, ctx->plan.th, ctx->plan.nt, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches)
+                                   : launch_fused(ctx->env, ctx->plan, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches);
             fused_used = 1;
-            prof_mark(ctx, st, true);
         } else if (want_two_pass) {
             const FusedPlan& pq = ctx->plan_q;
-            prof_mark(ctx, st, false);
-            rc = (pq.ps2 && pq.gauss_k) ? run_fused_gauss_ps2(ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl)
-               : pq.ps2 ? run_fused_ps2(ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl, pipe ? &ctx->maps : nullptr)
-               : pq.gauss_k ? run_fused_gauss(pq.th, pq.nt, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
-                            : run_fused(pq, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches);
-            prof_mark(ctx, st, true);
-            if (!rc) rc = run_gather_any(d, f, ctx->scratch.q, out_i, state_i, has_prev, st, &launches, gather_map);
+            rc = (pq.ps2 && pq.gauss_k) ? launch_fused_gauss_ps2(ctx->env, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl)
+               : pq.ps2 ? launch_fused_ps2(ctx->env, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl, pipe ? &ctx->maps : nullptr)
+               : pq.gauss_k ? launch_fused_gauss(ctx->env, pq.th, pq.nt, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
+                            : launch_fused(ctx->env, pq, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches);
+            if (!rc) rc = launch_gather(ctx->env, d, f, ctx->scratch.q, out_i, state_i, has_prev, st, &launches, gather_map);
             fused_used = 2;
         }
         else rc = run_staged(ctx, f, in_i, out_i, state_i, has_prev, img_i, st, &launches);
+        prof_mark(ctx, st, true);
         if (rc == CRT_ERR_CUDA) return fail(ctx, rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
         if (rc) return rc;
     }
@@ -348,6 +336,8 @@ int crt_create(int device, int width, int height, crt_ctx** out_ctx) {
     crt_ctx* c = new (std::nothrow) crt_ctx();
     if (!c) return fail(nullptr, CRT_ERR_INVALID, "out of host memory");
     c->device = device; c->W = width; c->H = height;
+    c->env.device = device;
+    if (cudaDeviceGetAttribute(&c->env.sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->env.sms < 1) c->env.sms = 148;
     ctx = c;
     const int hw = width / 2 > 1 ? width / 2 : 1, hh = height / 2 > 1 ? height / 2 : 1;
     c->h_dn_x = linear_coords(hw, width); c->h_dn_y = linear_coords(hh, height);
@@ -399,7 +389,8 @@ int crt_destroy(crt_ctx* ctx) {
 int crt_set_params(crt_ctx* ctx, const crt_params* params) {
     if (!ctx || !params) return CRT_ERR_INVALID;
     if (params->pixel_size < 1 || params->grain_size < 0 || params->text_mode < 0 || params->text_mode > 2 || params->vignette_on < 0 ||
-        params->vignette_on > 2 || !(params->persistence >= 0.0 && params->persistence < 1.0))
+        params->vignette_on > 2 || !(params->persistence >= 0.0 && params->persistence < 1.0) || params->channel_order < 0 ||
+        params->channel_order > 1)
         return fail(ctx, CRT_ERR_INVALID, "parameter out of range");
     ctx->p = *params;
     ctx->have_params = true;
@@ -534,9 +525,8 @@ int crt_generate_noise(crt_ctx* ctx, uint64_t frame_index, float* d_plane, void*
     if (!ctx->have_params) return fail(ctx, CRT_ERR_INVALID, "crt_set_params has not been called");
     if (!ctx->dev_ok) { int rc = build_dev(ctx); if (rc) return rc; }
     CU(cudaSetDevice(ctx->device));
-    const int cells = ctx->dev.gh * ctx->dev.gw;
-    k_noise_gen<<<((cells + 3) / 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_plane, cells, ctx->p.noise_seed, frame_index);
-    CU(cudaGetLastError());
+    if (launch_noise_gen(d_plane, ctx->dev.gh * ctx->dev.gw, ctx->p.noise_seed, frame_index, (cudaStream_t)stream))
+        return fail(ctx, CRT_ERR_CUDA, std::string("noise generator launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     return CRT_OK;
 }
 

@@ -45,8 +45,10 @@ inline bool glitch_active(const crt_params& p) { return p.glitch_amp_px > 0 && p
 inline int derive_dev(const crt_params& p, int W, int H, const TablePtrs& t, Dev* out, std::string* err) {
     Dev d{};
     d.W = W; d.H = H;
-    d.aberr = p.aberration_px;
-    d.aberr_mod = ((p.aberration_px % W) + W) % W;
+    d.bgr = p.channel_order == CRT_ORDER_BGR;
+    // aberration rolls the R plane by +a and the B plane by -a (:573-575): with B at index 0 the signs swap
+    d.aberr = d.bgr ? -p.aberration_px : p.aberration_px;
+    d.aberr_mod = ((d.aberr % W) + W) % W;
     if (p.pixel_size > 1) {
         if (t.bytes[CRT_TABLE_PIXELATE_X] != (size_t)W * 4 || t.bytes[CRT_TABLE_PIXELATE_Y] != (size_t)H * 4)
             { *err = "pixel_size > 1 needs CRT_TABLE_PIXELATE_X [W] and _Y [H]"; return CRT_ERR_INVALID; }
@@ -56,8 +58,9 @@ inline int derive_dev(const crt_params& p, int W, int H, const TablePtrs& t, Dev
     }
     d.col_sat = p.saturation != 1.0; d.sat_f = (float)p.saturation;
     d.col_temp = p.temperature != 0.0;
-    d.gain0 = (float)fmin(fmax(1.0 + 0.5 * p.temperature, 0.5), 1.5);
-    d.gain2 = (float)fmin(fmax(1.0 - 0.5 * p.temperature, 0.5), 1.5);
+    d.gain0 = (float)fmin(fmax(1.0 + 0.5 * p.temperature, 0.5), 1.5);          // R gain (:296), applied to the index that holds R
+    d.gain2 = (float)fmin(fmax(1.0 - 0.5 * p.temperature, 0.5), 1.5);          // B gain (:297)
+    if (d.bgr) { const float g = d.gain0; d.gain0 = d.gain2; d.gain2 = g; }
     d.col_bc = p.brightness != 0.0 || p.contrast != 1.0;
     d.contrast = (float)p.contrast; d.brightness = (float)p.brightness;
     d.col_gamma = p.gamma != 1.0 && p.gamma > 0.0;

@@ -23,10 +23,14 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
 #include "crt_stages.cuh"
+#if defined(__CUDACC__)
+#include "crt_launch.h"
+#endif
 
 namespace crt {
 
@@ -208,9 +212,10 @@ __device__ __forceinline__ F3 after_bloom_fast(const Dev& d, const FrameDev& f, 
         if (d.triad_comp) {
             if (x >= d.comp_x0 && x <= d.comp_x1) {               // regular column: one composite look-up per channel
                 const int ph = x - 3 * (int)__umulhi((unsigned)x, 0x55555556u);     // x % 3
-                v.x = (ph == 0 ? fwd : inv)[lut_index_fast(__saturatef(v.x))];
+                const int p0 = d.bgr ? 2 : 0;                     // mask phase of channel index 0 (R in RGB order)
+                v.x = (ph == p0 ? fwd : inv)[lut_index_fast(__saturatef(v.x))];
                 v.y = (ph == 1 ? fwd : inv)[lut_index_fast(__saturatef(v.y))];
-                v.z = (ph == 2 ? fwd : inv)[lut_index_fast(__saturatef(v.z))];
+                v.z = (ph == 2 - p0 ? fwd : inv)[lut_index_fast(__saturatef(v.z))];
             } else {
                 v = triad(d, v, x, d.lut_fwd, d.lut_inv);         // mask edge columns: full path from global memory
             }
@@ -274,7 +279,7 @@ __device__ __forceinline__ void finish_quad(const Dev& d, float* __restrict__ st
             sp[1] = make_float4(res[4], res[5], res[6], res[7]);
             sp[2] = make_float4(res[8], res[9], res[10], res[11]);
         }
-        if (q_out) return;
+        if (q_out || !out) return;          // float image only (first pass of the two-pass path / crt_process_static)
         uint32_t w[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j)
@@ -286,7 +291,7 @@ __device__ __forceinline__ void finish_quad(const Dev& d, float* __restrict__ st
         for (int k = 0; k < 12; ++k)
             if (k < npx * 3) {
                 if (state) state[o + k] = res[k];
-                if (!q_out) out[o + k] = quantise(res[k]);
+                if (!q_out && out) out[o + k] = quantise(res[k]);
             }
     }
 }
@@ -621,6 +626,7 @@ __global__ void __launch_bounds__(256) k_gather(Dev d, FrameDev f, const float* 
     finish_quad(d, state, out, nullptr, has_prev, y, xb, imin(4, d.W - xb), pixel);
 }
 
+#if defined(CRT_TU_FUSED)
 inline int run_gather(const Dev& d, const FrameDev& f, const float* qimg, uint8_t* out, float* state, int has_prev, cudaStream_t st, int* launches) {
     dim3 grid((d.W + FTW - 1) / FTW, (d.H + GATHER_TH - 1) / GATHER_TH);
     if (d.warp_on) k_gather<true><<<grid, 256, 0, st>>>(d, f, qimg, out, state, has_prev);
@@ -628,6 +634,8 @@ inline int run_gather(const Dev& d, const FrameDev& f, const float* qimg, uint8_
     ++*launches;
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
+
+#endif  // CRT_TU_FUSED
 
 #endif  // __CUDACC__
 
@@ -727,28 +735,24 @@ inline FusedPlan plan_fused(const Dev& hd, bool glitch_on) {
     return small.ok ? small : best;
 }
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && defined(CRT_TU_FUSED)      // launchers: compiled only in crt_tu_fused.cu
 template <int BLOOM, bool WARP, int NT>
-inline int launch_fused_t(const FusedPlan& pl, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state,
+inline int launch_fused_t(LaunchEnv& env, const FusedPlan& pl, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state,
                           float* q_out, int has_prev, cudaStream_t st) {
-    static size_t configured[64] = {};      // per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (pl.smem > configured[dev & 63]) {
-        if (cudaFuncSetAttribute(k_fused<BLOOM, WARP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) return 2;
-        configured[dev & 63] = pl.smem;
-    }
+    auto kern = k_fused<BLOOM, WARP, NT>;
+    if (env.raise((const void*)kern, (int)pl.smem) &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) return 2;
     dim3 grid((d.W + FTW - 1) / FTW, (d.H + pl.th - 1) / pl.th);
     FusedGeom g{pl.th, pl.cap_px, pl.cap_aux};
-    k_fused<BLOOM, WARP, NT><<<grid, NT, pl.smem, st>>>(d, f, in, out, state, q_out, has_prev, g);
+    kern<<<grid, NT, pl.smem, st>>>(d, f, in, out, state, q_out, has_prev, g);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
-inline int run_fused(const FusedPlan& pl, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
+inline int run_fused(LaunchEnv& env, const FusedPlan& pl, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
                      int has_prev, cudaStream_t st, int* launches) {
     int rc;
-#define CRT_LAUNCH(B, W) (pl.nt == 512 ? launch_fused_t<B, W, 512>(pl, d, f, in, out, state, q_out, has_prev, st) \
-                                       : launch_fused_t<B, W, 256>(pl, d, f, in, out, state, q_out, has_prev, st))
+#define CRT_LAUNCH(B, W) (pl.nt == 512 ? launch_fused_t<B, W, 512>(env, pl, d, f, in, out, state, q_out, has_prev, st) \
+                                       : launch_fused_t<B, W, 256>(env, pl, d, f, in, out, state, q_out, has_prev, st))
     if (d.warp_on) rc = d.bloom_mode == 1 ? CRT_LAUNCH(1, true) : CRT_LAUNCH(0, true);
     else rc = d.bloom_mode == 2 ? CRT_LAUNCH(2, false) : d.bloom_mode == 1 ? CRT_LAUNCH(1, false) : CRT_LAUNCH(0, false);
 #undef CRT_LAUNCH

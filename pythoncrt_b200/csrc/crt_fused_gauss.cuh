@@ -196,37 +196,34 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_fused_gauss(Dev d, FrameDev f
     for (int y = oy0 + trow; y <= oy1; y += NT / FROW_THREADS) finish_quad(d, state, out, q_out, has_prev, y, xb, imin(4, ox1 - xb + 1), pixel);
 }
 
+#if defined(CRT_TU_GAUSS)      // launcher: compiled only in the translation unit that owns these kernels (build.py)
 template <int K, int GAUSS_NT>
-inline int launch_fused_gauss_t(int th, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
+inline int launch_fused_gauss_t(LaunchEnv& env, int th, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
                                 int has_prev, cudaStream_t st) {
-    static size_t configured[64] = {};
     const size_t smem = fused_gauss_smem(K, th);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (smem > configured[dev & 63]) {
-        if (cudaFuncSetAttribute(k_fused_gauss<K, GAUSS_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
-        configured[dev & 63] = smem;
-    }
+    auto kern = k_fused_gauss<K, GAUSS_NT>;
+    if (env.raise((const void*)kern, (int)smem) &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
     dim3 grid((d.W + FTW - 1) / FTW, (d.H + th - 1) / th);
-    k_fused_gauss<K, GAUSS_NT><<<grid, GAUSS_NT, smem, st>>>(d, f, in, out, state, q_out, has_prev, th);
+    kern<<<grid, GAUSS_NT, smem, st>>>(d, f, in, out, state, q_out, has_prev, th);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
-inline int run_fused_gauss(int th, int nt, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
+inline int run_fused_gauss(LaunchEnv& env, int th, int nt, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
                            int has_prev, cudaStream_t st, int* launches) {
     int rc = 4;
+#define CRT_GAUSS_CASE(K) case K: rc = nt == 512 ? launch_fused_gauss_t<K, 512>(env, th, d, f, in, out, state, q_out, has_prev, st) \
+                                                  : launch_fused_gauss_t<K, 256>(env, th, d, f, in, out, state, q_out, has_prev, st); break;
     switch (d.ksize) {
-        case 5: rc = nt == 512 ? launch_fused_gauss_t<5, 512>(th, d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_t<5, 256>(th, d, f, in, out, state, q_out, has_prev, st); break;
-        case 7: rc = nt == 512 ? launch_fused_gauss_t<7, 512>(th, d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_t<7, 256>(th, d, f, in, out, state, q_out, has_prev, st); break;
-        case 9: rc = nt == 512 ? launch_fused_gauss_t<9, 512>(th, d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_t<9, 256>(th, d, f, in, out, state, q_out, has_prev, st); break;
-        case 11: rc = nt == 512 ? launch_fused_gauss_t<11, 512>(th, d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_t<11, 256>(th, d, f, in, out, state, q_out, has_prev, st); break;
-        case 13: rc = nt == 512 ? launch_fused_gauss_t<13, 512>(th, d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_t<13, 256>(th, d, f, in, out, state, q_out, has_prev, st); break;
-        case 25: rc = nt == 512 ? launch_fused_gauss_t<25, 512>(th, d, f, in, out, state, q_out, has_prev, st) : launch_fused_gauss_t<25, 256>(th, d, f, in, out, state, q_out, has_prev, st); break;
+        CRT_GAUSS_CASE(5) CRT_GAUSS_CASE(7) CRT_GAUSS_CASE(9) CRT_GAUSS_CASE(11) CRT_GAUSS_CASE(13) CRT_GAUSS_CASE(25)
         default: break;
     }
-    ++*launches;
+#undef CRT_GAUSS_CASE
+    if (rc != 4) ++*launches;
     return rc;
 }
+
+#endif  // CRT_TU_GAUSS
 
 #endif  // __CUDACC__
 

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
         if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
     }
     s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
-    ps2_fill_sel(s_sel, tid);
+    ps2_fill_sel(s_sel, tid, d.bgr);
     if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += blockDim.x) s_pow[i] = d.pow_tab[i];
     float taps[K];                                  // the kernel is symmetric: R + 1 registers
 #pragma unroll
@@ -220,50 +220,46 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
     }
 }
 
+#if defined(CRT_TU_GAUSS_PS2)      // launcher: compiled only in the translation unit that owns these kernels (build.py)
 template <int K, int MINB>
-inline int launch_fused_gauss_ps2_t(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
+inline int launch_fused_gauss_ps2_t(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
                                     int has_prev, cudaStream_t st, bool pdl) {
-    static bool configured[64] = {};
-    static int resident = 0;
     const size_t smem = fused_gauss_ps2_smem(K);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-        if (cudaFuncSetAttribute(k_fused_gauss_ps2<K, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
-        if (cudaFuncSetAttribute(k_fused_gauss_ps2<K, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
-        configured[dev & 63] = true;
+    const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1 && !d.noise_on;
+    auto kern = fast ? k_fused_gauss_ps2<K, true, MINB> : k_fused_gauss_ps2<K, false, MINB>;
+    // per context and kernel: opt-in shared-memory size, then the number of CTAs the device holds (persistent grid)
+    auto it = env.memo.find((const void*)kern);
+    if (it == env.memo.end()) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P2_NT, smem);
+        it = env.memo.emplace((const void*)kern, env.sms * (per_sm > 0 ? per_sm : 1)).first;
     }
-    if (!resident) {
-        int sms = 148, per_sm = 4;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_gauss_ps2<K, true, MINB>, P2_NT, smem);
-        resident = sms * (per_sm > 0 ? per_sm : 1);
-        if (env_int("CRT_PS2_PERSIST", 1) == 0) resident = 1 << 30;
-    }
+    static const bool persist = env_int("CRT_PS2_PERSIST", 1) != 0;
+    const int resident = persist ? it->second : (1 << 30);
     const int ntiles = ((d.W + P2_TW - 1) / P2_TW) * ((d.H + P2_TH - 1) / P2_TH);
     const dim3 grid(ntiles < resident ? ntiles : resident);
-    const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1 && !d.noise_on;
-    const cudaError_t e = launch_pdl(fast ? k_fused_gauss_ps2<K, true, MINB> : k_fused_gauss_ps2<K, false, MINB>, grid, dim3(P2_NT), smem, st, pdl,
-                                     d, f, in, out, state, q_out, has_prev);
+    const cudaError_t e = launch_pdl(kern, grid, dim3(P2_NT), smem, st, pdl, d, f, in, out, state, q_out, has_prev);
     return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
 }
 
-inline int run_fused_gauss_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
+inline int run_fused_gauss_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
                                cudaStream_t st, int* launches, bool pdl = false) {
     int rc = 4;
-    static const int minb = env_int("CRT_GPS2_MINB", 3);        // CTAs per SM the kernel is compiled for (64 vs 80 registers)
     switch (d.ksize) {
-        case 5: rc = minb == 3 ? launch_fused_gauss_ps2_t<5, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<5, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
-        case 7: rc = minb == 3 ? launch_fused_gauss_ps2_t<7, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<7, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
-        case 9: rc = minb == 3 ? launch_fused_gauss_ps2_t<9, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<9, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
-        case 11: rc = minb == 3 ? launch_fused_gauss_ps2_t<11, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<11, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
-        case 13: rc = minb == 3 ? launch_fused_gauss_ps2_t<13, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<13, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
-        case 25: rc = minb == 3 ? launch_fused_gauss_ps2_t<25, 3>(d, f, in, out, state, q_out, has_prev, st, pdl) : launch_fused_gauss_ps2_t<25, 4>(d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 5: rc = launch_fused_gauss_ps2_t<5, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 7: rc = launch_fused_gauss_ps2_t<7, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 9: rc = launch_fused_gauss_ps2_t<9, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 11: rc = launch_fused_gauss_ps2_t<11, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 13: rc = launch_fused_gauss_ps2_t<13, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 25: rc = launch_fused_gauss_ps2_t<25, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl); break;
         default: break;
     }
-    ++*launches;
+    if (rc != 4) ++*launches;        // an unsupported tap count launches nothing
     return rc;
 }
+
+#endif  // CRT_TU_GAUSS_PS2
 
 #endif  // __CUDACC__
 

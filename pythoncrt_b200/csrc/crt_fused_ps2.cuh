@@ -15,6 +15,7 @@
 // Two variants: k_fused_ps2 (plain loads) and k_fused_ps2_pipe (tile input and state by TMA, below).
 #pragma once
 #include "crt_fused.cuh"
+#include "crt_launch.h"
 #include "crt_tma.cuh"
 
 namespace crt {
@@ -134,10 +135,10 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
 }
 
 // s_sel[p][3 k + ch]: index offset of the table column k (0..3) of a quad with xb % 3 == p uses for channel ch
-__device__ __forceinline__ void ps2_fill_sel(int (*s_sel)[12], int tid) {
+__device__ __forceinline__ void ps2_fill_sel(int (*s_sel)[12], int tid, int bgr) {
     if (tid < 36) {
         const int p = tid / 12, e = tid - 12 * p, k = e / 3, ch = e - 3 * k;
-        s_sel[p][e] = ((p + k) % 3 == ch) ? 0 : 1028;
+        s_sel[p][e] = ((p + k) % 3 == (bgr ? 2 - ch : ch)) ? 0 : 1028;
     }
 }
 
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_ps2(Dev d, FrameDev f, co
         if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
     }
     s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
-    ps2_fill_sel(s_sel, tid);
+    ps2_fill_sel(s_sel, tid, d.bgr);
     if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += blockDim.x) s_pow[i] = d.pow_tab[i];
     MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
     // Persistent CTAs: the tables above are staged once, then the CTA walks over tiles
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, Fr
         if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
     }
     s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
-    ps2_fill_sel(s_sel, tid);
+    ps2_fill_sel(s_sel, tid, d.bgr);
     if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += blockDim.x) s_pow[i] = d.pow_tab[i];
     MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
     int it = 0;
@@ -496,7 +497,8 @@ inline bool fused_ps2_pipe_supported(const Dev& d) {
     return (d.W & 7) == 0 && as >= -6 && as <= 6 && env_int("CRT_PIPE", 1) != 0;
 }
 
-inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
+#if defined(CRT_TU_PS2)      // launcher: compiled only in the translation unit that owns these kernels (build.py)
+inline int run_fused_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
                          cudaStream_t st, int* launches, bool pdl = false, const Ps2Maps* maps = nullptr) {
     dim3 grid((d.W + P2_TW - 1) / P2_TW, (d.H + P2_TH - 1) / P2_TH);
     const int ntiles = (int)(grid.x * grid.y);
@@ -505,39 +507,23 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
     // every CTA walks over several tiles
     static const int pipe_min_tiles = env_int("CRT_PIPE_MIN_TILES", 256);      // measured: wins at 720p (460 tiles, +1.5 %), 1080p (+15 %) and 4K, neutral at VGA (150)
     if (maps && (q_out || has_prev) && ntiles >= pipe_min_tiles) {
-        static int sms = 0;
-        static bool configured[64] = {};                         // the opt-in shared-memory size is a per-device attribute
         const bool thr = d.bloom_mode == 1 && d.thr_on;
         auto kern = !thr ? (d.bloom_mode == 1 ? (fast ? k_fused_ps2_pipe<true, true, false> : k_fused_ps2_pipe<true, false, false>)
                                               : (fast ? k_fused_ps2_pipe<false, true, false> : k_fused_ps2_pipe<false, false, false>))
                          : (fast ? k_fused_ps2_pipe<true, true, true> : k_fused_ps2_pipe<true, false, true>);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (!configured[dev & 63]) {
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaFuncSetAttribute(k_fused_ps2_pipe<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM);
-            cudaFuncSetAttribute(k_fused_ps2_pipe<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM);
-            cudaFuncSetAttribute(k_fused_ps2_pipe<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM);
-            cudaFuncSetAttribute(k_fused_ps2_pipe<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM);
-            cudaFuncSetAttribute(k_fused_ps2_pipe<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM);
-            cudaFuncSetAttribute(k_fused_ps2_pipe<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM);
-            configured[dev & 63] = true;
-        }
-        const int resident_pipe = sms * (thr ? 3 : 4);
+        // the opt-in shared-memory size is a per-device, per-kernel attribute: set once per context and kernel
+        if (env.raise((const void*)kern, P2_PIPE_SMEM) &&
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM) != cudaSuccess) return 2;
+        const int resident_pipe = env.sms * (thr ? 3 : 4);
         const cudaError_t e = launch_pdl(kern, dim3(ntiles < resident_pipe ? ntiles : resident_pipe), dim3(P2_NT), (size_t)P2_PIPE_SMEM, st, pdl,
                                          d, f, in, out, state, q_out, has_prev, maps->in, maps->st, maps->frame);
         ++*launches;
         return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
     }
-    static int resident = 0;                                     // CTAs the GPU holds at once: SMs x MINB (launch bounds)
     static const int minb = env_int("CRT_PS2_MINB", 4);
-    if (!resident) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        resident = sms * (minb == 3 ? 3 : 4) * env_int("CRT_PS2_WAVES", 1);
-        if (env_int("CRT_PS2_PERSIST", 1) == 0) resident = 1 << 30;
-    }
+    static const int waves = env_int("CRT_PS2_WAVES", 1);
+    static const bool persist = env_int("CRT_PS2_PERSIST", 1) != 0;
+    const int resident = persist ? env.sms * (minb == 3 ? 3 : 4) * waves : (1 << 30);      // CTAs the GPU holds at once: SMs x MINB (launch bounds)
     const dim3 pgrid(ntiles < resident ? ntiles : resident);       // persistent 1-D grid
     auto kern = d.bloom_mode == 1 ? (fast ? (minb == 3 ? k_fused_ps2<true, true, 3> : k_fused_ps2<true, true, 4>) : k_fused_ps2<true, false, 4>)
                                   : (fast ? k_fused_ps2<false, true, 4> : k_fused_ps2<false, false, 4>);
@@ -545,6 +531,8 @@ inline int run_fused_ps2(const Dev& d, const FrameDev& f, const uint8_t* in, uin
     ++*launches;
     return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
 }
+
+#endif  // CRT_TU_PS2
 
 #endif  // __CUDACC__
 

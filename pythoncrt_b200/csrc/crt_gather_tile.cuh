@@ -74,10 +74,12 @@ __global__ void __launch_bounds__(256) k_gather_tile(Dev d, FrameDev f, const fl
         sp[0] = make_float4(res[0], res[1], res[2], res[3]);
         sp[1] = make_float4(res[4], res[5], res[6], res[7]);
         sp[2] = make_float4(res[8], res[9], res[10], res[11]);
-        uint32_t* op = reinterpret_cast<uint32_t*>(out + ((size_t)y * d.W + xb) * 3);
-        op[0] = pack4(res[0], res[1], res[2], res[3]);
-        op[1] = pack4(res[4], res[5], res[6], res[7]);
-        op[2] = pack4(res[8], res[9], res[10], res[11]);
+        if (out) {
+            uint32_t* op = reinterpret_cast<uint32_t*>(out + ((size_t)y * d.W + xb) * 3);
+            op[0] = pack4(res[0], res[1], res[2], res[3]);
+            op[1] = pack4(res[4], res[5], res[6], res[7]);
+            op[2] = pack4(res[8], res[9], res[10], res[11]);
+        }
     }
     fence_proxy_async();                // the new state in shared memory -> visible to the TMA engine
     __syncthreads();
@@ -88,6 +90,7 @@ __global__ void __launch_bounds__(256) k_gather_tile(Dev d, FrameDev f, const fl
     }
 }
 
+#if defined(CRT_TU_FUSED)
 // map_st: float32 [H][W*3] tensor map of the state buffer with a 192 x 16 box, or null (plain k_gather)
 inline int run_gather_any(const Dev& d, const FrameDev& f, const float* qimg, uint8_t* out, float* state, int has_prev, cudaStream_t st,
                           int* launches, const CUtensorMap* map_st) {
@@ -98,6 +101,8 @@ inline int run_gather_any(const Dev& d, const FrameDev& f, const float* qimg, ui
     ++*launches;
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
+
+#endif  // CRT_TU_FUSED
 
 #endif  // __CUDACC__
 

@@ -107,6 +107,7 @@ struct Lerp1 { int32_t s0, s1; float w; };
 // ---- device-side parameter block ------------------------------------------------
 struct Dev {
     int W, H;
+    int bgr;                     // crt_params.channel_order == CRT_ORDER_BGR: channel index 0 is B, index 2 is R
     // stage 1-2: aberration + pixelate (crt_filter.py:571-584)
     int aberr;                   // aberration_px
     int aberr_mod;               // aberration_px mod W, in [0, W): lets the kernels wrap with one compare
@@ -272,7 +273,9 @@ CRT_HD float pow_unit(float x, float y, const float* __restrict__ T) {
 // apply_color_adjustments (:279-305), float32, numpy operation order.
 CRT_HD F3 colour(const Dev& d, F3 v, const float* __restrict__ pow_tab) {
     if (d.col_sat) {
-        float l = fadd(fadd(fmul(0.2126f, v.x), fmul(0.7152f, v.y)), fmul(0.0722f, v.z));
+        // Rec.709 luma in the reference's association ((wR R + wG G) + wB B), whichever index holds R
+        const float cr = d.bgr ? v.z : v.x, cb = d.bgr ? v.x : v.z;
+        float l = fadd(fadd(fmul(0.2126f, cr), fmul(0.7152f, v.y)), fmul(0.0722f, cb));
         v.x = sat(fadd(l, fmul(fsub(v.x, l), d.sat_f)));
         v.y = sat(fadd(l, fmul(fsub(v.y, l), d.sat_f)));
         v.z = sat(fadd(l, fmul(fsub(v.z, l), d.sat_f)));
@@ -300,9 +303,9 @@ CRT_HD F3 text_blend(const Dev& d, F3 v, int y, int x) {
     const uint8_t* t = d.text + ((size_t)y * d.W + x) * 4;
     float a = unit(t[3]);
     float ia = fsub(1.0f, a);
-    v.x = sat(fadd(fmul(v.x, ia), fmul(unit(t[0]), a)));
+    v.x = sat(fadd(fmul(v.x, ia), fmul(unit(t[d.bgr ? 2 : 0]), a)));      // the layer is RGBA
     v.y = sat(fadd(fmul(v.y, ia), fmul(unit(t[1]), a)));
-    v.z = sat(fadd(fmul(v.z, ia), fmul(unit(t[2]), a)));
+    v.z = sat(fadd(fmul(v.z, ia), fmul(unit(t[d.bgr ? 0 : 2]), a)));
     return v;
 }
 
@@ -376,14 +379,15 @@ CRT_HD int lut_index(float v) {           // (np.clip(v,0,1) * 1024).astype(int3
     return (int)fmul(sat(v), 1024.0f);    // [0, 1024] is a no-op: the product of a value in [0, 1] never exceeds 1024
 }
 CRT_HD F3 triad(const Dev& d, F3 v, int x, const float* __restrict__ fwd, const float* __restrict__ inv) {
-    const float* m = d.triad_cols + (size_t)x * 3;
-    float m0 = m[0], m1 = m[1], m2 = m[2];
+    const float* m = d.triad_cols + (size_t)x * 3;          // the table is in the reference's RGB order
+    float m0 = m[d.bgr ? 2 : 0], m1 = m[1], m2 = m[d.bgr ? 0 : 2];
     if (d.triad_mode == 1) return mk3(sat(fmul(v.x, m0)), sat(fmul(v.y, m1)), sat(fmul(v.z, m2)));
     float l0 = fwd[lut_index(v.x)], l1 = fwd[lut_index(v.y)], l2 = fwd[lut_index(v.z)];
     float o0 = fmul(l0, m0), o1 = fmul(l1, m1), o2 = fmul(l2, m2);
     if (d.triad_mode == 3) {
-        float before = fadd(fadd(fmul(0.2126f, l0), fmul(0.7152f, l1)), fmul(0.0722f, l2));
-        float after = fadd(fadd(fmul(0.2126f, o0), fmul(0.7152f, o1)), fmul(0.0722f, o2));
+        const float lr = d.bgr ? l2 : l0, lb = d.bgr ? l0 : l2, orr = d.bgr ? o2 : o0, ob = d.bgr ? o0 : o2;
+        float before = fadd(fadd(fmul(0.2126f, lr), fmul(0.7152f, l1)), fmul(0.0722f, lb));
+        float after = fadd(fadd(fmul(0.2126f, orr), fmul(0.7152f, o1)), fmul(0.0722f, ob));
         float ratio = clampf(fdiv(before, fmaxf(after, 1e-6f)), 0.5f, 2.0f);
         o0 = fmul(o0, ratio); o1 = fmul(o1, ratio); o2 = fmul(o2, ratio);
     }

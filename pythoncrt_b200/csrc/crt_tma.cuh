@@ -81,15 +81,14 @@ inline bool tma_encode(CUtensorMap* map, CUtensorMapDataType type, int rank, con
                        const uint64_t* strides_bytes, const uint32_t* box) {
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static encode_fn fn = nullptr;
-    static bool looked = false;
-    if (!looked) {
-        looked = true;
+    // resolved once, thread-safely (C++11 static initialisation): two contexts created from two threads both see it
+    static const encode_fn fn = []() -> encode_fn {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<encode_fn>(p);
-    }
+            return reinterpret_cast<encode_fn>(p);
+        return nullptr;
+    }();
     if (!fn) return false;
     cuuint64_t gd[5], gs[4];
     cuuint32_t bd[5], es[5];

@@ -1,0 +1,10 @@
+// crt_tu_ps2.cu — translation unit of the pixel_size-2 block kernels (fast bloom / no bloom), crt_fused_ps2.cuh
+#define CRT_TU_PS2
+#include "crt_fused_ps2.cuh"
+
+namespace crt {
+int launch_fused_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
+                     cudaStream_t st, int* launches, bool pdl, const Ps2Maps* maps) {
+    return run_fused_ps2(env, d, f, in, out, state, q_out, has_prev, st, launches, pdl, maps);
+}
+}  // namespace crt

@@ -74,7 +74,7 @@ class CrtEngine:
     # ----------------------------------------------------------- configure --
     def configure(self, params: CrtParams, *, variant: str = "export", triad_cols="auto", vignette="auto",
                   text_rgba: Optional[np.ndarray] = None, text_after: bool = True, noise_mode: str = "inject",
-                  glitch_mode: str = "inject", seed: int = 0, policy: str = "auto") -> "CrtEngine":
+                  glitch_mode: str = "inject", seed: int = 0, policy: str = "auto", channel_order: str = "rgb") -> "CrtEngine":
         """Upload parameters and host-built tables.
 
         triad_cols: "auto" builds the table from params.triad_strength/softness the
@@ -85,9 +85,12 @@ class CrtEngine:
             evaluated analytically on the device, anything else is uploaded; None = off.
         noise_mode / glitch_mode: "inject" = draws supplied per frame (the reference's
             own draws, for verification), "generate" = counter-based RNG on the device.
+        channel_order: "rgb" = channel index 0 is R, as the reference assumes (crt_filter.py:289,
+            :296-297, :573-575); "bgr" = frames (and state) are B,G,R: the R rules go to index 2.
         """
         c, tabs = build_config(params, self.width, self.height, variant=variant, triad_cols=triad_cols, vignette=vignette,
-                               text_rgba=text_rgba, text_after=text_after, noise_mode=noise_mode, glitch_mode=glitch_mode, seed=seed)
+                               text_rgba=text_rgba, text_after=text_after, noise_mode=noise_mode, glitch_mode=glitch_mode, seed=seed,
+                               channel_order=channel_order)
         for which, arr in tabs.items():
             self._table(which, arr)
         p = params
@@ -231,13 +234,17 @@ class CrtEngine:
         self._check(self.lib.crt_generate_noise(self.ctx, int(frame_index), plane.data_ptr(), C.c_void_p(stream)), "crt_generate_noise")
         return plane
 
-    def generate_glitch(self, frame_index: int):
+    def generate_glitch(self, frame_index: int = 0, phase_px: Optional[float] = None, fps: float = 30.0):
+        """Offsets [rows][segments] of the device glitch generator for one frame.  The pattern is keyed on the frame's
+        scanline phase exactly as the reference seeds its generator (crt_filter.py:670, :841); without `phase_px` the
+        phase of frame `frame_index` at `fps` is used (process_video's rule, :1043)."""
         torch = _torch()
         p = self.params
         y0, rows, seg_len, nseg = tables.glitch_geometry(self.variant, self.height, self.width, p.glitch_height_frac)
         offs = torch.empty((max(rows, 1), nseg), dtype=torch.int32, device=f"cuda:{self.device}")
         rec = cabi.CrtFrameC()
         rec.frame_index = int(frame_index)
+        rec.phase_px = float(phase_px) if phase_px is not None else p.phase_px(int(frame_index), fps)
         stream = torch.cuda.current_stream(offs.device).cuda_stream
         self._check(self.lib.crt_generate_glitch(self.ctx, C.byref(rec), offs.data_ptr(), C.c_void_p(stream)), "crt_generate_glitch")
         return offs

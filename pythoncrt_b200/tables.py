@@ -13,6 +13,7 @@ remember their parameters, so the device path never has to upload an H x W mask.
 """
 from __future__ import annotations
 
+import functools
 from typing import Optional, Tuple
 
 import numpy as np
@@ -77,7 +78,13 @@ def _row_blur_replicate(cols: np.ndarray, taps: np.ndarray) -> np.ndarray:
 # -------------------------------------------------------------- triad mask --
 def triad_columns(w: int, strength: float, softness_px: float = 0.0) -> np.ndarray:
     """Row 0 of the reference's triad mask as a [W][3] float32 table
-    (crt_filter.py:220-235; the mask is identical on every row)."""
+    (crt_filter.py:220-235; the mask is identical on every row).  Memoised: the GUI rebuilds the
+    mask on every preview tick (:1813) with unchanged arguments."""
+    return _triad_columns_cached(int(w), float(strength), float(softness_px)).copy()
+
+
+@functools.lru_cache(maxsize=16)
+def _triad_columns_cached(w: int, strength: float, softness_px: float) -> np.ndarray:
     col = np.arange(w)
     base = 1.0 - float(strength)
     cols = np.stack([(base + float(strength) * (col % 3 == c).astype(F32)) for c in range(3)], axis=1).astype(F32)
@@ -88,10 +95,27 @@ def triad_columns(w: int, strength: float, softness_px: float = 0.0) -> np.ndarr
     return np.ascontiguousarray(cols, dtype=F32)
 
 
-class TriadMask(np.ndarray):
+class _MadeMask(np.ndarray):
+    """ndarray that remembers the parameters it was built from.  The memory survives only on exact views of the
+    whole mask (same shape, dtype and values); anything derived — `mask * 0.5`, `mask.astype(...)`, a slice —
+    forgets them (None), so that such an array is inspected numerically / uploaded as a plane instead of being
+    taken for the mask it came from."""
+    _REMEMBER = ()
+
+    def __array_finalize__(self, obj):
+        for name in self._REMEMBER:
+            setattr(self, name, None)
+
+    def __array_wrap__(self, out, context=None, return_scalar=False):       # ufunc results are plain arrays
+        out = np.asarray(out)
+        return out[()] if return_scalar else out
+
+
+class TriadMask(_MadeMask):
     """H x W x 3 float32 mask (a broadcast view of one row) that remembers how it was made."""
-    strength: float = 0.0
-    softness: float = 0.0
+    _REMEMBER = ("strength", "softness")
+    strength: Optional[float] = None
+    softness: Optional[float] = None
 
 
 def make_triad_mask(h: int, w: int, strength: float, softness_px: float = 0.0) -> np.ndarray:
@@ -111,9 +135,10 @@ def triad_luts(gamma: float) -> Tuple[np.ndarray, np.ndarray]:
 
 
 # ---------------------------------------------------------------- vignette --
-class VignetteMask(np.ndarray):
+class VignetteMask(_MadeMask):
     """H x W float64 vignette (crt_filter.py:266-276) that remembers its strength."""
-    strength: float = 0.0
+    _REMEMBER = ("strength",)
+    strength: Optional[float] = None
 
 
 def make_vignette(h: int, w: int, strength: float) -> np.ndarray:
@@ -124,6 +149,27 @@ def make_vignette(h: int, w: int, strength: float) -> np.ndarray:
     v = (1.0 - strength * np.clip(nx * nx + ny * ny, 0.0, 1.0)).view(VignetteMask)
     v.strength = float(strength)
     return v
+
+
+class LazyVignette:
+    """make_vignette for callers that rebuild the mask on every preview tick (the GUI does, crt_filter.py:1821): carries
+    (h, w, strength) and builds the H x W float64 array only if somebody asks for it (np.asarray).  The device path never
+    does: it evaluates the vignette analytically from the strength (crt_params.vignette_on = 1)."""
+
+    def __init__(self, h: int, w: int, strength: float):
+        self.shape, self.strength, self.dtype, self.ndim = (int(h), int(w)), float(strength), np.dtype(np.float64), 2
+
+    def __array__(self, dtype=None, copy=None):
+        a = np.asarray(make_vignette(self.shape[0], self.shape[1], self.strength))
+        return a.astype(dtype) if dtype is not None else a
+
+    def __getitem__(self, idx):
+        return np.asarray(self)[idx]
+
+
+def make_vignette_lazy(h: int, w: int, strength: float) -> LazyVignette:
+    """Drop-in for make_vignette (crt_filter.py:266-276) without the per-tick H x W host array."""
+    return LazyVignette(h, w, strength)
 
 
 def infer_vignette_strength(mask: np.ndarray) -> Optional[float]:
@@ -139,12 +185,15 @@ def infer_vignette_strength(mask: np.ndarray) -> Optional[float]:
     if r2 <= 0:
         return None
     s = (1.0 - float(mask[0, 0])) / r2
+    if np.asarray(mask).dtype != np.float64:
+        s = float(np.round(s, 6))
     ys = np.array([0, h // 3, h // 2, h - 1, h // 5])
     xs = np.array([0, w // 2, w // 3, w - 1, (4 * w) // 5])
     nx = (xs - (w - 1) / 2.0) / max(1.0, w / 2.0)
     ny = (ys - (h - 1) / 2.0) / max(1.0, h / 2.0)
     want = 1.0 - s * np.clip(nx * nx + ny * ny, 0.0, 1.0)
-    if np.allclose(np.asarray(mask)[ys, xs], want, rtol=0, atol=1e-12):
+    atol = 1e-12 if np.asarray(mask).dtype == np.float64 else 2e-7          # a float32 copy of the mask is still that mask
+    if np.allclose(np.asarray(mask)[ys, xs], want, rtol=0, atol=atol):
         return float(s)
     return None
 

@@ -51,15 +51,16 @@ def oracle_to_product_params(p) -> CrtParams:
     return CrtParams(**{k: v for k, v in vars(p).items() if k in names})
 
 
-def run_case(case, variant: str, static: bool = False):
-    """Run an oracle Case through the host build of the kernel arithmetic."""
+def run_case(case, variant: str, static: bool = False, channel_order: str = "rgb"):
+    """Run an oracle Case through the host build of the kernel arithmetic.  With channel_order="bgr" the
+    frames are fed channel-swapped and the results swapped back (must equal the "rgb" run exactly)."""
     from oracle import harness
     from oracle.cases import case_frames, case_text_layer
     L = lib()
     p = oracle_to_product_params(case.params)
     H, W = case.h, case.w
     text = case_text_layer(case)
-    c, tabs = build_config(p, W, H, variant=variant, text_rgba=text, text_after=(case.text != "before"))
+    c, tabs = build_config(p, W, H, variant=variant, text_rgba=text, text_after=(case.text != "before"), channel_order=channel_order)
     assert L.emu_sizeof_params() == C.sizeof(cabi.CrtParamsC) and L.emu_sizeof_frame() == C.sizeof(cabi.CrtFrameC)
     ptrs = (C.c_void_p * 8)()
     sizes = (C.c_size_t * 8)()
@@ -67,6 +68,8 @@ def run_case(case, variant: str, static: bool = False):
         ptrs[k] = a.ctypes.data
         sizes[k] = a.nbytes
     frames = np.ascontiguousarray(np.stack(case_frames(case)))
+    if channel_order == "bgr":
+        frames = np.ascontiguousarray(frames[..., ::-1])
     n = frames.shape[0]
     planes = harness.noise_planes(case)
     recs = (cabi.CrtFrameC * n)()
@@ -93,6 +96,9 @@ def run_case(case, variant: str, static: bool = False):
                        recs, n, err, 512)
     if rc != 0:
         raise RuntimeError(f"emu_process failed ({rc}): {err.value.decode()}")
+    if channel_order == "bgr":
+        out, state = np.ascontiguousarray(out[..., ::-1]), np.ascontiguousarray(state[..., ::-1])
+        img = None if img is None else np.ascontiguousarray(img[..., ::-1])
     return (img if static else list(out)), state
 
 

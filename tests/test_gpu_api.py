@@ -42,18 +42,26 @@ def test_apply_crt_effect_drop_in(name):
     assert state.shape == (case.h, case.w, 3) and np.asarray(state).dtype == np.float32
 
 
-def test_apply_static_effects_drop_in():
+@pytest.mark.parametrize("name", ["cfg3_warp", "cfg1_cli_default", "cfg2_gauss_grade", "glitch_big", "text_after_warp", "odd_size_gauss", "gauss_k61"])
+def test_apply_static_effects_drop_in(name):
+    """apply_static_effects (:702-861) = crt_process_static; every kernel family (block kernels through q_out, two-pass
+    with the gather writing the float image, general tile kernels, staged fallback) against the oracle's float image."""
     import pythoncrt_b200 as crt
-    case = CASES_BY_NAME["cfg3_warp"]
+    from oracle.cases import case_text_layer
+    case = CASES_BY_NAME[name]
     p = case.params
     tri = crt.make_triad_mask(case.h, case.w, p.triad_strength, p.triad_softness)
     vig = crt.make_vignette(case.h, case.w, p.vignette_strength)
     frame = case_frames(case)[0]
     phase, tsec = harness.frame_scalars(case, 0)
+    text = case_text_layer(case)
     img = crt.apply_static_effects(frame, *_args(p, tri, vig, phase), p.scanline_period_px, phase, p.fast_bloom, int(p.pixel_size),
-                                   0, 0.0, **_kw(p, tsec))
-    ref = O.static_chain(frame, p, phase_px=phase, time_sec=tsec, variant="export")
-    assert img.dtype == np.float32 and np.max(np.abs(ref - img)) < 4e-6
+                                   int(p.glitch_amp_px), float(p.glitch_height_frac), text_overlay_rgba=text,
+                                   text_overlay_after=(case.text != "before"), **_kw(p, tsec))
+    ref = O.static_chain(frame, p, phase_px=phase, time_sec=tsec, variant="export", text_rgba=text, text_after=(case.text != "before"))
+    d = np.abs(ref - img)
+    # float32 against the reference's float64 tail; a sample may sit on the other side of a LUT bin after the colour gamma
+    assert img.dtype == np.float32 and d.max() < 1.0 / 255 and (d > 4e-6).mean() < 2e-3, (d.max(), (d > 4e-6).mean())
 
 
 def test_host_buffer_path_equals_device_path():

@@ -1,0 +1,336 @@
+"""Boundary behaviour on the B200 beyond per-case parity: channel order, thread safety of the C ABI,
+distribution of the device generators against the reference's own draws, long persistence halos,
+and the patched export pipeline (effects.install) end to end."""
+import threading
+import types
+
+import numpy as np
+import pytest
+
+from gpu_util import run_case_gpu
+from oracle import crt_oracle as O
+from oracle import harness
+from oracle.cases import BASE, CASES_BY_NAME, GAUSS, GRADE, LIVE, WARP, Case, case_frames
+
+pytestmark = pytest.mark.gpu
+
+
+# ----------------------------------------------------------------------------------------- channel order --
+@pytest.mark.parametrize("name", ["cfg1_cli_default", "cfg2_gauss_grade", "cfg4_full", "cfg1_gui_default", "text_after_warp", "odd_size"])
+def test_bgr_frames_equal_swapped_rgb(name):
+    """crt_params.channel_order = BGR: same bytes as the RGB run on the channel-swapped clip, swapped back
+    (the reference's index rules :289, :296-297, :573-575 follow the colour, not the index)."""
+    import torch
+    from pythoncrt_b200.engine import CrtEngine
+    import host_emu
+    from oracle.cases import case_text_layer
+    case = CASES_BY_NAME[name]
+    p = host_emu.oracle_to_product_params(case.params)
+    frames = torch.from_numpy(np.ascontiguousarray(np.stack(case_frames(case)))).cuda()
+    planes = harness.noise_planes(case)
+    nz = None if planes is None else torch.from_numpy(np.stack(planes)).cuda()
+    sc = [harness.frame_scalars(case, j) for j in range(case.frames)]
+    kw = dict(phases=[s[0] for s in sc], times=[s[1] for s in sc], first_index=case.first_index, noise_planes=nz)
+    outs = {}
+    for order in ("rgb", "bgr"):
+        eng = CrtEngine(case.w, case.h).configure(p, variant="export", text_rgba=case_text_layer(case), text_after=(case.text != "before"),
+                                                  channel_order=order)
+        src = frames if order == "rgb" else frames.flip(-1).contiguous()
+        out, state = eng.process(src, **kw)
+        outs[order] = (out if order == "rgb" else out.flip(-1), state if order == "rgb" else state.flip(-1))
+        eng.close()
+    assert torch.equal(outs["rgb"][0], outs["bgr"][0]) and torch.equal(outs["rgb"][1], outs["bgr"][1])
+
+
+# ----------------------------------------------------------------------------------------- thread safety --
+def test_two_threads_two_contexts_match_the_serial_run():
+    """The reference calls the chain from two pool threads (crt_filter.py:1015-1017); one context per thread.  Two
+    engines with DIFFERENT parameter sets (different kernels, different shared-memory opt-ins) process their clips
+    concurrently, several times over; every output must equal the same engine's single-threaded result."""
+    import torch
+    from pythoncrt_b200.engine import CrtEngine
+    import host_emu
+    jobs = [("cfg2_gauss_grade", 1080, 1920), ("cfg3_warp", 720, 1280), ("cfg1_cli_default", 1080, 1920), ("cfg4_full_fastbloom", 480, 640)]
+    clips, want, params = [], [], []
+    for k, (name, h, w) in enumerate(jobs):
+        p = host_emu.oracle_to_product_params(CASES_BY_NAME[name].params).but(noise_strength=0.0, glitch_amp_px=0)
+        g = torch.Generator(device="cuda").manual_seed(50 + k)
+        fr = torch.randint(0, 256, (6, h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+        eng = CrtEngine(w, h).configure(p)
+        out, _ = eng.process(fr, fps=30.0)
+        torch.cuda.synchronize()
+        eng.close()
+        clips.append(fr); want.append(out.clone()); params.append(p)
+    errors = []
+
+    def worker(k):
+        try:
+            name, h, w = jobs[k]
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for rep in range(4):
+                    eng = CrtEngine(w, h).configure(params[k])          # fresh context: first-use configuration races are exercised
+                    out, _ = eng.process(clips[k], fps=30.0)
+                    stream.synchronize()
+                    if not torch.equal(out, want[k]):
+                        errors.append((name, rep, int((out != want[k]).sum())))
+                    eng.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((jobs[k][0], repr(e)))
+
+    for pair in ((0, 1), (2, 3), (0, 2)):
+        ts = [threading.Thread(target=worker, args=(k,)) for k in pair]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    assert not errors, errors
+
+
+def test_drop_in_noise_differs_between_frames_of_two_workers():
+    """after install(), frames handled by the two export workers must not share their grain."""
+    import pythoncrt_b200 as crt
+    case = CASES_BY_NAME["noise_grain1"]
+    p = case.params
+    frame = np.full((case.h, case.w, 3), 128, np.uint8)
+    tri = crt.make_triad_mask(case.h, case.w, p.triad_strength, p.triad_softness)
+    vig = crt.make_vignette(case.h, case.w, p.vignette_strength)
+    imgs = {}
+
+    def worker(start):
+        for i in range(start, 6, 2):
+            t = i / 30.0
+            imgs[i] = crt.apply_static_effects(frame, p.scanline_strength, tri, float(p.triad_gamma), False, 1, p.bloom_sigma, p.bloom_strength,
+                                               0.0, p.noise_strength, vig, p.scanline_period_px, t * 30.0, True, 2, 0, 0.0, time_sec=t)
+    ts = [threading.Thread(target=worker, args=(s,)) for s in (0, 1)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    flat = [imgs[i] for i in range(6)]
+    for a in range(6):
+        for b in range(a + 1, 6):
+            assert not np.array_equal(flat[a], flat[b]), (a, b)
+
+
+# ----------------------------------------------------------------------------- generators vs the reference --
+def _ks(a, b):
+    from scipy import stats
+    return stats.ks_2samp(np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel())
+
+
+def test_generated_noise_has_the_distribution_of_cv2_randn():
+    """noise_mode = generate (what bench.py times) against the reference's own generator (cv2.randn, :641): two-sample
+    Kolmogorov-Smirnov on 2 x 300k draws, moments, tail mass, and independence across frames and cells."""
+    import cv2
+    import torch
+    from pythoncrt_b200 import CrtEngine, CrtParams
+    h, w = 480, 640
+    eng = CrtEngine(w, h).configure(CrtParams(noise_strength=2.0, grain_size=1), noise_mode="generate", seed=77)
+    a = eng.generate_noise(5).cpu().numpy().ravel()
+    b = eng.generate_noise(6).cpu().numpy().ravel()
+    ref = np.empty((h, w), np.float32)
+    cv2.setRNGSeed(123)
+    cv2.randn(ref, 0.0, 1.0)
+    ks = _ks(a, ref)
+    assert ks.pvalue > 1e-3, ks
+    for x in (a, b):
+        assert abs(x.mean()) < 6e-3 and abs(x.std() - 1.0) < 6e-3
+        assert abs(float((x ** 3).mean())) < 0.03 and abs(float((x ** 4).mean()) - 3.0) < 0.08        # skewness 0, kurtosis 3
+        assert abs(float((np.abs(x) > 3.0).mean()) - 0.0027) < 6e-4                                      # tail mass of N(0,1)
+    assert abs(float(np.corrcoef(a, b)[0, 1])) < 6e-3                       # frames independent
+    assert abs(float(np.corrcoef(a[:-1], a[1:])[0, 1])) < 6e-3              # neighbouring cells independent
+    assert np.array_equal(a, eng.generate_noise(5).cpu().numpy().ravel())   # counter-based: same (seed, frame) -> same plane
+
+
+@pytest.mark.parametrize("variant", ["gui", "export"])
+def test_generated_glitch_has_the_distribution_of_the_reference_draws(variant):
+    """glitch_mode = generate against numpy PCG64 draws made exactly as the reference makes them (:672-679, :845-853;
+    tables.glitch_offsets is bit-identical to the reference, test_host_logic): per row band, the offsets of 48 patterns
+    from each generator must come from the same distribution (KS), with the same mean magnitude."""
+    from pythoncrt_b200 import CrtEngine, CrtParams, tables
+    h, w, amp, frac = 480, 640, 48, 0.5
+    eng = CrtEngine(w, h).configure(CrtParams(glitch_amp_px=amp, glitch_height_frac=frac, noise_strength=0.0), variant=variant,
+                                    glitch_mode="generate", seed=9)
+    k = 0.05 if variant == "gui" else 2.0
+    phases = [(j * 3 + 1) / k for j in range(48)]          # 48 distinct reference seeds
+    gen = np.stack([eng.generate_glitch(phase_px=ph).cpu().numpy() for ph in phases]).astype(np.float64)
+    ref = np.stack([tables.glitch_offsets(variant, h, w, amp, frac, ph) for ph in phases]).astype(np.float64)
+    assert gen.shape == ref.shape
+    rows = gen.shape[1]
+    for lo, hi in ((0, rows // 4), (rows // 4, rows // 2), (rows // 2, rows)):       # the amplitude decays down the band
+        ks = _ks(gen[:, lo:hi], ref[:, lo:hi])
+        assert ks.pvalue > 1e-3, (variant, lo, hi, ks)
+        ma, mb = np.abs(gen[:, lo:hi]).mean(), np.abs(ref[:, lo:hi]).mean()
+        assert abs(ma - mb) <= 0.08 * max(mb, 0.5), (variant, lo, hi, ma, mb)
+    assert np.abs(gen).max() <= amp * (1.0 if variant == "gui" else 4.0)
+
+
+def test_generated_glitch_is_keyed_like_the_reference():
+    """Temporal coherence: the reference reseeds on int(|phase| * k) (+ geometry) — the GUI holds a pattern for 20 phase-px
+    (:670), the export for half a pixel (:841).  The device generator uses the same key."""
+    import torch
+    from pythoncrt_b200 import CrtEngine, CrtParams
+    for variant, same, other in (("gui", (40.0, 59.9), 60.0), ("export", (3.0, 3.49), 3.5)):
+        eng = CrtEngine(640, 480).configure(CrtParams(glitch_amp_px=32, glitch_height_frac=0.5), variant=variant, glitch_mode="generate", seed=1)
+        a, b, c = (eng.generate_glitch(phase_px=ph) for ph in (same[0], same[1], other))
+        assert torch.equal(a, b) and not torch.equal(a, c), variant
+        assert torch.equal(a, eng.generate_glitch(phase_px=-same[0]))      # |phase|
+        eng.close()
+
+
+# ------------------------------------------------------------------------------------- long persistence halo --
+def test_temporal_shards_with_persistence_095():
+    """SURVEY.md §8e at the CLI's maximum persistence: 149 warm-up frames (0.95^149 <= 1/2040).  Two shards of a
+    400-frame clip against the serial run."""
+    import torch
+    from pythoncrt_b200 import CrtEngine, CrtParams, clip
+    h, w, n = 96, 160, 400
+    p = CrtParams(noise_strength=0.0, persistence=0.95)
+    assert clip.halo_frames(p.persistence) == 149
+    eng = CrtEngine(w, h).configure(p)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    frames = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+    # slowly varying content: persistence 0.95 of white noise is a grey field, a drifting ramp is the harder case
+    ramp = (torch.arange(n, device="cuda").view(n, 1, 1, 1) * 2 + torch.arange(w, device="cuda").view(1, 1, w, 1)) % 256
+    frames = ((frames.to(torch.int32) // 4 + ramp.to(torch.int32)) % 256).to(torch.uint8).contiguous()
+    serial, _ = clip.process_clip(eng, frames, fps=30.0)
+    for rank in range(2):
+        def run_range(first, last, fresh):
+            out, _ = clip.process_clip(eng, frames[first:last], fps=30.0, first_index=first)
+            return out
+        mine, (a, b) = clip.process_clip_sharded(run_range, n, p, rank, 2)
+        warm, _, _ = clip.shard_plan(n, rank, 2, p.persistence)
+        assert (rank == 0 and warm == 0) or a - warm == 149
+        d = (mine.to(torch.int16) - serial[a:b].to(torch.int16)).abs()
+        assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 2e-3, (rank, int(d.max()), float((d > 0).float().mean()))
+    # a halo that is too short is visibly wrong: the test above is not vacuous
+    short, _ = clip.process_clip(eng, frames[200 - 10:260], fps=30.0, first_index=190)
+    assert int((short[10:].to(torch.int16) - serial[200:260].to(torch.int16)).abs().max()) > 1
+
+
+# ------------------------------------------------------------------------ patched export pipeline end to end --
+_DRAIN_SRC = '''
+def export_like(frames, fps, speed, persistence, chain_args, chain_kw, workers=2):
+    """The frame loop of process_video (crt_filter.py:1015-1131) without decode / encode: 2-worker pool running
+    apply_static_effects, ordered drain with the persistence blend (:1092) and convertScaleAbs (:1098)."""
+    from concurrent.futures import ThreadPoolExecutor
+    outs, futures, next_write, prev_state = [], {}, 0, None
+    def drain_one():
+        nonlocal next_write, prev_state
+        static_img = futures.pop(next_write).result()
+        if prev_state is not None and persistence > 0.0:
+            blended = np.clip(persistence * prev_state + (1.0 - persistence) * static_img, 0.0, 1.0)
+        else:
+            blended = static_img
+        prev_state = blended
+        outs.append(cv2.convertScaleAbs(blended, alpha=255.0, beta=0))
+        next_write += 1
+    with ThreadPoolExecutor(max_workers=workers) as executor:
+        for i, frame in enumerate(frames):
+            a = list(chain_args)
+            a[11] = (i / float(fps)) * speed
+            futures[i] = executor.submit(apply_static_effects, frame, *a, time_sec=(i / float(fps)), **chain_kw)
+            while len(futures) >= workers * 4 or next_write in futures:
+                if next_write in futures:
+                    drain_one()
+                else:
+                    break
+        while next_write in futures:
+            drain_one()
+    return outs
+'''
+
+
+@pytest.mark.parametrize("name,persistence", [("cfg1_cli_default", 0.2), ("cfg4_full", 0.35), ("cfg3_warp", 0.0)])
+def test_install_runs_the_export_drain_on_the_device(name, persistence):
+    """effects.install on a stand-in module whose frame loop restates process_video's: the patched pipeline must give the
+    oracle's export frames (+-1 LSB), identical bytes to the device-resident engine path, and move exactly 3 bytes per
+    pixel each way per frame (no float image crosses the host link)."""
+    import cv2
+    import pythoncrt_b200 as crt
+    from pythoncrt_b200 import effects
+    case = CASES_BY_NAME[name]
+    p = case.params.but(persistence=persistence, noise_strength=0.0)
+    case = Case(case.name, case.h, case.w, p, frames=7, fps=case.fps, source=case.source)
+    mod = types.ModuleType("crt_filter_standin")
+    mod.np, mod.cv2 = np, cv2
+    mod.apply_static_effects = lambda *a, **k: (_ for _ in ()).throw(AssertionError("not patched"))
+    exec(_DRAIN_SRC, mod.__dict__)
+    effects.install(mod)
+    tri = mod.make_triad_mask(case.h, case.w, p.triad_strength, p.triad_softness)
+    vig = mod.make_vignette(case.h, case.w, p.vignette_strength)
+    args = (p.scanline_strength, tri, float(p.triad_gamma), bool(p.triad_preserve_luma), int(p.aberration_px), p.bloom_sigma, p.bloom_strength,
+            float(p.bloom_threshold), p.noise_strength, vig, p.scanline_period_px, 0.0, p.fast_bloom, int(p.pixel_size), int(p.glitch_amp_px),
+            float(p.glitch_height_frac))
+    kw = dict(brightness=p.brightness, contrast=p.contrast, gamma=p.gamma, saturation=p.saturation, temperature=p.temperature,
+              flicker_strength=p.flicker_strength, flicker_hz=p.flicker_hz, grain_size=p.grain_size, scanline_angle=p.scanline_angle,
+              scanline_thickness=p.scanline_thickness, warp_strength=p.warp_strength)
+    frames = case_frames(case)
+    before = dict(effects.TRANSFER_LOG)
+    outs = mod.export_like(frames, case.fps, p.scanline_speed_px_s, p.persistence, args, kw)
+    moved = {k: effects.TRANSFER_LOG[k] - before[k] for k in before}
+    fbytes = case.h * case.w * 3
+    assert moved == {"h2d_bytes": 7 * fbytes, "d2h_bytes": 7 * fbytes, "frames": 7}, moved
+    want, _ = harness.run_oracle(case, "export")
+    for a, b in zip(want, outs):
+        st = harness.diff_stats(a, b)
+        assert b.dtype == np.uint8 and st["max"] <= 1 and st["psnr"] >= 50, st
+    got, _, _ = run_case_gpu(case, "export")
+    assert all(np.array_equal(a, b) for a, b in zip(got, outs))
+
+
+def test_export_frame_still_converts_to_the_float_image():
+    """An ExportFrame handed to any other consumer behaves like apply_static_effects' return value (:861)."""
+    import pythoncrt_b200 as crt
+    from pythoncrt_b200 import effects
+    case = CASES_BY_NAME["cfg3_warp"]
+    p = case.params
+    tri = crt.make_triad_mask(case.h, case.w, p.triad_strength, p.triad_softness)
+    vig = crt.make_vignette(case.h, case.w, p.vignette_strength)
+    frame = case_frames(case)[0]
+    phase, tsec = harness.frame_scalars(case, 0)
+    a = (frame, p.scanline_strength, tri, float(p.triad_gamma), False, int(p.aberration_px), p.bloom_sigma, p.bloom_strength, 0.0,
+         p.noise_strength, vig, p.scanline_period_px, phase, p.fast_bloom, int(p.pixel_size), 0, 0.0)
+    kw = dict(time_sec=tsec, scanline_angle=p.scanline_angle, scanline_thickness=p.scanline_thickness, warp_strength=p.warp_strength)
+    lazy = effects.apply_static_effects_lazy(*a, **kw)
+    img = np.asarray(lazy)
+    ref = O.static_chain(frame, p, phase_px=phase, time_sec=tsec, variant="export")
+    assert img.dtype == np.float32 and img.shape == ref.shape and np.max(np.abs(ref - img)) < 4e-6
+    assert np.array_equal(img, crt.apply_static_effects(*a, **kw))
+
+
+def test_stale_state_is_resized_like_the_reference():
+    """State of another frame size: the GUI chain resizes it with cv2.resize INTER_LINEAR (:689-690), the export drain
+    through uint8 and PIL bilinear (:1088-1091)."""
+    import cv2
+    from PIL import Image
+    import pythoncrt_b200 as crt
+    from pythoncrt_b200 import effects
+    case = CASES_BY_NAME["cfg1_cli_default"]
+    p = case.params
+    h, w = case.h, case.w
+    frame = case_frames(case)[0]
+    rng = np.random.default_rng(4)
+    small = rng.random((h // 2, w // 2 + 8, 3)).astype(np.float32)
+    tri = crt.make_triad_mask(h, w, p.triad_strength, p.triad_softness)
+    vig = crt.make_vignette(h, w, p.vignette_strength)
+    args = (p.scanline_strength, tri, float(p.triad_gamma), False, 1, p.bloom_sigma, p.bloom_strength, 0.0, 0.0, vig)
+    # GUI: oracle fed the state resized the reference's way
+    out, state = crt.apply_crt_effect(frame, *args, 0.5, small, p.scanline_period_px, 7.0, True, 2)
+    want, _ = O.frame_step(frame, p.but(persistence=0.5), cv2.resize(small, (w, h), interpolation=cv2.INTER_LINEAR), phase_px=7.0, time_sec=0.0,
+                           variant="gui")
+    assert harness.diff_stats(want, out)["max"] <= 1
+    # export drain: blend against a foreign float state of another size
+    cur = effects.apply_static_effects_lazy(frame, *args, p.scanline_period_px, 7.0, True, 2, 0, 0.0)
+    blended = np.clip(0.5 * _Foreign(small) + (1.0 - 0.5) * cur, 0.0, 1.0)
+    got = blended.quantised()
+    prev = np.asarray(Image.fromarray(np.clip(small * 255.0, 0, 255).astype(np.uint8)).resize((w, h), Image.BILINEAR)).astype(np.float32) / 255.0
+    img = O.static_chain(frame, p, phase_px=7.0, time_sec=0.0, variant="export")
+    want = cv2.convertScaleAbs(np.clip(0.5 * prev + 0.5 * img, 0.0, 1.0), alpha=255.0, beta=0)
+    assert harness.diff_stats(want, got)["max"] <= 1
+
+
+class _Foreign:
+    """A float state that did not come from this library (e.g. kept by the caller across an install())."""
+    def __init__(self, arr):
+        self.arr, self.shape, self.state = arr, arr.shape, None
+
+    def __rmul__(self, k):
+        from pythoncrt_b200 import effects
+        return effects._Scaled(self.arr, k)

@@ -18,6 +18,9 @@ FULL = [
     Case("full_default_4k_thr", 2160, 3840, BASE.but(bloom_threshold=0.5, flicker_strength=0.3, flicker_hz=50.0), frames=3, source="structured"),
     Case("full_cfg3_4k", 2160, 3840, BASE.but(**WARP), frames=2),
     Case("full_cfg4_4k", 2160, 3840, BASE.but(**GAUSS, **GRADE, **WARP, **LIVE), frames=2, fps=60.0, first_index=100),
+    # BASELINE configs[4] at its real size: K = 25 taps at 7680 x 4320 (tile counts, the < 2^31 offset check of plan_fused,
+    # the 398 MB pre-warp scratch of the two-pass path).  One frame: the CPU path needs ~20 s for it.
+    Case("full_cfg5_8k", 4320, 7680, BASE.but(**GRADE, **WARP, **LIVE, fast_bloom=False, bloom_sigma=4.0, bloom_strength=0.3), frames=1, first_index=3),
 ]
 
 
@@ -29,7 +32,7 @@ def test_full_size_matches_oracle(case):
     for a, b in zip(want, got):
         st = harness.diff_stats(a, b)
         log_report(case=case.name, what=f"fullsize/fused={fused}", **st)
-        assert st["psnr"] >= 50.0 and st["frac_gt1"] <= (1e-6 if case.params.gamma != 1.0 else 0.0), st
+        assert st["psnr"] >= 50.0 and st["max"] <= 1, st
 
 
 def test_identity_4k_bit_exact():

@@ -61,10 +61,7 @@ def test_random_parameters_match_oracle(i):
                  "frac_ne": max(worst["frac_ne"], st["frac_ne"]), "psnr": min(worst["psnr"], st["psnr"])}
     log_report(case=case.name, what=f"{variant}/auto/fused={fused}", w=case.w, h=case.h, **worst)
     assert worst["psnr"] >= 50.0, (worst, vars(case.params))
-    if case.params.gamma != 1.0:
-        assert worst["frac_gt1"] <= 1e-4, (worst, vars(case.params))     # a handful of samples at these frame sizes
-    else:
-        assert worst["max"] <= 1, (worst, vars(case.params))
+    assert worst["max"] <= 1, (worst, vars(case.params))
     assert worst["frac_ne"] <= 5e-3, (worst, vars(case.params))
     d = np.abs(want_state.astype(np.float64) - state)
     assert d.max() < 1.0 / 255 and (d > 4e-6).mean() < 4e-3, (d.max(), (d > 4e-6).mean())

@@ -1,11 +1,11 @@
 """Parity of the CUDA path (through the C ABI) against the oracle, on the B200.
 
 Bar (north_star): within +-1 LSB per uint8 channel and PSNR >= 50 dB, with the
-RNG-driven stages fed the reference's own draws.  Cases that run colour gamma
-(numpy's float32 `power` is SVML: within 1 ulp, not correctly rounded, and not
-reproducible by any other implementation) may flip a triad LUT bin on an
-isolated dark sample; for those the fraction of samples off by more than 1 LSB
-is bounded instead (parity section)."""
+RNG-driven stages fed the reference's own draws.  Asserted as max |delta| <= 1
+for EVERY case, colour gamma included: numpy's float32 `power` (SVML, within
+1 ulp, not correctly rounded) cannot be matched bit for bit, and a 1-ulp
+difference could in principle flip a triad LUT bin on a dark sample, but no
+committed seed does (profiles/r01/parity_*.jsonl, profiles/r02)."""
 import numpy as np
 import pytest
 
@@ -24,10 +24,7 @@ def _check(case, want, got, what):
                  "frac_ne": max(worst["frac_ne"], st["frac_ne"]), "psnr": min(worst["psnr"], st["psnr"])}
     log_report(case=case.name, what=what, **worst)
     assert worst["psnr"] >= 50.0, worst
-    if case.params.gamma != 1.0:
-        assert worst["frac_gt1"] <= 3e-5, worst
-    else:
-        assert worst["max"] <= 1, worst
+    assert worst["max"] <= 1, worst
     assert worst["frac_ne"] <= 5e-3, worst
 
 
@@ -44,7 +41,7 @@ def test_cuda_matches_oracle(case, variant, policy, golden):
     assert d.max() < 1.0 / 255 and (d > 4e-6).mean() < 2e-3, (d.max(), (d > 4e-6).mean())
     # and against the fixture made from the unmodified reference
     st = harness.diff_stats(golden["last_frame"](case.name, variant), got[-1])
-    assert st["psnr"] >= 50.0 and (st["max"] <= 1 or (case.params.gamma != 1.0 and st["frac_gt1"] <= 3e-5)), st
+    assert st["psnr"] >= 50.0 and st["max"] <= 1, st
 
 
 def test_identity_chain_is_exact():

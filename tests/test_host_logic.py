@@ -203,3 +203,101 @@ def test_rawvideo_streaming_chunks_and_short_read():
     assert eng.calls == [(3, 10, 24.0), (3, 13, 24.0), (1, 16, 24.0)]
     want = (255 - np.frombuffer(data[:7 * fb], np.uint8)).tobytes()
     assert dst.getvalue() == want
+
+
+# ------------------------------------------------- round-2 host logic (ADVICE.md / VERDICT.md items) --
+def test_derived_masks_forget_their_parameters():
+    """A mask derived from make_vignette / make_triad_mask (astype, scaling, slicing) must not be taken for the
+    mask it came from: its remembered strength is dropped and the array is inspected numerically instead."""
+    v = tables.make_vignette(48, 64, 0.4)
+    assert v.strength == 0.4 and tables.infer_vignette_strength(v) == 0.4
+    f32 = v.astype(np.float32)
+    assert getattr(f32, "strength", None) is None and tables.infer_vignette_strength(f32) == 0.4      # still that mask, numerically
+    half = v * 0.5
+    assert getattr(half, "strength", None) is None and tables.infer_vignette_strength(half) is None   # not of the form 1 - s r^2
+    assert getattr(v[4:], "strength", None) is None
+    c, tabs = build_config(CrtParams(noise_strength=0.0), 64, 48, vignette=half)
+    assert c.vignette_on == 2 and np.allclose(tabs[cabi.TABLE_VIGNETTE_PLANE], np.asarray(half, np.float32))
+    m = tables.make_triad_mask(8, 64, 0.35, 0.5)
+    assert (m.strength, m.softness) == (0.35, 0.5)
+    assert getattr(m * 0.5, "strength", None) is None and getattr(m.astype(np.float64), "strength", None) is None
+    from pythoncrt_b200 import effects
+    assert effects._mask_key(m)[0] == "made" and effects._mask_key(m * 0.5)[0] == "raw"
+    assert effects._mask_key(m * 0.5) != effects._mask_key(m * 0.25)                                # no collision in the config cache
+
+
+def test_lazy_vignette_is_make_vignette():
+    lv = tables.make_vignette_lazy(48, 64, 0.3)
+    assert lv.shape == (48, 64) and tables.infer_vignette_strength(lv) == 0.3
+    assert np.array_equal(np.asarray(lv), np.asarray(tables.make_vignette(48, 64, 0.3))) and lv[3, 5] == tables.make_vignette(48, 64, 0.3)[3, 5]
+
+
+def test_drop_in_noise_index_depends_on_the_frame_not_on_the_thread():
+    """two export workers must not hand frames 2k and 2k+1 the same grain."""
+    import threading
+    from pythoncrt_b200 import effects
+    fps, speed = 30.0, 30.0
+    want = [effects._frame_index(i / fps, (i / fps) * speed) for i in range(64)]
+    assert len(set(want)) == 64 and all(0 <= v < 2 ** 63 for v in want)
+    got = {}
+    def worker(start):
+        for i in range(start, 64, 2):
+            got[i] = effects._frame_index(i / fps, (i / fps) * speed)
+    ts = [threading.Thread(target=worker, args=(s,)) for s in (0, 1)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert [got[i] for i in range(64)] == want
+
+
+def test_channel_order_bgr_equals_swapped_rgb_on_the_host_build():
+    """crt_params.channel_order: BGR frames give the reference's result on the channel-swapped frame, swapped back,
+    bit for bit (kernels' arithmetic compiled for the host; the GPU test repeats this through the C ABI)."""
+    import host_emu
+    from oracle.cases import CASES_BY_NAME
+    for name in ("cfg2_gauss_grade", "cfg1_gui_default", "text_before", "neg_aberration_ps3", "triad_hard_nosoft"):
+        case = CASES_BY_NAME[name]
+        a, sa = host_emu.run_case(case, "export")
+        b, sb = host_emu.run_case(case, "export", channel_order="bgr")
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)) and np.array_equal(sa, sb), name
+    with pytest.raises(ValueError):
+        build_config(CrtParams(), 64, 48, channel_order="grb")
+
+
+def test_lazy_export_expression_and_cv2_proxy():
+    """effects.install(lazy_export=True): the reference's drain expression (:1092, :1098) builds a blend record
+    instead of touching pixels, and the cv2 proxy leaves everything else to the real cv2.  No GPU needed."""
+    import types
+    from pythoncrt_b200 import effects
+    eng = types.SimpleNamespace(height=4, width=6)
+    prev = effects.ExportFrame(eng, None, (), {}, None, 0, 1.0, 0.5)
+    prev.state = "resolved"                                     # stands for the device state of an already written frame
+    cur = effects.ExportFrame(eng, None, (), {}, None, 0, 2.0, 0.6)
+    persistence = 0.2
+    blended = np.clip(persistence * prev + (1.0 - persistence) * cur, 0.0, 1.0)
+    assert blended is cur and cur.blend_with[0] is prev and cur.blend_with[1] == 0.2 and blended.shape == (4, 6, 3)
+    blended = np.clip(np.float64(0.3) * prev + (1.0 - np.float64(0.3)) * cur, 0.0, 1.0)       # numpy scalars defer too
+    assert blended is cur and abs(cur.blend_with[1] - 0.3) < 1e-15
+    mod = types.ModuleType("crt_filter_standin")
+    mod.cv2, mod.np = cv2, np
+    effects.install(mod)
+    assert mod.apply_crt_effect is effects.apply_crt_effect and mod.apply_static_effects is effects.apply_static_effects_lazy
+    assert mod.make_vignette is tables.make_vignette_lazy and isinstance(mod.cv2, effects._Cv2Proxy)
+    x = np.random.default_rng(0).random((5, 7, 3)).astype(np.float32)
+    assert np.array_equal(mod.cv2.convertScaleAbs(x, alpha=255.0, beta=0), cv2.convertScaleAbs(x, alpha=255.0, beta=0))
+    assert mod.cv2.INTER_LINEAR == cv2.INTER_LINEAR and mod.cv2.resize is cv2.resize
+    effects.install(mod)                                        # idempotent: no proxy around a proxy
+    assert isinstance(mod.cv2._real, type(cv2))
+    mod2 = types.ModuleType("standin2"); mod2.cv2 = cv2
+    effects.install(mod2, lazy_export=False)
+    assert mod2.apply_static_effects is effects.apply_static_effects and mod2.cv2 is cv2
+
+
+@pytest.mark.reference
+def test_reference_drain_is_what_the_lazy_export_intercepts():
+    """The two source lines of process_video the lazy export path relies on (build container only)."""
+    path = "/root/reference/crt_filter.py"
+    if not os.path.isfile(path):
+        pytest.skip("reference not present")
+    src = open(path).read()
+    assert src.count("blended = np.clip(persistence * prev_state + (1.0 - persistence) * static_img, 0.0, 1.0)") == 2
+    assert src.count("out_frame = cv2.convertScaleAbs(blended, alpha=255.0, beta=0)") == 2
+    assert "executor.submit(\n                    apply_static_effects," in src
