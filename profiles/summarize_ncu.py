@@ -46,9 +46,10 @@ def main(rep, out):
             if k in hdr:
                 lines.append(f"| stall {s} (warps per issue) | {r[hdr.index(k)]} | |")
         lines.append("")
+    # per source line: instructions and warp-stall samples (the "sass,cuda" view lists every CUDA line with its totals)
     src = list(csv.reader(io.StringIO(run("-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"))))
-    per_line, text, ops = collections.Counter(), {}, collections.Counter()
-    cur, h, seen = None, None, set()
+    per_line, samples, text, why = collections.Counter(), collections.Counter(), {}, {}
+    cur, h = None, None
     for r in src:
         if not r:
             continue
@@ -56,25 +57,44 @@ def main(rep, out):
             cur, h = r[1].split("/")[-1], None
         elif r[0] == "Line No":
             h = r
-        elif h and cur and r[0].isdigit():
+        elif h and cur and r[0].isdigit() and r[2] == "-":
             try:
-                n = int(r[h.index("Instructions Executed")])
+                n, smp = int(r[h.index("Instructions Executed")]), int(r[h.index("# Samples")])
             except (ValueError, IndexError):
                 continue
-            if r[2] == "-":
-                per_line[(cur, int(r[0]))] += n
-                text[(cur, int(r[0]))] = r[1].strip()
-            elif r[2] not in seen:
-                seen.add(r[2])
-                m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[3])
-                if m:
-                    ops[m.group(2).split(".")[0]] += n
+            key = (cur, int(r[0]))
+            per_line[key] += n
+            samples[key] += smp
+            text[key] = r[1].strip()
+            st = {c[6:]: int(r[i]) for i, c in enumerate(h) if c.startswith("stall_") and "(" not in c and r[i].isdigit() and int(r[i])}
+            why[key] = ", ".join(f"{k} {v}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:3])
     tot = sum(per_line.values()) or 1
     lines += ["## hottest source lines (share of executed warp instructions, all captured launches)", "", "| file:line | % | source |", "|---|---|---|"]
     for k, v in per_line.most_common(25):
         lines.append(f"| {k[0]}:{k[1]} | {100 * v / tot:.1f} | `{text[k][:110]}` |")
+    tot_s = sum(samples.values()) or 1
+    lines += ["", "## source lines by warp-stall samples (where the warps wait; top stall reasons of the line)", "",
+              "| file:line | % of samples | top stalls | source |", "|---|---|---|---|"]
+    for k, v in samples.most_common(25):
+        lines.append(f"| {k[0]}:{k[1]} | {100 * v / tot_s:.1f} | {why.get(k, '')} | `{text[k][:90]}` |")
+    # SASS opcode mix (the "sass" view lists every instruction once per kernel)
+    sass = list(csv.reader(io.StringIO(run("-i", rep, "--page", "source", "--csv", "--print-source", "sass"))))
+    ops, h = collections.Counter(), None
+    for r in sass:
+        if not r:
+            continue
+        if r[0] == "Address":
+            h = r
+        elif h and r[0].startswith("0x"):
+            try:
+                n = int(r[h.index("Instructions Executed")])
+            except (ValueError, IndexError):
+                continue
+            m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_]+)", r[1])
+            if m:
+                ops[m.group(2)] += n
     tot_ops = sum(ops.values()) or 1
-    lines += ["", "## SASS opcode mix", "", ", ".join(f"{k} {100 * v / tot_ops:.1f}%" for k, v in ops.most_common(24)), ""]
+    lines += ["", "## SASS opcode mix (share of executed warp instructions)", "", ", ".join(f"{k} {100 * v / tot_ops:.1f}%" for k, v in ops.most_common(30)), ""]
     open(out, "w").write("\n".join(lines))
     print("wrote", out)
 

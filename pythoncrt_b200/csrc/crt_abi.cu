@@ -12,6 +12,8 @@
 #include "../../include/crt_b200.h"
 #include "crt_derive.h"
 #include "crt_fused_ps2.cuh"      // types and constants only: the kernels are instantiated in the crt_tu_*.cu units
+#include "crt_fused_warp_ps2.cuh"
+#include "crt_gather_box.cuh"
 #include "crt_launch.h"
 
 using namespace crt;
@@ -62,6 +64,11 @@ struct crt_ctx {
     const void* maps_in = nullptr; const void* maps_st = nullptr; int maps_frames = 0;
     FusedPlan plan{};                   // single-pass fused kernel
     FusedPlan plan_q{};                 // two-pass: fused first pass without warp/glitch/text-after, then k_gather
+    WarpPs2Plan plan_w{};               // single-pass warp on the block kernels (crt_fused_warp_ps2.cuh)
+    GatherBoxPlan plan_g{};             // second pass with the footprint staged by TMA (crt_gather_box.cuh)
+    int* d_origin = nullptr;            // device copy of plan_g.origin
+    CUtensorMap map_gq{}, map_gst{};    // tensor maps of the pre-warp image (box of plan_g) and of the state (96 x 32 box)
+    const void* map_gq_ptr = nullptr; const void* map_gst_ptr = nullptr; int map_gq_bw = 0, map_gq_bh = 0;
     Dev dev_q{};                        // parameter block of that first pass
     std::vector<cudaEvent_t> prof_ev;   // start/stop pairs (crt_profile_begin/end)
     int prof_cap = 0, prof_n = 0;
@@ -132,6 +139,10 @@ int build_dev(crt_ctx* ctx) {
     hd.dn_x = ctx->h_dn_x.data(); hd.dn_y = ctx->h_dn_y.data(); hd.up_x = ctx->h_up_x.data(); hd.up_y = ctx->h_up_y.data();
     ctx->plan = plan_fused(hd, glitch_active(p));
     ctx->plan_q = FusedPlan{};
+    // measured (round 2, run 3): the single-pass warp block kernel is slower than the two-pass path on BASELINE configs[2]
+    // (152 vs 125 us at 4K: the aligned footprint of a 64 x 32 tile holds 1.6-1.8x its pixels) -> opt-in only
+    ctx->plan_w = env_int("CRT_WARP_PS2", 0) ? plan_warp_ps2(hd, glitch_active(p)) : WarpPs2Plan{};
+    ctx->plan_g = GatherBoxPlan{};
     const bool gather_needed = ctx->dev.warp_on || glitch_active(p) || ctx->dev.text_mode == 2;
     if (!ctx->plan.ok || gather_needed || env_int("CRT_TWO_PASS", 0)) {
         Dev hq = hd;
@@ -144,6 +155,15 @@ int build_dev(crt_ctx* ctx) {
         const int pref = env_int("CRT_TWO_PASS", -1);
         if (ctx->plan.ok && ctx->plan_q.ok && ctx->dev.warp_on && (pref == 1 || (pref != 0 && ctx->plan_q.ps2))) ctx->plan.ok = false;
         if (ctx->plan.ok && ctx->plan_q.ok && !ctx->dev.warp_on && pref == 1) ctx->plan.ok = false;
+        if (ctx->dev.warp_on && env_int("CRT_GATHER_BOX", 1)) {
+            const GlitchGeom gg = glitch_geom(p, ctx->W, ctx->H);
+            ctx->plan_g = plan_gather_box(hd, gg.rows > 0 ? gg.y0 : ctx->H + 1, gg.rows > 0 ? env_int("CRT_GATHER_SLACK", 12) : 0);
+            if (ctx->plan_g.ok) {
+                if (ctx->d_origin) { cudaFree(ctx->d_origin); ctx->d_origin = nullptr; }
+                CU(cudaMalloc((void**)&ctx->d_origin, ctx->plan_g.origin.size() * sizeof(int)));
+                CU(cudaMemcpy(ctx->d_origin, ctx->plan_g.origin.data(), ctx->plan_g.origin.size() * sizeof(int), cudaMemcpyHostToDevice));
+            }
+        }
     }
     return CRT_OK;
 }
@@ -227,9 +247,10 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
     int launches = 0, fused_used = 0;
     // crt_process_static (d_img) takes the same kernels: the float image leaves through the path the pre-warp image of the
     // two-pass path takes (q_out), or is what the gather writes as "state" when no previous state is blended in
-    const bool want_fused = ctx->policy != 1 && ctx->plan.ok;
-    const bool want_two_pass = ctx->policy != 1 && !want_fused && ctx->plan_q.ok;
-    if (ctx->policy == 2 && !want_fused && !want_two_pass)
+    const bool want_warp = ctx->policy != 1 && ctx->plan_w.ok && !d_img;          // single-pass warp block kernel
+    const bool want_fused = ctx->policy != 1 && !want_warp && ctx->plan.ok;
+    const bool want_two_pass = ctx->policy != 1 && !want_warp && !want_fused && ctx->plan_q.ok;
+    if (ctx->policy == 2 && !want_warp && !want_fused && !want_two_pass)
         return fail(ctx, CRT_ERR_UNSUPPORTED, std::string("fused kernel not available: ") + ctx->plan.why);
     if (want_two_pass && !ctx->scratch.q) CU(cudaMalloc((void**)&ctx->scratch.q, frame_px * 3 * sizeof(float)));
     static const bool use_pdl = env_int("CRT_PDL", 1) != 0;
@@ -244,6 +265,24 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
             if (tma_encode(&ctx->map_gather, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_state, dims, strides, box)) ctx->map_gather_ptr = d_state;
         }
         if (ctx->map_gather_ptr == d_state) gather_map = &ctx->map_gather;
+    }
+    // second pass with the footprint staged by TMA: tensor maps of the pre-warp image (box from the plan) and of the state
+    bool gather_box = false;
+    if (want_two_pass && ctx->plan_g.ok && !d_img && d_state && !((uintptr_t)d_state & 15)) {
+        const uint64_t W3 = (uint64_t)d.W * 3;
+        const uint64_t dims[2] = {W3, (uint64_t)d.H}, strides[1] = {W3 * 4};
+        bool ok = true;
+        if (ctx->map_gq_ptr != ctx->scratch.q || ctx->map_gq_bw != ctx->plan_g.bw || ctx->map_gq_bh != ctx->plan_g.bh) {
+            const uint32_t box[2] = {(uint32_t)ctx->plan_g.bw * 3, (uint32_t)ctx->plan_g.bh};
+            ok = tma_encode(&ctx->map_gq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ctx->scratch.q, dims, strides, box);
+            if (ok) { ctx->map_gq_ptr = ctx->scratch.q; ctx->map_gq_bw = ctx->plan_g.bw; ctx->map_gq_bh = ctx->plan_g.bh; }
+        }
+        if (ok && ctx->map_gst_ptr != d_state) {
+            const uint32_t box[2] = {(uint32_t)GB_TW * 3, (uint32_t)GB_TH};
+            ok = tma_encode(&ctx->map_gst, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_state, dims, strides, box);
+            if (ok) ctx->map_gst_ptr = d_state;
+        }
+        gather_box = ok;
     }
     // TMA-pipelined block kernel: needs tensor maps of this call's clip and state buffers
     const bool pipe = (want_fused && ctx->plan.ps2 && !ctx->plan.gauss_k && persist && prepare_ps2_maps(ctx, d, d_in, n_frames, d_state)) ||
@@ -294,7 +333,10 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
         const bool pdl = i > 0 && use_pdl;
         ctx->maps.frame = i;
         int rc;
-        if (want_fused) {
+        if (want_warp) {
+            rc = launch_warp_ps2(ctx->env, ctx->plan_w, d, f, in_i, out_i, state_i, has_prev, st, &launches, pdl);
+            fused_used = 1;
+        } else if (want_fused) {
             rc = (ctx->plan.ps2 && ctx->plan.gauss_k) ? launch_fused_gauss_ps2(ctx->env, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches, pdl)
                : ctx->plan.ps2 ? launch_fused_ps2(ctx->env, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches, pdl, pipe ? &ctx->maps : nullptr)
                : ctx->plan.gauss_k ? launch_fused_gauss(ctx->env, ctx->plan.th, ctx->plan.nt, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches)
@@ -306,7 +348,9 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
                : pq.ps2 ? launch_fused_ps2(ctx->env, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl, pipe ? &ctx->maps : nullptr)
                : pq.gauss_k ? launch_fused_gauss(ctx->env, pq.th, pq.nt, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
                             : launch_fused(ctx->env, pq, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches);
-            if (!rc) rc = launch_gather(ctx->env, d, f, ctx->scratch.q, out_i, state_i, has_prev, st, &launches, gather_map);
+            if (!rc) rc = gather_box ? launch_gather_box(ctx->env, d, f, ctx->scratch.q, out_i, has_prev, st, &launches, ctx->d_origin, ctx->plan_g.bw,
+                                                         ctx->plan_g.bh, ctx->plan_g.smem, &ctx->map_gq, &ctx->map_gst)
+                                     : launch_gather(ctx->env, d, f, ctx->scratch.q, out_i, state_i, has_prev, st, &launches, gather_map);
             fused_used = 2;
         }
         else rc = run_staged(ctx, f, in_i, out_i, state_i, has_prev, img_i, st, &launches);
@@ -369,6 +413,7 @@ int crt_destroy(crt_ctx* ctx) {
     if (ctx->glitch_buf) cudaFree(ctx->glitch_buf);
     if (ctx->state) cudaFree(ctx->state);
     if (ctx->comp_lut) cudaFree(ctx->comp_lut);
+    if (ctx->d_origin) cudaFree(ctx->d_origin);
     if (ctx->pow_tab) cudaFree(ctx->pow_tab);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     HostRing& r = ctx->ring;

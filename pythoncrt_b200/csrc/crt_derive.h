@@ -80,6 +80,7 @@ inline int derive_dev(const crt_params& p, int W, int H, const TablePtrs& t, Dev
         d.thr_on = p.bloom_threshold > 0.0;
         double thr = fmin(0.99, fmax(0.0, p.bloom_threshold));
         d.thr = (float)thr; d.thr_den = (float)fmax(1e-6, 1.0 - thr);
+        d.thr_rcp = rcp_rn(d.thr_den);
         if (d.bloom_mode == 2) {
             int k = (int)py_round(p.bloom_sigma * 3.0) * 2 + 1;
             d.ksize = k > 1 ? k : 1;

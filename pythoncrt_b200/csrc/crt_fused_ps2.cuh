@@ -37,16 +37,17 @@ template <bool BLOOM, bool FAST, typename BloomFn, typename RowFn = NoRowHook>
 __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, const MaskTabs& mt, const float* s_fwd, const float* s_inv,
                                                const int (*s_sel)[12], float* __restrict__ state, uint8_t* __restrict__ out, float* __restrict__ q_out, int has_prev,
                                                int ox0, int oy0, int ox1, int oy1, int xb, int y0, const float (&t1)[2][3], BloomFn&& bloom,
-                                               float* s_prev = nullptr, bool state_in_smem = false, RowFn&& row_begin = RowFn()) {
+                                               float* s_prev = nullptr, bool state_in_smem = false, RowFn&& row_begin = RowFn(),
+                                               int s_pitch = P2_TW * 3) {
     // row_begin(r) runs before row r of the patch is evaluated (e.g. to compute that row's bloom values only then)
     // Both rows of the patch are inside the frame (even frame height, even y0), so the two rows' arithmetic is one
     // straight-line block the scheduler can interleave.
-    // s_prev: the patch's previous state in shared memory (row pitch P2_TW * 3 floats) when a TMA copy fetched it
+    // s_prev: the patch's previous state in shared memory (row pitch s_pitch floats) when a TMA copy fetched it
     auto finish = [&](int r, int y, auto&& pixel) {
         if (s_prev && state_in_smem) {
             // previous state read from (single-pass), and the new state / pre-warp image written back to, the tile buffer
             // in shared memory (it leaves with one TMA store per tile); only the packed uint8 pixels are stored from here
-            float4* sp = reinterpret_cast<float4*>(s_prev + r * (P2_TW * 3));
+            float4* sp = reinterpret_cast<float4*>(s_prev + r * s_pitch);
             const bool blend = has_prev && !q_out;
             float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa, pc = pa;
             if (blend) { pa = sp[0]; pb = sp[1]; pc = sp[2]; }
@@ -72,7 +73,7 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
                 op[2] = pack4(res[8], res[9], res[10], res[11]);
             }
         } else if (s_prev) {
-            const float4* sp = reinterpret_cast<const float4*>(s_prev + r * (P2_TW * 3));
+            const float4* sp = reinterpret_cast<const float4*>(s_prev + r * s_pitch);
             finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel, true, sp[0], sp[1], sp[2]);
         } else {
             finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, Fr
         fence_mbar_init();
         // first tile's input: independent of the previous kernel
         mbar_expect_tx(&bar_in[0], P2_RAW_BYTES);
-        tma_load_2d(s_raw, &map_in, (6 * ((tbx * P2_TW >> 1) - 1) - 3 * aa) & ~15, frame * d.hh + (tby * P2_TH >> 1) - 1, &bar_in[0]);
+        tma_load_2d_hint(s_raw, &map_in, (6 * ((tbx * P2_TW >> 1) - 1) - 3 * aa) & ~15, frame * d.hh + (tby * P2_TH >> 1) - 1, &bar_in[0], L2_EVICT_FIRST);
     }
     const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
     const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
@@ -390,8 +391,8 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, Fr
             }
             if (tile + (int)gridDim.x < ntiles) {      // next tile's input into the other buffer (last read two barriers ago)
                 mbar_expect_tx(&bar_in[buf ^ 1], P2_RAW_BYTES);
-                tma_load_2d(s_raw + (buf ^ 1) * P2_RAW_BYTES, &map_in, (6 * ((nbx * P2_TW >> 1) - 1) - 3 * aa) & ~15,
-                            frame * d.hh + (nby * P2_TH >> 1) - 1, &bar_in[buf ^ 1]);
+                tma_load_2d_hint(s_raw + (buf ^ 1) * P2_RAW_BYTES, &map_in, (6 * ((nbx * P2_TW >> 1) - 1) - 3 * aa) & ~15,
+                                 frame * d.hh + (nby * P2_TH >> 1) - 1, &bar_in[buf ^ 1], L2_EVICT_FIRST);
             }
         }
         if (tid < P2_TH) {
@@ -484,7 +485,9 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, Fr
         if (tile_out) fence_proxy_async();      // the new state in shared memory -> visible to the TMA engine
         __syncthreads();        // everyone is done with this tile's tables, block values and state tile
         if (tile_out && tid == 0) {            // the tile's new state leaves with one coalesced TMA store (rows outside the frame are clipped)
-            tma_store_2d(&map_st, s_state, ox0 * 3, oy0);
+            // the pre-warp image is read back by the next kernel (keep it in L2); the state only a frame later
+            // (measured, run 7: marking the state EVICT_FIRST costs the default chain 2 % — part of it is still in L2 a frame later)
+            tma_store_2d_hint(&map_st, s_state, ox0 * 3, oy0, q_out ? L2_EVICT_LAST : L2_EVICT_NORMAL);
             bulk_commit();
         }
         tbx = nbx; tby = nby;

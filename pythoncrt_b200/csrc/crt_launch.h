@@ -32,11 +32,14 @@ struct LaunchEnv {
 };
 
 struct FusedPlan;
+struct WarpPs2Plan;
 struct Ps2Maps;
 struct Scratch;
 
 int launch_fused_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
                      cudaStream_t st, int* launches, bool pdl, const Ps2Maps* maps);
+int launch_warp_ps2(LaunchEnv& env, const WarpPs2Plan& pl, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state,
+                    int has_prev, cudaStream_t st, int* launches, bool pdl);
 int launch_fused_gauss_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
                            int has_prev, cudaStream_t st, int* launches, bool pdl);
 int launch_fused_gauss(LaunchEnv& env, int th, int nt, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state,
@@ -45,6 +48,8 @@ int launch_fused(LaunchEnv& env, const FusedPlan& pl, const Dev& d, const FrameD
                  float* q_out, int has_prev, cudaStream_t st, int* launches);
 int launch_gather(LaunchEnv& env, const Dev& d, const FrameDev& f, const float* qimg, uint8_t* out, float* state, int has_prev,
                   cudaStream_t st, int* launches, const CUtensorMap* map_st);
+int launch_gather_box(LaunchEnv& env, const Dev& d, const FrameDev& f, const float* qimg, uint8_t* out, int has_prev, cudaStream_t st,
+                      int* launches, const int* origin, int bw, int bh, size_t smem, const CUtensorMap* map_q, const CUtensorMap* map_st);
 // staged kernels: bloom plane(s), pre-warp image, output; *dominant_first = launches before the output kernel
 int launch_staged(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, int has_prev, float* img,
                   const Scratch& s, cudaStream_t st, int* launches);

@@ -40,10 +40,11 @@ namespace crt {
 #define CRT_POW_TABLE static const
 #include "crt_pow_tables.h"     // host copies; kernels read the same values through Dev::pow_tab / shared memory
 #undef CRT_POW_TABLE
-constexpr int POW_TAB_FLOATS = 32 * 4 + 32 * 2;     // [log: 32 x (invc, logc_hi, logc_lo, 0) | exp2: 32 x (hi, lo)]
+constexpr int POW_TAB_EXP = 128 * 4;                 // offset of the exp2 table
+constexpr int POW_TAB_FLOATS = 128 * 4 + 64 * 2;     // [log: 128 x (invc, logc_hi, logc_lo, 0) | exp2: 64 x (hi, lo)]
 inline void fill_pow_table(float* t) {
-    for (int i = 0; i < 32; ++i) for (int c = 0; c < 4; ++c) t[4 * i + c] = kPowLog[i][c];
-    for (int j = 0; j < 32; ++j) { t[128 + 2 * j] = kPowExp2[j][0]; t[128 + 2 * j + 1] = kPowExp2[j][1]; }
+    for (int i = 0; i < 128; ++i) for (int c = 0; c < 4; ++c) t[4 * i + c] = kPowLog[i][c];
+    for (int j = 0; j < 64; ++j) { t[POW_TAB_EXP + 2 * j] = kPowExp2[j][0]; t[POW_TAB_EXP + 2 * j + 1] = kPowExp2[j][1]; }
 }
 
 // ---- exact float32 primitives ------------------------------------------------
@@ -125,6 +126,7 @@ struct Dev {
     int bloom_mode;              // 0 off, 1 fast, 2 gaussian
     float bloom_strength;
     int thr_on; float thr, thr_den;
+    float thr_rcp;               // correctly rounded 1 / thr_den (div_const)
     int ksize; const float* taps;
     int hw, hh;                  // half-size plane of the fast path
     int even_dims;               // W and H even: closed-form 2x coordinates
@@ -186,16 +188,16 @@ CRT_HD void source_bytes(const Dev& d, const uint8_t* __restrict__ in, int y, in
 
 // ---- x^y for the colour gamma (:304) ------------------------------------------------------------
 // numpy evaluates np.power(img, 1/gamma, dtype=float32) with SVML: within 1 ulp, correctly rounded
-// for only ~80 % of inputs, not reproducible elsewhere.  pow_unit is a table-driven float32 scheme
-// with double-float (hi, lo) intermediates where the precision is needed:
-//   log2 x = k + logc_i + log2(1 + r)   32 mantissa sub-intervals, r = m * invc_i - 1 held as an exact
-//                                       (hi, lo) pair, c1 * r as a double-float product, the r^2.. r^4
-//                                       terms in plain float32, the sum by Fast2Sum;
-//   E = y * log2 x                      double-float times float;
-//   x^y = 2^n * T_j * 2^f               n + j / 32 split off with a magic-number add, T_j = 2^(j/32)
-//                                       as (hi, lo), 2^f - 1 by a degree-4 polynomial, one final rounding.
-// ~50 float32 / integer instructions, no FP64 and no 64-bit integer work (the double version this
-// replaces compiled to ~115).  Error < 0.51 ulp; correctly rounded for ~99 % of inputs.
+// for only ~80 % of inputs, not reproducible elsewhere.  pow_unit is a table-driven float32 scheme that
+// keeps double-float (hi, lo) precision only where it is needed:
+//   log2 x = (k + logc_hi) + lo          128 mantissa sub-intervals: r = m * invc_i - 1 is ONE fma (|r| <= 2^-8, so
+//                                        its rounding error is 2^-33), lo = logc_lo + c1 r - c1 r^2/2 + c1 r^3/3 in plain
+//                                        float32 (|lo| < 2^-7: errors ~2^-32), k + logc_hi exact (16 fraction bits);
+//   E = y * log2 x                       E0 = y * hi rounded, its exact residual by fma, El = y * lo + residual;
+//   x^y = 2^n * T_j * 2^g                n + j / 64 split off E0 with a magic-number add (exact), g = f + El,
+//                                        T_j = 2^(j/64) as (hi, lo), 2^g - 1 by a degree-3 polynomial, one final rounding.
+// 37 float32 / integer instructions (the 32-entry-table version this replaces: ~65, with Fast2Sum chains for a
+// 2^-6 residual), no FP64.  Error < 0.52 ulp over the GUI's gamma range; tests/test_host_emu.py compares with float64.
 // Domain: x in [0, 1] (the stage input is clipped), y > 0.  Results below 2^-125 flush to 0.
 CRT_HD uint32_t f2u(float f) {
 #if CRT_DEVICE_CODE
@@ -212,60 +214,43 @@ CRT_HD float u2f(uint32_t u) {
 #endif
 }
 CRT_HD float pow_unit(float x, float y, const float* __restrict__ T) {
-    // Straight-line code (the two special cases are selects at the end), so that the three channels'
+    // Straight-line code (the two special cases are one select at the end), so that the three channels'
     // evaluations interleave in the instruction stream.
-    const uint32_t ix = f2u(x), tmp = ix - 0x3f330000u;
-    const uint32_t i = (tmp >> 18) & 31u;
+    const uint32_t ix = f2u(x), tmp = ix - 0x3f328000u;
+    const uint32_t i = (tmp >> 16) & 127u;
     const uint32_t top = tmp & 0xff800000u;
-    const float m = u2f(ix - top);                                         // x = 2^k * m, m in [0.7, 1.4)
-    const float kf = fsub(u2f(0x4b400000u + (uint32_t)((int32_t)top >> 23)), 12582912.0f);      // (float)k without a conversion
+    const float m = u2f(ix - top);                                         // x = 2^k * m, m in [0.697, 1.395)
+    const float kf = (float)((int32_t)top >> 23);
 #if CRT_DEVICE_CODE
     const float4 lt = *reinterpret_cast<const float4*>(T + 4 * i);
     const float invc = lt.x, lch = lt.y, lcl = lt.z;
 #else
     const float invc = T[4 * i], lch = T[4 * i + 1], lcl = T[4 * i + 2];
 #endif
-    // r = m * invc - 1 exactly, as rh + rl
-    const float ph = fmul(m, invc), rl = ffma(m, invc, -ph), rh = fsub(ph, 1.0f);
-    // c1 * r, c1 = 1 / ln 2 = c1h + c1l
-    const float c1h = 0x1.715476p+0f, c1l = 0x1.4ae0cp-26f;
-    const float P = fmul(c1h, rh);
-    float lo = ffma(c1h, rh, -P);
-    lo = ffma(c1l, rh, lo);
-    lo = ffma(c1h, rl, lo);
-    // c1 * (-r^2/2 + r^3/3 - r^4/4 + r^5/5)
-    const float r2 = fmul(rh, rh);
-    float q = ffma((float)(1.4426950408889634 / 5.0), rh, (float)(-1.4426950408889634 / 4.0));
-    q = ffma(q, rh, (float)(1.4426950408889634 / 3.0));
-    q = ffma(q, rh, (float)(-1.4426950408889634 / 2.0));
-    lo = ffma(r2, q, lo);
-    // log2 x = (k + logc_hi) + P + lo + logc_lo;  |k + logc_hi| >= 2 |P| or it is 0 (Fast2Sum is exact)
-    const float S = fadd(kf, lch);
-    const float hi = fadd(S, P);
-    lo = fadd(fadd(lo, lcl), fsub(P, fsub(hi, S)));
-    // E = y * log2 x as Eh + El
+    const float r = ffma(m, invc, -1.0f);                                  // |r| <= 2^-8: one rounding of 2^-33
+    const float r2 = fmul(r, r);
+    float lo = ffma(r2, ffma((float)(1.4426950408889634 / 3.0), r, (float)(-1.4426950408889634 / 2.0)), lcl);
+    lo = ffma(0x1.715476p+0f, r, lo);                                      // + r / ln 2
+    const float hi = fadd(kf, lch);                                        // exact
     const float E0 = fmul(y, hi);
-    float El = ffma(y, lo, ffma(y, hi, -E0));                             // lo carries the r^2.. terms: up to 2^-12
-    const float Eh = fadd(E0, El);                                        // renormalise so that |El| <= ulp(Eh) / 2
+    float El = ffma(y, lo, ffma(y, hi, -E0));                              // y * lo + (y * hi - E0): up to y * 2^-7
+    const float Eh = fadd(E0, El);                                         // renormalise (Fast2Sum): |El| <= ulp(Eh) / 2 for any y
     El = fsub(El, fsub(Eh, E0));
-    const float t = fadd(Eh, 393216.0f);                                  // 1.5 * 2^18: ulp 2^-5, the mantissa holds round(32 Eh)
+    const float t = fadd(Eh, 196608.0f);                                   // 1.5 * 2^17: ulp 2^-6, the mantissa holds round(64 Eh)
     const uint32_t ki = f2u(t);
-    const float f = fsub(Eh, fsub(t, 393216.0f));                         // exact, |f| <= 2^-6
-    const uint32_t j = ki & 31u;
+    const float g = fadd(fsub(Eh, fsub(t, 196608.0f)), El);                // exact difference (|.| <= 2^-7) + El
+    const uint32_t j = ki & 63u;
 #if CRT_DEVICE_CODE
-    const float2 tj = *reinterpret_cast<const float2*>(T + 128 + 2 * j);
+    const float2 tj = *reinterpret_cast<const float2*>(T + POW_TAB_EXP + 2 * j);
     const float th = tj.x, tl = tj.y;
 #else
-    const float th = T[128 + 2 * j], tl = T[128 + 2 * j + 1];
+    const float th = T[POW_TAB_EXP + 2 * j], tl = T[POW_TAB_EXP + 2 * j + 1];
 #endif
-    const float ln2 = (float)0.6931471805599453;
-    float e = ffma((float)0.009618129107628477, f, (float)0.05550410866482158);     // ln2^4 / 24, ln2^3 / 6
-    e = ffma(e, f, (float)0.2402265069591007);                            // ln2^2 / 2
-    e = ffma(e, f, ln2);
-    e = fmul(e, f);
-    e = ffma(El, ln2, e);                                                 // 2^(f + El) - 1
+    float e = ffma((float)0.05550410866482158, g, (float)0.2402265069591007);      // ln2^3 / 6, ln2^2 / 2
+    e = ffma(e, g, (float)0.6931471805599453);
+    e = fmul(e, g);                                                        // 2^g - 1
     const float res = fadd(th, ffma(th, e, tl));
-    const float out = u2f(f2u(res) + ((ki & ~31u) << 18));                // * 2^n, n = (round(32 Eh) - j) / 32
+    const float out = u2f(f2u(res) + ((ki & ~63u) << 17));                // * 2^n, n = (round(64 E0) - j) / 64
     // x = 0 (and sub-normals, which the chain never produces) -> 0; results below 2^-125 -> 0
     return (x >= 1.17549435e-38f && Eh >= -125.0f) ? out : 0.0f;
 }
@@ -341,8 +326,27 @@ CRT_HD F3 graded_source_lut(const Dev& d, const uint8_t* __restrict__ in, int sy
     return v;
 }
 
+// n / d for a divisor fixed per clip, bit-identical to the IEEE quotient: q = RN(n * y) with y = RN(1 / d), the exact
+// residual r = n - q d (one fma), q' = RN(q + r y).  Correctly rounded whenever y is (Markstein); checked exhaustively
+// against the hardware division for every float n in (1e-9, d] and fifteen divisors (3.6e9 quotients, no mismatch) and
+// sampled in tests/test_host_emu.py.  3 instructions instead of the ~9 of a general IEEE division.
+CRT_HD float div_const(float n, float d, float y) {
+    const float q = fmul(n, y);
+    return ffma(ffma(-q, d, n), y, q);
+}
+// Correctly rounded float32 reciprocal of d (host): the double quotient narrowed, checked against both neighbours.
+inline float rcp_rn(float d) {
+    float best = (float)(1.0 / (double)d);
+    double err = fabs(1.0 - (double)best * (double)d);           // products of two float32 are exact in double
+    const float cand[2] = {nextafterf(best, 0.0f), nextafterf(best, INFINITY)};
+    for (float c : cand) {
+        const double e = fabs(1.0 - (double)c * (double)d);
+        if (e < err) { err = e; best = c; }
+    }
+    return best;
+}
 // Bloom source: clip((img - thr) / max(1e-6, 1 - thr)) (:602-604)
-CRT_HD float bloom_src1(const Dev& d, float v) { return d.thr_on ? sat(fdiv(fsub(v, d.thr), d.thr_den)) : v; }
+CRT_HD float bloom_src1(const Dev& d, float v) { return d.thr_on ? sat(div_const(fsub(v, d.thr), d.thr_den, d.thr_rcp)) : v; }
 CRT_HD F3 bloom_src(const Dev& d, F3 v) { return mk3(bloom_src1(d, v.x), bloom_src1(d, v.y), bloom_src1(d, v.z)); }
 
 // cv2.resize lerp: fma(q - p, w, p)

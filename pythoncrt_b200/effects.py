@@ -141,7 +141,8 @@ def apply_crt_effect(frame, scanline_strength, triad_mask, triad_gamma, triad_pr
                      warp_strength=0.0, text_overlay_rgba=None, text_overlay_after=True, *, noise_plane=None, device: int = 0):
     """GUI chain incl. persistence and uint8 quantise; returns (uint8 H x W x 3, DeviceState)."""
     import torch
-    h, w = int(hw[0]), int(hw[1])
+    frame = np.asarray(frame)
+    h, w = frame.shape[0], frame.shape[1]
     eng = _engine_for(h, w, device)
     p = _params(scanline_strength, triad_gamma, triad_preserve_luma, aberration_px, bloom_sigma, bloom_strength, bloom_threshold,
                 noise_strength, persistence, scanline_period_px, fast_bloom, pixel_size, glitch_amp_px, glitch_height_frac,

@@ -108,6 +108,12 @@ extern "C" int emu_plan(const crt_params* p, int W, int H, const void* const* ta
 }
 
 // pow_unit on arrays, for the accuracy test
+// n / d through div_const (csrc/crt_math.cuh) next to the compiler's IEEE division
+extern "C" void emu_div_const(const float* n, float* out, float* want, int count, float d) {
+    const float y = rcp_rn(d);
+    for (int i = 0; i < count; ++i) { out[i] = div_const(n[i], d, y); volatile float q = n[i] / d; want[i] = q; }
+}
+
 extern "C" void emu_pow_unit(const float* x, float* out, int n, double y) {
     alignas(16) static float pow_tab[POW_TAB_FLOATS];
     fill_pow_table(pow_tab);

@@ -56,3 +56,21 @@ def test_pow_unit_is_correctly_rounded_almost_everywhere():
         assert ulp.max() <= max_ulp and (ulp > 0).mean() < max_miss, (gamma, ulp.max(), (ulp > 0).mean())
         assert np.all(out[~big] < 1e-37)
         assert out[256] == 1.0 and out[258] == 0.0
+
+
+def test_constant_divisor_division_is_the_ieee_quotient():
+    """csrc/crt_math.cuh div_const (bloom threshold, crt_filter.py:603): reciprocal, exact residual, one correction —
+    must be the correctly rounded quotient for every operand the stage can see (v - thr with v in [0, 1])."""
+    import ctypes as C
+    L = host_emu.lib()
+    rng = np.random.default_rng(3)
+    for thr in (0.7, 0.5, 0.3, 0.99, 0.01, 0.123456, 0.9, 1.0 - 1e-6, 0.6180339):
+        thr32 = np.float32(min(0.99, max(0.0, thr)))
+        d = np.float32(max(1e-6, 1.0 - float(min(0.99, max(0.0, thr)))))
+        v = np.concatenate([rng.random(1_000_000, dtype=np.float32), np.arange(256, dtype=np.float32) / np.float32(255.0),
+                            np.float32(thr32) + d * rng.random(200_000, dtype=np.float32)])
+        n = (v - thr32).astype(np.float32)
+        out, want = np.empty_like(n), np.empty_like(n)
+        L.emu_div_const(n.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p), C.c_int(n.size), C.c_float(float(d)))
+        assert np.array_equal(want, n / d)
+        assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), (thr, int((out != want).sum()))
