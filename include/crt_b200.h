@@ -134,7 +134,7 @@ typedef struct crt_frame {
 typedef struct crt_launch_info {
     int32_t kernels_launched;       /* kernels of this library launched by the call */
     int32_t fused;                  /* 1 = single fused tile kernel, 2 = two-pass (fused first pass + gather), 0 = staged kernels */
-    int32_t reserved[6];
+    int32_t reserved[6];            /* [0] = temporal shards the call ran concurrently (crt_set_shards), [1] = warm-up frames per shard */
 } crt_launch_info;
 
 int crt_abi_version(void);
@@ -151,6 +151,17 @@ int crt_set_table(crt_ctx* ctx, int table /* crt_table */, const void* h_data, s
 /* Execution policy: 0 = auto (fused tile kernel when the parameters allow, else
  * staged kernels), 1 = force staged, 2 = force fused (error if not possible). */
 int crt_set_policy(crt_ctx* ctx, int policy);
+
+/*
+ * Intra-GPU temporal shards for crt_process: a long clip is cut into up to `shards` contiguous pieces that run concurrently
+ * on one GPU (own stream and context each), every piece after the first preceded by a persistence warm-up of
+ * ceil(ln(1/2040) / ln(persistence)) frames whose outputs are discarded — the scheme process_video's frame order admits
+ * (the only cross-frame dependency is the blend at :1092) and the one used across GPUs (pythoncrt_b200/clip.py).  The result
+ * differs from the strictly serial run by at most persistence^warm-up <= 1/8 LSB before quantisation (identical when
+ * persistence == 0).  1 = off (default: every call is strictly serial), 0 = automatic (up to 4 shards, each at least 48 frames
+ * and 8 warm-ups long), k = at most k.  Calls shorter than that, and crt_process_static / crt_process_host, stay serial.
+ */
+int crt_set_shards(crt_ctx* ctx, int shards);
 
 /*
  * Run n_frames consecutive frames through the chain, persistence included.

@@ -21,7 +21,7 @@ POLICY_AUTO, POLICY_STAGED, POLICY_FUSED = 0, 1, 2
 
 # every symbol include/crt_b200.h declares
 EXPORTS = ("crt_abi_version", "crt_create", "crt_destroy", "crt_last_error", "crt_set_params", "crt_set_table",
-           "crt_set_policy", "crt_process", "crt_process_static", "crt_process_host", "crt_reset_state",
+           "crt_set_policy", "crt_set_shards", "crt_process", "crt_process_static", "crt_process_host", "crt_reset_state",
            "crt_generate_noise", "crt_generate_glitch", "crt_profile_begin", "crt_profile_end", "crt_profile_sample_every")
 
 
@@ -96,6 +96,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.crt_set_table.argtypes = [vp, i32, vp, sz]
     lib.crt_set_policy.restype = C.c_int
     lib.crt_set_policy.argtypes = [vp, i32]
+    lib.crt_set_shards.restype = C.c_int
+    lib.crt_set_shards.argtypes = [vp, i32]
     lib.crt_process.restype = C.c_int
     lib.crt_process.argtypes = [vp, vp, vp, vp, i32, C.POINTER(CrtFrameC), i32, vp, C.POINTER(CrtLaunchInfoC)]
     lib.crt_process_static.restype = C.c_int

@@ -34,6 +34,17 @@ struct HostRing {                       // crt_process_host staging
 
 }  // namespace
 
+struct crt_ctx;
+struct Shard {                          // one extra temporal shard of a clip: its own context, stream and buffers
+    crt_ctx* kid = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    float* state = nullptr;             // [H][W][3] persistence state of the shard
+    uint8_t* halo_out = nullptr;        // outputs of the warm-up frames (discarded)
+    size_t halo_cap = 0;
+    unsigned long long version = 0;     // configuration of the parent this kid was last synchronised with
+};
+
 struct crt_ctx {
     int device = 0, W = 0, H = 0;
     crt_params p{};
@@ -70,6 +81,11 @@ struct crt_ctx {
     CUtensorMap map_gq{}, map_gst{};    // tensor maps of the pre-warp image (box of plan_g) and of the state (96 x 32 box)
     const void* map_gq_ptr = nullptr; const void* map_gst_ptr = nullptr; int map_gq_bw = 0, map_gq_bh = 0;
     Dev dev_q{};                        // parameter block of that first pass
+    std::vector<uint8_t> h_tab[CRT_TABLE_COUNT];    // host copy of every table (replayed into the shard contexts)
+    unsigned long long version = 1;     // bumped by crt_set_params / crt_set_table / crt_set_policy
+    int shards_wanted = 1;              // crt_set_shards: 1 = off, 0 = auto, k > 1 = at most k
+    std::vector<Shard> shards;          // shards 1 .. K-1 (shard 0 is this context on the caller's stream)
+    cudaEvent_t ev_fork = nullptr;
     std::vector<cudaEvent_t> prof_ev;   // start/stop pairs (crt_profile_begin/end)
     int prof_cap = 0, prof_n = 0;
     int prof_every = 1, prof_tick = 0;  // one launch in prof_every is timed (crt_profile_sample_every)
@@ -227,48 +243,56 @@ bool prepare_ps2_maps(crt_ctx* ctx, const Dev& d, const uint8_t* d_in, int n_fra
     return true;
 }
 
-int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_state, int state_valid, float* d_img,
-                 const crt_frame* frames, int n_frames, cudaStream_t st, crt_launch_info* info) {
-    if (!ctx) return CRT_ERR_INVALID;
+// ---- one call = prepare (validation, path selection, tensor maps) + one launch_frame per frame ----------------------
+struct Call {
+    bool want_warp = false, want_fused = false, want_two_pass = false, pipe = false, gather_box = false, persist = false;
+    const CUtensorMap* gather_map = nullptr;
+    GlitchGeom gg{};
+    size_t frame_px = 0;
+    int fused_used = 0;
+};
+
+// d_in / n_frames describe the whole clip the frames of this call are taken from (the TMA-pipelined kernels address the
+// clip as ONE tensor: a frame is selected by its index), d_state the state buffer THIS context blends against.
+int prepare_call(crt_ctx* ctx, const uint8_t* d_in, int n_frames, const uint8_t* d_out, float* d_state, const float* d_img, Call* c) {
     if (!ctx->have_params) return fail(ctx, CRT_ERR_INVALID, "crt_set_params has not been called");
     if (!ctx->dev_ok) { int rc = build_dev(ctx); if (rc) return rc; }
-    if (n_frames < 0 || (n_frames > 0 && (!d_in || !frames || (!d_out && !d_img)))) return fail(ctx, CRT_ERR_INVALID, "null buffer");
+    if (n_frames < 0 || (n_frames > 0 && (!d_in || (!d_out && !d_img)))) return fail(ctx, CRT_ERR_INVALID, "null buffer");
     const crt_params& p = ctx->p;
     const Dev& d = ctx->dev;
-    const bool persist = p.persistence > 0.0 && !d_img;
-    if (persist && !d_state) return fail(ctx, CRT_ERR_INVALID, "persistence > 0 needs a state buffer");
+    c->persist = p.persistence > 0.0 && !d_img;
+    if (c->persist && !d_state) return fail(ctx, CRT_ERR_INVALID, "persistence > 0 needs a state buffer");
     // the kernels move the state with 16-byte and the pixels with 4-byte accesses (device allocations are aligned far beyond that)
     // (frames whose width is not a multiple of 4 take scalar accesses and have no such requirement)
     if ((d.W & 3) == 0 && (((uintptr_t)d_state & 15) || ((uintptr_t)d_out & 3) || ((uintptr_t)d_img & 15)))
         return fail(ctx, CRT_ERR_INVALID, "the state / float image buffer must be 16-byte aligned, the output clip 4-byte aligned");
     CU(cudaSetDevice(ctx->device));
-    const size_t frame_px = (size_t)d.W * d.H;
-    const GlitchGeom gg = glitch_geom(p, d.W, d.H);
-    int launches = 0, fused_used = 0;
+    c->frame_px = (size_t)d.W * d.H;
+    c->gg = glitch_geom(p, d.W, d.H);
     // crt_process_static (d_img) takes the same kernels: the float image leaves through the path the pre-warp image of the
     // two-pass path takes (q_out), or is what the gather writes as "state" when no previous state is blended in
-    const bool want_warp = ctx->policy != 1 && ctx->plan_w.ok && !d_img;          // single-pass warp block kernel
-    const bool want_fused = ctx->policy != 1 && !want_warp && ctx->plan.ok;
-    const bool want_two_pass = ctx->policy != 1 && !want_warp && !want_fused && ctx->plan_q.ok;
-    if (ctx->policy == 2 && !want_warp && !want_fused && !want_two_pass)
+    c->want_warp = ctx->policy != 1 && ctx->plan_w.ok && !d_img;          // single-pass warp block kernel
+    c->want_fused = ctx->policy != 1 && !c->want_warp && ctx->plan.ok;
+    c->want_two_pass = ctx->policy != 1 && !c->want_warp && !c->want_fused && ctx->plan_q.ok;
+    if (ctx->policy == 2 && !c->want_warp && !c->want_fused && !c->want_two_pass)
         return fail(ctx, CRT_ERR_UNSUPPORTED, std::string("fused kernel not available: ") + ctx->plan.why);
-    if (want_two_pass && !ctx->scratch.q) CU(cudaMalloc((void**)&ctx->scratch.q, frame_px * 3 * sizeof(float)));
-    static const bool use_pdl = env_int("CRT_PDL", 1) != 0;
+    c->fused_used = (c->want_warp || c->want_fused) ? 1 : c->want_two_pass ? 2 : 0;
+    if (c->want_two_pass && !ctx->scratch.q) CU(cudaMalloc((void**)&ctx->scratch.q, c->frame_px * 3 * sizeof(float)));
     // second pass of the two-pass path with the state moved by TMA: needs a tensor map of the state buffer (192 x 16 box)
     static const bool use_gather_tile = env_int("CRT_GATHER_TILE", 1) != 0;
-    const CUtensorMap* gather_map = nullptr;
-    if (want_two_pass && use_gather_tile && !d_img && d_state && !((uintptr_t)d_state & 15) && !(d.W & 3)) {
+    c->gather_map = nullptr;
+    if (c->want_two_pass && use_gather_tile && !d_img && d_state && !((uintptr_t)d_state & 15) && !(d.W & 3)) {
         if (ctx->map_gather_ptr != d_state) {
             const uint64_t W3 = (uint64_t)d.W * 3;
             const uint64_t dims[2] = {W3, (uint64_t)d.H}, strides[1] = {W3 * 4};
             const uint32_t box[2] = {(uint32_t)FTW * 3, (uint32_t)GATHER_TH};
             if (tma_encode(&ctx->map_gather, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_state, dims, strides, box)) ctx->map_gather_ptr = d_state;
         }
-        if (ctx->map_gather_ptr == d_state) gather_map = &ctx->map_gather;
+        if (ctx->map_gather_ptr == d_state) c->gather_map = &ctx->map_gather;
     }
     // second pass with the footprint staged by TMA: tensor maps of the pre-warp image (box from the plan) and of the state
-    bool gather_box = false;
-    if (want_two_pass && ctx->plan_g.ok && !d_img && d_state && !((uintptr_t)d_state & 15)) {
+    c->gather_box = false;
+    if (c->want_two_pass && ctx->plan_g.ok && !d_img && d_state && !((uintptr_t)d_state & 15)) {
         const uint64_t W3 = (uint64_t)d.W * 3;
         const uint64_t dims[2] = {W3, (uint64_t)d.H}, strides[1] = {W3 * 4};
         bool ok = true;
@@ -282,83 +306,208 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
             ok = tma_encode(&ctx->map_gst, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_state, dims, strides, box);
             if (ok) ctx->map_gst_ptr = d_state;
         }
-        gather_box = ok;
+        c->gather_box = ok;
     }
-    // TMA-pipelined block kernel: needs tensor maps of this call's clip and state buffers
-    const bool pipe = (want_fused && ctx->plan.ps2 && !ctx->plan.gauss_k && persist && prepare_ps2_maps(ctx, d, d_in, n_frames, d_state)) ||
-                      (want_two_pass && ctx->plan_q.ps2 && !ctx->plan_q.gauss_k && prepare_ps2_maps(ctx, ctx->dev_q, d_in, n_frames, ctx->scratch.q));
+    // TMA-pipelined block kernels: tensor maps of the clip and of this context's state buffer (or pre-warp image)
+    c->pipe = (c->want_fused && ctx->plan.ps2 && c->persist && prepare_ps2_maps(ctx, d, d_in, n_frames, d_state)) ||
+              (c->want_two_pass && ctx->plan_q.ps2 && prepare_ps2_maps(ctx, ctx->dev_q, d_in, n_frames, ctx->scratch.q));
+    return CRT_OK;
+}
+
+// Frame `index` of the clip (d_in + index frames) -> out_i (uint8) / img_i (float image); blends against d_state when has_prev.
+int launch_frame(crt_ctx* ctx, const Call& c, int index, const uint8_t* in_i, uint8_t* out_i, float* img_i, float* d_state, int has_prev,
+                 bool pdl, const crt_frame& fr, cudaStream_t st, int* launches_out) {
+    const crt_params& p = ctx->p;
+    const Dev& d = ctx->dev;
+    const GlitchGeom& gg = c.gg;
+    int launches = 0;
+    FrameDev f = derive_frame(p, fr);
+    prof_mark(ctx, st, false);          // whole frame: generators + every pass
+    if (d.noise_on) {
+        f.noise = fr.d_noise;
+        if (!f.noise) {
+            if (p.noise_mode != 1) return fail(ctx, CRT_ERR_INVALID, "noise_strength > 0 with noise_mode 0 needs crt_frame.d_noise");
+            if (!ctx->noise_buf) CU(cudaMalloc((void**)&ctx->noise_buf, c.frame_px * sizeof(float)));
+            if (launch_noise_gen(ctx->noise_buf, d.gh * d.gw, p.noise_seed, fr.frame_index, st)) return fail(ctx, CRT_ERR_CUDA, "noise generator launch failed");
+            ++launches;
+            f.noise = ctx->noise_buf;
+        }
+    }
+    if (gg.rows > 0) {
+        if (fr.d_glitch_offs) {
+            if (fr.glitch_rows != gg.rows || fr.glitch_y0 != gg.y0 || fr.glitch_seg_len <= 0 ||
+                fr.glitch_segments != (d.W + fr.glitch_seg_len - 1) / fr.glitch_seg_len)
+                return fail(ctx, CRT_ERR_INVALID, "injected glitch table geometry does not match the parameters");
+            f.goffs = fr.d_glitch_offs; f.gy0 = fr.glitch_y0; f.gseg = fr.glitch_seg_len; f.gnseg = fr.glitch_segments;
+        } else {
+            if (p.glitch_mode != 1) return fail(ctx, CRT_ERR_INVALID, "glitch on with glitch_mode 0 needs crt_frame.d_glitch_offs");
+            size_t need = (size_t)gg.rows * gg.nseg;
+            if (need > ctx->glitch_cap) {
+                if (ctx->glitch_buf) cudaFree(ctx->glitch_buf);
+                ctx->glitch_buf = nullptr; ctx->glitch_cap = 0;
+                CU(cudaMalloc((void**)&ctx->glitch_buf, need * sizeof(int32_t)));
+                ctx->glitch_cap = need;
+            }
+            int rc = gen_glitch(ctx, fr, gg, ctx->glitch_buf, st); if (rc) return rc;
+            ++launches;
+            f.goffs = ctx->glitch_buf; f.gy0 = gg.y0; f.gseg = gg.seg_len; f.gnseg = gg.nseg;
+        }
+    }
+    float* state_i = (c.persist || (d_state && !img_i)) ? d_state : nullptr;
+    float* q_i = nullptr;               // single-pass kernels: where the float image goes instead of out / state
+    if (img_i) { if (c.want_two_pass) state_i = img_i; else q_i = img_i; }
+    ctx->maps.frame = index;
+    int rc;
+    if (c.want_warp) {
+        rc = launch_warp_ps2(ctx->env, ctx->plan_w, d, f, in_i, out_i, state_i, has_prev, st, &launches, pdl);
+    } else if (c.want_fused) {
+        const Ps2Maps* maps = c.pipe ? &ctx->maps : nullptr;
+        rc = (ctx->plan.ps2 && ctx->plan.gauss_k) ? launch_fused_gauss_ps2(ctx->env, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches, pdl, maps)
+           : ctx->plan.ps2 ? launch_fused_ps2(ctx->env, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches, pdl, maps)
+           : ctx->plan.gauss_k ? launch_fused_gauss(ctx->env, ctx->plan.th, ctx->plan.nt, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches)
+                               : launch_fused(ctx->env, ctx->plan, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches);
+    } else if (c.want_two_pass) {
+        const FusedPlan& pq = ctx->plan_q;
+        const Ps2Maps* maps = c.pipe ? &ctx->maps : nullptr;
+        rc = (pq.ps2 && pq.gauss_k) ? launch_fused_gauss_ps2(ctx->env, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl, maps)
+           : pq.ps2 ? launch_fused_ps2(ctx->env, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl, maps)
+           : pq.gauss_k ? launch_fused_gauss(ctx->env, pq.th, pq.nt, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
+                        : launch_fused(ctx->env, pq, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches);
+        if (!rc) rc = c.gather_box ? launch_gather_box(ctx->env, d, f, ctx->scratch.q, out_i, has_prev, st, &launches, ctx->d_origin, ctx->plan_g.bw,
+                                                       ctx->plan_g.bh, ctx->plan_g.smem, &ctx->map_gq, &ctx->map_gst)
+                                   : launch_gather(ctx->env, d, f, ctx->scratch.q, out_i, state_i, has_prev, st, &launches, c.gather_map);
+    }
+    else rc = run_staged(ctx, f, in_i, out_i, state_i, has_prev, img_i, st, &launches);
+    prof_mark(ctx, st, true);
+    *launches_out += launches;
+    if (rc == CRT_ERR_CUDA) return fail(ctx, rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}
+
+int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_state, int state_valid, float* d_img,
+                 const crt_frame* frames, int n_frames, cudaStream_t st, crt_launch_info* info) {
+    if (!ctx) return CRT_ERR_INVALID;
+    if (n_frames > 0 && !frames) return fail(ctx, CRT_ERR_INVALID, "null buffer");
+    Call c;
+    int rc = prepare_call(ctx, d_in, n_frames, d_out, d_state, d_img, &c); if (rc) return rc;
+    static const bool use_pdl = env_int("CRT_PDL", 1) != 0;
+    const size_t fb = c.frame_px * 3;
+    int launches = 0;
     for (int i = 0; i < n_frames; ++i) {
-        const crt_frame& fr = frames[i];
-        FrameDev f = derive_frame(p, fr);
-        prof_mark(ctx, st, false);          // whole frame: generators + every pass
-        if (d.noise_on) {
-            f.noise = fr.d_noise;
-            if (!f.noise) {
-                if (p.noise_mode != 1) return fail(ctx, CRT_ERR_INVALID, "noise_strength > 0 with noise_mode 0 needs crt_frame.d_noise");
-                if (!ctx->noise_buf) CU(cudaMalloc((void**)&ctx->noise_buf, frame_px * sizeof(float)));
-                if (launch_noise_gen(ctx->noise_buf, d.gh * d.gw, p.noise_seed, fr.frame_index, st)) return fail(ctx, CRT_ERR_CUDA, "noise generator launch failed");
-                ++launches;
-                f.noise = ctx->noise_buf;
-            }
-        }
-        if (gg.rows > 0) {
-            if (fr.d_glitch_offs) {
-                if (fr.glitch_rows != gg.rows || fr.glitch_y0 != gg.y0 || fr.glitch_seg_len <= 0 ||
-                    fr.glitch_segments != (d.W + fr.glitch_seg_len - 1) / fr.glitch_seg_len)
-                    return fail(ctx, CRT_ERR_INVALID, "injected glitch table geometry does not match the parameters");
-                f.goffs = fr.d_glitch_offs; f.gy0 = fr.glitch_y0; f.gseg = fr.glitch_seg_len; f.gnseg = fr.glitch_segments;
-            } else {
-                if (p.glitch_mode != 1) return fail(ctx, CRT_ERR_INVALID, "glitch on with glitch_mode 0 needs crt_frame.d_glitch_offs");
-                size_t need = (size_t)gg.rows * gg.nseg;
-                if (need > ctx->glitch_cap) {
-                    if (ctx->glitch_buf) cudaFree(ctx->glitch_buf);
-                    ctx->glitch_buf = nullptr; ctx->glitch_cap = 0;
-                    CU(cudaMalloc((void**)&ctx->glitch_buf, need * sizeof(int32_t)));
-                    ctx->glitch_cap = need;
-                }
-                int rc = gen_glitch(ctx, fr, gg, ctx->glitch_buf, st); if (rc) return rc;
-                ++launches;
-                f.goffs = ctx->glitch_buf; f.gy0 = gg.y0; f.gseg = gg.seg_len; f.gnseg = gg.nseg;
-            }
-        }
-        const int has_prev = persist && (state_valid || i > 0);
-        const uint8_t* in_i = d_in + (size_t)i * frame_px * 3;
-        uint8_t* out_i = d_out ? d_out + (size_t)i * frame_px * 3 : nullptr;
-        float* img_i = d_img ? d_img + (size_t)i * frame_px * 3 : nullptr;
-        float* state_i = (persist || (d_state && !d_img)) ? d_state : nullptr;
-        float* q_i = nullptr;               // single-pass kernels: where the float image goes instead of out / state
-        if (d_img) { if (want_two_pass) state_i = img_i; else q_i = img_i; }
         // Frames after the first may overlap the previous frame's kernel tail (launch_pdl, crt_fused.cuh).  Never frame 0:
         // its input may come from the caller's immediately preceding kernel.
-        const bool pdl = i > 0 && use_pdl;
-        ctx->maps.frame = i;
-        int rc;
-        if (want_warp) {
-            rc = launch_warp_ps2(ctx->env, ctx->plan_w, d, f, in_i, out_i, state_i, has_prev, st, &launches, pdl);
-            fused_used = 1;
-        } else if (want_fused) {
-            rc = (ctx->plan.ps2 && ctx->plan.gauss_k) ? launch_fused_gauss_ps2(ctx->env, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches, pdl)
-               : ctx->plan.ps2 ? launch_fused_ps2(ctx->env, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches, pdl, pipe ? &ctx->maps : nullptr)
-               : ctx->plan.gauss_k ? launch_fused_gauss(ctx->env, ctx->plan.th, ctx->plan.nt, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches)
-                                   : launch_fused(ctx->env, ctx->plan, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches);
-            fused_used = 1;
-        } else if (want_two_pass) {
-            const FusedPlan& pq = ctx->plan_q;
-            rc = (pq.ps2 && pq.gauss_k) ? launch_fused_gauss_ps2(ctx->env, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl)
-               : pq.ps2 ? launch_fused_ps2(ctx->env, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl, pipe ? &ctx->maps : nullptr)
-               : pq.gauss_k ? launch_fused_gauss(ctx->env, pq.th, pq.nt, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
-                            : launch_fused(ctx->env, pq, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches);
-            if (!rc) rc = gather_box ? launch_gather_box(ctx->env, d, f, ctx->scratch.q, out_i, has_prev, st, &launches, ctx->d_origin, ctx->plan_g.bw,
-                                                         ctx->plan_g.bh, ctx->plan_g.smem, &ctx->map_gq, &ctx->map_gst)
-                                     : launch_gather(ctx->env, d, f, ctx->scratch.q, out_i, state_i, has_prev, st, &launches, gather_map);
-            fused_used = 2;
-        }
-        else rc = run_staged(ctx, f, in_i, out_i, state_i, has_prev, img_i, st, &launches);
-        prof_mark(ctx, st, true);
-        if (rc == CRT_ERR_CUDA) return fail(ctx, rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        rc = launch_frame(ctx, c, i, d_in + (size_t)i * fb, d_out ? d_out + (size_t)i * fb : nullptr, d_img ? d_img + (size_t)i * fb : nullptr, d_state,
+                          c.persist && (state_valid || i > 0), i > 0 && use_pdl, frames[i], st, &launches);
         if (rc) return rc;
     }
-    if (info) { info->kernels_launched = launches; info->fused = fused_used; }
+    if (info) { info->kernels_launched = launches; info->fused = c.fused_used; }
+    return CRT_OK;
+}
+
+// ---- intra-GPU temporal shards ------------------------------------------------------------------------------------------
+// One stream of frame kernels does not fill a B200: the kernels are latency bound and every frame ends in a
+// partial wave.  The chain's only cross-frame dependency is the persistence recurrence s_t = clip(p s_{t-1} + (1-p) x_t)
+// (crt_filter.py:1092), whose memory of the past decays as p^k, so a clip can be cut into contiguous temporal shards exactly
+// as it is across GPUs (pythoncrt_b200/clip.py): shard k > 0 starts `halo` frames early from an empty state,
+// discards those outputs and then matches the serial run to within p^halo <= 1/2040 (an eighth of an LSB).  Here the shards
+// run CONCURRENTLY on one GPU, each on its own stream with its own context (scratch buffers, tensor maps), launches
+// interleaved frame by frame.  Measured (round 2, profiles/tools/concurrency_probe.py): default chain at 4K 18.7k -> 21.9k
+// frames/s with 3 shards, 1080p gaussian chain 40.3k -> 55.7k, VGA 113k -> 185k with 4.
+int halo_frames(double persistence) {
+    if (!(persistence > 0.0)) return 0;
+    return (int)ceil(log(1.0 / 2040.0) / log(persistence));
+}
+
+int choose_shards(const crt_ctx* ctx, int n_frames) {
+    static const int forced = env_int("CRT_SHARDS", -1);
+    const int wanted = forced >= 0 ? forced : ctx->shards_wanted;
+    if (wanted == 1 || n_frames < 2) return 1;
+    const int halo = halo_frames(ctx->p.persistence);
+    // a shard must be worth its warm-up: at least 8 halos (<= 12.5 % extra frames) and 48 frames long
+    const int min_chunk = halo * 8 > 48 ? halo * 8 : 48;
+    int k = n_frames / min_chunk;
+    const int cap = wanted == 0 ? 4 : wanted;
+    if (k > cap) k = cap;
+    return k < 1 ? 1 : k;
+}
+
+int sync_shards(crt_ctx* ctx, int K) {
+    if (!ctx->ev_fork) CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    while ((int)ctx->shards.size() < K - 1) {
+        Shard s;
+        int rc = crt_create(ctx->device, ctx->W, ctx->H, &s.kid);
+        if (rc) return fail(ctx, rc, std::string("shard context: ") + crt_last_error(nullptr));
+        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        ctx->shards.push_back(s);
+    }
+    for (int k = 0; k < K - 1; ++k) {
+        Shard& s = ctx->shards[k];
+        if (s.version == ctx->version) continue;
+        for (int t = 0; t < CRT_TABLE_COUNT; ++t) {
+            int rc = crt_set_table(s.kid, t, ctx->h_tab[t].empty() ? nullptr : ctx->h_tab[t].data(), ctx->h_tab[t].size());
+            if (rc) return fail(ctx, rc, std::string("shard table: ") + crt_last_error(s.kid));
+        }
+        int rc = crt_set_params(s.kid, &ctx->p);
+        if (!rc) rc = crt_set_policy(s.kid, ctx->policy);
+        if (rc) return fail(ctx, rc, std::string("shard parameters: ") + crt_last_error(s.kid));
+        s.version = ctx->version;
+    }
+    return CRT_OK;
+}
+
+int process_sharded(crt_ctx* ctx, int K, const uint8_t* d_in, uint8_t* d_out, float* d_state, int state_valid, const crt_frame* frames,
+                    int n_frames, cudaStream_t st, crt_launch_info* info) {
+    int rc = sync_shards(ctx, K); if (rc) return rc;
+    const int halo = halo_frames(ctx->p.persistence);
+    const size_t fb = (size_t)ctx->W * ctx->H * 3;
+    struct Part { crt_ctx* c; cudaStream_t st; float* state; uint8_t* halo_out; int warm, a, b; Call call; };
+    std::vector<Part> parts(K);
+    const int base = n_frames / K, extra = n_frames % K;
+    int longest = 0;
+    for (int k = 0; k < K; ++k) {
+        Part& pt = parts[k];
+        pt.a = k * base + (k < extra ? k : extra);
+        pt.b = pt.a + base + (k < extra ? 1 : 0);
+        pt.warm = k == 0 ? 0 : pt.a - halo;                   // >= 0: a shard is at least 8 halos long (choose_shards)
+        if (k == 0) { pt.c = ctx; pt.st = st; pt.state = d_state; pt.halo_out = nullptr; }
+        else {
+            Shard& s = ctx->shards[k - 1];
+            if (!s.state) CU(cudaMalloc((void**)&s.state, fb * sizeof(float)));
+            if (halo > 0 && s.halo_cap < (size_t)halo * fb) {
+                if (s.halo_out) cudaFree(s.halo_out);
+                s.halo_out = nullptr; s.halo_cap = 0;
+                CU(cudaMalloc((void**)&s.halo_out, (size_t)halo * fb));
+                s.halo_cap = (size_t)halo * fb;
+            }
+            pt.c = s.kid; pt.st = s.stream; pt.state = s.state; pt.halo_out = s.halo_out;
+        }
+        rc = prepare_call(pt.c, d_in, n_frames, d_out, pt.state, nullptr, &pt.call);
+        if (rc) return k == 0 ? rc : fail(ctx, rc, std::string("shard: ") + crt_last_error(pt.c));
+        if (pt.b - pt.warm > longest) longest = pt.b - pt.warm;
+    }
+    // fork: the shards' streams start after whatever the caller's stream has queued so far (the clip may come from a kernel there)
+    CU(cudaEventRecord(ctx->ev_fork, st));
+    for (int k = 1; k < K; ++k) CU(cudaStreamWaitEvent(parts[k].st, ctx->ev_fork, 0));
+    static const bool use_pdl = env_int("CRT_PDL", 1) != 0;
+    int launches = 0;
+    for (int j = 0; j < longest; ++j)                       // launches interleaved frame by frame so that every stream stays fed
+        for (int k = 0; k < K; ++k) {
+            Part& pt = parts[k];
+            const int i = pt.warm + j;
+            if (i >= pt.b) continue;
+            uint8_t* out_i = i < pt.a ? pt.halo_out + (size_t)(i - pt.warm) * fb : d_out + (size_t)i * fb;
+            const int has_prev = pt.call.persist && ((k == 0 && state_valid) || j > 0);
+            rc = launch_frame(pt.c, pt.call, i, d_in + (size_t)i * fb, out_i, nullptr, pt.state, has_prev, j > 0 && use_pdl, frames[i], pt.st, &launches);
+            if (rc) return k == 0 ? rc : fail(ctx, rc, std::string("shard: ") + crt_last_error(pt.c));
+        }
+    // join, then hand the caller the state after the LAST frame of the clip
+    for (int k = 1; k < K; ++k) {
+        CU(cudaEventRecord(ctx->shards[k - 1].done, parts[k].st));
+        CU(cudaStreamWaitEvent(st, ctx->shards[k - 1].done, 0));
+    }
+    if (d_state) CU(cudaMemcpyAsync(d_state, parts[K - 1].state, fb * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (info) { info->kernels_launched = launches; info->fused = parts[0].call.fused_used; info->reserved[0] = K; info->reserved[1] = halo; }
     return CRT_OK;
 }
 
@@ -414,6 +563,14 @@ int crt_destroy(crt_ctx* ctx) {
     if (ctx->state) cudaFree(ctx->state);
     if (ctx->comp_lut) cudaFree(ctx->comp_lut);
     if (ctx->d_origin) cudaFree(ctx->d_origin);
+    for (Shard& sh : ctx->shards) {
+        if (sh.stream) { cudaStreamSynchronize(sh.stream); cudaStreamDestroy(sh.stream); }
+        if (sh.done) cudaEventDestroy(sh.done);
+        if (sh.state) cudaFree(sh.state);
+        if (sh.halo_out) cudaFree(sh.halo_out);
+        crt_destroy(sh.kid);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->pow_tab) cudaFree(ctx->pow_tab);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     HostRing& r = ctx->ring;
@@ -440,6 +597,7 @@ int crt_set_params(crt_ctx* ctx, const crt_params* params) {
     ctx->p = *params;
     ctx->have_params = true;
     ctx->dev_ok = false;
+    ++ctx->version;
     return CRT_OK;
 }
 
@@ -447,11 +605,14 @@ int crt_set_table(crt_ctx* ctx, int table, const void* h_data, size_t bytes) {
     if (!ctx || table < 0 || table >= CRT_TABLE_COUNT) return CRT_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
     if (ctx->tab[table] && ctx->tab_bytes[table] != bytes) { CU(cudaDeviceSynchronize()); cudaFree(ctx->tab[table]); ctx->tab[table] = nullptr; ctx->tab_bytes[table] = 0; }
+    ++ctx->version;
     if (!h_data || bytes == 0) {
         if (ctx->tab[table]) { CU(cudaDeviceSynchronize()); cudaFree(ctx->tab[table]); }
         ctx->tab[table] = nullptr; ctx->tab_bytes[table] = 0; ctx->dev_ok = false;
+        ctx->h_tab[table].clear();
         return CRT_OK;
     }
+    ctx->h_tab[table].assign((const uint8_t*)h_data, (const uint8_t*)h_data + bytes);
     if (!ctx->tab[table]) CU(cudaMalloc(&ctx->tab[table], bytes));
     CU(cudaMemcpy(ctx->tab[table], h_data, bytes, cudaMemcpyHostToDevice));
     ctx->tab_bytes[table] = bytes;
@@ -467,12 +628,24 @@ int crt_set_table(crt_ctx* ctx, int table, const void* h_data, size_t bytes) {
 int crt_set_policy(crt_ctx* ctx, int policy) {
     if (!ctx || policy < 0 || policy > 2) return CRT_ERR_INVALID;
     ctx->policy = policy;
+    ++ctx->version;
     return CRT_OK;
 }
 
 int crt_process(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_state, int state_valid, const crt_frame* frames, int n_frames,
                 void* stream, crt_launch_info* info) {
+    if (!ctx) return CRT_ERR_INVALID;
+    const int K = (ctx->have_params && d_in && d_out && frames) ? choose_shards(ctx, n_frames) : 1;
+    if (K > 1 && (d_state || !(ctx->p.persistence > 0.0)))
+        return process_sharded(ctx, K, d_in, d_out, d_state, state_valid, frames, n_frames, (cudaStream_t)stream, info);
+    if (info) { info->reserved[0] = 1; info->reserved[1] = 0; }
     return process_impl(ctx, d_in, d_out, d_state, state_valid, nullptr, frames, n_frames, (cudaStream_t)stream, info);
+}
+
+int crt_set_shards(crt_ctx* ctx, int shards) {
+    if (!ctx || shards < 0 || shards > 16) return CRT_ERR_INVALID;
+    ctx->shards_wanted = shards;
+    return CRT_OK;
 }
 
 int crt_process_static(crt_ctx* ctx, const uint8_t* d_in, float* d_img, const crt_frame* frames, int n_frames, void* stream, crt_launch_info* info) {

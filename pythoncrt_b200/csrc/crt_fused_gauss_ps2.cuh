@@ -44,9 +44,10 @@ CRT_HD GaussPs2Geo gauss_ps2_geo(int K) {
     g.pitch = (g.nby & 3) == 2 ? g.nby : g.nby + 2;
     return g;
 }
-inline size_t fused_gauss_ps2_smem(int K) {
+inline size_t fused_gauss_ps2_smem(int K, bool state_tile = false) {
     const GaussPs2Geo g = gauss_ps2_geo(K);
-    return sizeof(float) * ((size_t)3 * g.nbx * g.pitch + (size_t)3 * g.nby * P2_TW + (size_t)3 * (P2_TH / 2) * (P2_TW / 2));
+    return sizeof(float) * ((size_t)3 * g.nbx * g.pitch + (size_t)3 * g.nby * P2_TW + (size_t)3 * (P2_TH / 2) * (P2_TW / 2) +
+                            (state_tile ? (size_t)P2_TH * P2_TW * 3 : 0));
 }
 CRT_HD bool fused_gauss_ps2_supported(const Dev& d, bool glitch_on) {
     return d.bloom_mode == 2 && d.pix_uniform == 2 && d.even_dims && (d.W & 3) == 0 && !d.warp_on && !glitch_on && d.text_mode == 0;
@@ -54,15 +55,22 @@ CRT_HD bool fused_gauss_ps2_supported(const Dev& d, bool glitch_on) {
 
 #if defined(__CUDACC__)
 
-template <int K, bool FAST, int MINB>
+// TST: the tile's previous state arrives by ONE tiled tensor-map copy (TMA) issued at the top of the tile's iteration and is
+// consumed two phases later from shared memory; the new state (or the pre-warp image of the two-pass path) goes back into the
+// same tile and leaves with one TMA store — as in k_fused_ps2_pipe.  ncu (round 2, run 3) put 10.6 % of this kernel's
+// warp-stall samples on the first use of the per-thread state loads (L2 latency: at 1080p the state lives in L2) and another
+// 10 % on the table staging at kernel entry; with TST the tables also arrive by bulk copies that are only waited for at their
+// first use, after the first tile's input loads are in flight.  24.5 KB more shared memory: still three CTAs per SM.
+template <int K, bool FAST, int MINB, bool TST>
 __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
-                                                           float* __restrict__ state, float* __restrict__ q_out, int has_prev) {
+                                                           float* __restrict__ state, float* __restrict__ q_out, int has_prev,
+                                                           const __grid_constant__ CUtensorMap map_st) {
     constexpr int R = K / 2, HB = (R + 1) / 2, OFF = R & 1;
     constexpr int NBX = P2_TW / 2 + 2 * HB, NBY = P2_TH / 2 + 2 * HB;
     constexpr int PITCH = (NBY & 3) == 2 ? NBY : NBY + 2;
     constexpr int MR = ((K + 2 + OFF) >> 1) + 1;                  // distinct block columns under 4 outputs' taps
     constexpr int MC = ((2 * R + 1 + OFF) >> 1) + 1;              // distinct block rows under 2 output rows' taps
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
     __shared__ __align__(16) float s_lut[2 * 1028];
     __shared__ __align__(16) int s_sel[3][12];
     float* const s_fwd = s_lut;
@@ -70,21 +78,37 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
     __shared__ float s_unit[256];
     __shared__ __align__(16) float s_pow[POW_TAB_FLOATS];
     __shared__ float s_rows[2 * P2_TH], s_cols[2 * P2_TW];
-    float* Sb = sm;                                 // [3][NBX][PITCH]   thresholded bloom source per block, transposed
+    __shared__ __align__(8) uint64_t bar_tab, bar_st;
+    float* const s_state = sm;                      // [TH][TW*3]        state tile (TST only; first: TMA wants 128-byte alignment)
+    float* Sb = sm + (TST ? P2_TH * P2_TW * 3 : 0); // [3][NBX][PITCH]   thresholded bloom source per block, transposed
     float* Rp = Sb + 3 * NBX * PITCH;               // [3][NBY][P2_TW]   row-pass result per block row
     float* T1 = Rp + 3 * NBY * P2_TW;               // [3][TH/2][TW/2]   graded block values of the tile
     const int tid = threadIdx.x;
     griddep_launch_dependents();        // the next frame's kernel may begin its state-independent phases (see launch_pdl)
     const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
     const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
-    if (d.triad_mode >= 2) {
-        reinterpret_cast<float4*>(s_fwd)[tid] = reinterpret_cast<const float4*>(lut_a)[tid];
-        reinterpret_cast<float4*>(s_inv)[tid] = reinterpret_cast<const float4*>(lut_b)[tid];
-        if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
+    const bool use_state = has_prev && !q_out;      // a previous state to fetch
+    const bool tile_out = TST && (state || q_out);  // the result leaves through the shared-memory tile
+    if (TST) {
+        if (tid == 0) {                             // tables by bulk copies (16-byte multiples; element 1024 of each LUT below)
+            mbar_init(&bar_tab, 1); mbar_init(&bar_st, 1);
+            fence_mbar_init();
+            const uint32_t bytes = (d.triad_mode >= 2 ? 2 * 4096 : 0) + (d.col_gamma ? POW_TAB_FLOATS * 4 : 0);
+            mbar_expect_tx(&bar_tab, bytes);
+            if (d.triad_mode >= 2) { bulk_g2s(s_fwd, lut_a, 4096, &bar_tab); bulk_g2s(s_inv, lut_b, 4096, &bar_tab); }
+            if (d.col_gamma) bulk_g2s(s_pow, d.pow_tab, POW_TAB_FLOATS * 4, &bar_tab);
+            if (d.triad_mode >= 2) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
+        }
+    } else {
+        if (d.triad_mode >= 2) {
+            reinterpret_cast<float4*>(s_fwd)[tid] = reinterpret_cast<const float4*>(lut_a)[tid];
+            reinterpret_cast<float4*>(s_inv)[tid] = reinterpret_cast<const float4*>(lut_b)[tid];
+            if (tid == 0) { s_fwd[1024] = lut_a[1024]; s_inv[1024] = lut_b[1024]; }
+        }
+        if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += blockDim.x) s_pow[i] = d.pow_tab[i];
     }
     s_unit[tid] = __fdiv_rn((float)tid, 255.0f);
     ps2_fill_sel(s_sel, tid, d.bgr);
-    if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += blockDim.x) s_pow[i] = d.pow_tab[i];
     float taps[K];                                  // the kernel is symmetric: R + 1 registers
 #pragma unroll
     for (int i = 0; i <= R; ++i) { taps[R + i] = d.taps[R + i]; taps[R - i] = taps[R + i]; }
@@ -93,9 +117,16 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
     const int tiles_x = (d.W + P2_TW - 1) / P2_TW, ntiles = tiles_x * ((d.H + P2_TH - 1) / P2_TH);
     const int step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;      // tile += gridDim.x without a division per tile
     int tby = blockIdx.x / tiles_x, tbx = blockIdx.x - tby * tiles_x;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {      // persistent CTAs, tables staged once
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {    // persistent CTAs, tables staged once
         const int ox0 = tbx * P2_TW, oy0 = tby * P2_TH;
         const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + P2_TH, d.H) - 1;
+        if (TST && tile_out && tid == 0) {
+            // The previous tile's TMA store must have drained the tile buffer; then fetch this tile's state.  The first tile
+            // waits for the previous kernel of the stream first (this thread only: the other warps start their grading).
+            if (iter > 0) bulk_wait_read(); else griddep_wait();
+            if (use_state) { mbar_expect_tx(&bar_st, P2_ST_BYTES); tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st); }
+        }
         if (tid < P2_TH) {
             const int y = oy0 + tid;
             if (d.scan_mode == 1) mt.row_scan[tid] = scan_row(d, f, y);
@@ -143,6 +174,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
                     raw[it][2] = row[wrap(sx + a0, d.W) * 3 + 2];
                 }
             }
+            if (TST && iter == 0) mbar_wait(&bar_tab, 0);   // the tables have landed (the loads above are already in flight)
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
                 if ((tid & ~31) + it * P2_NT >= NBX * NBY) break;
@@ -183,6 +215,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
         }
         __syncthreads();
         griddep_wait();         // previous kernel of the stream complete: state / pre-warp image / noise may be touched from here on
+        if (TST && use_state) mbar_wait(&bar_st, iter & 1);      // this tile's previous state has landed
 
         // ---- phase 3 + 4: column pass in registers, then the per-pixel tail for a 4 x 2 patch ----
         const int tx = tid & 15, ty = tid >> 4;
@@ -212,21 +245,34 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev
                 }
             }
             ps2_patch_tail<true, FAST>(d, f, mt, s_fwd, s_inv, s_sel, state, out, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
-                                       [&](int r, int k) { return mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]); });
+                                       [&](int r, int k) { return mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]); },
+                                       tile_out ? s_state + (y0 - oy0) * (P2_TW * 3) + 12 * tx : nullptr, tile_out);
         }
-        __syncthreads();        // everyone is done with this tile's tables before the next tile overwrites them
+        if (tile_out) fence_proxy_async();      // the new state in shared memory -> visible to the TMA engine
+        __syncthreads();        // everyone is done with this tile's tables (and state tile) before the next tile overwrites them
+        if (tile_out && tid == 0) {             // one coalesced TMA store per tile (rows outside the frame are clipped); the pre-warp
+            tma_store_2d_hint(&map_st, s_state, ox0 * 3, oy0, q_out ? L2_EVICT_LAST : L2_EVICT_NORMAL);      // image is read back by the next kernel
+            bulk_commit();
+        }
         tbx += step_x; tby += step_y;
         if (tbx >= tiles_x) { tbx -= tiles_x; ++tby; }
     }
+    if (tile_out && tid == 0) bulk_wait_all();      // the last tile's store has completed before the CTA exits
 }
 
 #if defined(CRT_TU_GAUSS_PS2)      // launcher: compiled only in the translation unit that owns these kernels (build.py)
 template <int K, int MINB>
 inline int launch_fused_gauss_ps2_t(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
-                                    int has_prev, cudaStream_t st, bool pdl) {
-    const size_t smem = fused_gauss_ps2_smem(K);
+                                    int has_prev, cudaStream_t st, bool pdl, const Ps2Maps* maps) {
     const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1 && !d.noise_on;
-    auto kern = fast ? k_fused_gauss_ps2<K, true, MINB> : k_fused_gauss_ps2<K, false, MINB>;
+    // state tile by TMA: needs the tensor map of the state buffer (or of the pre-warp image) and the tile to fit beside three CTAs
+    static const bool use_tst = env_int("CRT_GPS2_TMA_STATE", 1) != 0;
+    // (measured, run 9: 30.1 -> 29.0 us per 1080p frame with a state to blend; the pre-warp image of the two-pass path is 2 % faster
+    // through per-thread stores, as in round 1)
+    const bool tst = maps && use_tst && state && !q_out && fused_gauss_ps2_smem(K, true) + 16 * 1024 <= 76 * 1024;
+    const size_t smem = fused_gauss_ps2_smem(K, tst);
+    auto kern = tst ? (fast ? k_fused_gauss_ps2<K, true, MINB, true> : k_fused_gauss_ps2<K, false, MINB, true>)
+                    : (fast ? k_fused_gauss_ps2<K, true, MINB, false> : k_fused_gauss_ps2<K, false, MINB, false>);
     // per context and kernel: opt-in shared-memory size, then the number of CTAs the device holds (persistent grid)
     auto it = env.memo.find((const void*)kern);
     if (it == env.memo.end()) {
@@ -239,20 +285,21 @@ inline int launch_fused_gauss_ps2_t(LaunchEnv& env, const Dev& d, const FrameDev
     const int resident = persist ? it->second : (1 << 30);
     const int ntiles = ((d.W + P2_TW - 1) / P2_TW) * ((d.H + P2_TH - 1) / P2_TH);
     const dim3 grid(ntiles < resident ? ntiles : resident);
-    const cudaError_t e = launch_pdl(kern, grid, dim3(P2_NT), smem, st, pdl, d, f, in, out, state, q_out, has_prev);
+    static const CUtensorMap no_map{};
+    const cudaError_t e = launch_pdl(kern, grid, dim3(P2_NT), smem, st, pdl, d, f, in, out, state, q_out, has_prev, tst ? maps->st : no_map);
     return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
 }
 
 inline int run_fused_gauss_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
-                               cudaStream_t st, int* launches, bool pdl = false) {
+                               cudaStream_t st, int* launches, bool pdl = false, const Ps2Maps* maps = nullptr) {
     int rc = 4;
     switch (d.ksize) {
-        case 5: rc = launch_fused_gauss_ps2_t<5, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl); break;
-        case 7: rc = launch_fused_gauss_ps2_t<7, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl); break;
-        case 9: rc = launch_fused_gauss_ps2_t<9, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl); break;
-        case 11: rc = launch_fused_gauss_ps2_t<11, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl); break;
-        case 13: rc = launch_fused_gauss_ps2_t<13, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl); break;
-        case 25: rc = launch_fused_gauss_ps2_t<25, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl); break;
+        case 5: rc = launch_fused_gauss_ps2_t<5, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps); break;
+        case 7: rc = launch_fused_gauss_ps2_t<7, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps); break;
+        case 9: rc = launch_fused_gauss_ps2_t<9, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps); break;
+        case 11: rc = launch_fused_gauss_ps2_t<11, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps); break;
+        case 13: rc = launch_fused_gauss_ps2_t<13, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps); break;
+        case 25: rc = launch_fused_gauss_ps2_t<25, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps); break;
         default: break;
     }
     if (rc != 4) ++*launches;        // an unsupported tap count launches nothing

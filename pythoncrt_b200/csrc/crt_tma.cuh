@@ -81,6 +81,11 @@ __device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, const 
 }
 // wait until all bulk stores of this thread have completed (not only finished reading shared memory)
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// Tiled tensor-map PREFETCH into L2: one instruction per box, no shared memory, no completion to wait for.  Used by kernels
+// that keep their per-thread global loads (no room for another tile buffer) but want them to hit L2 instead of HBM.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

@@ -74,7 +74,7 @@ class CrtEngine:
     # ----------------------------------------------------------- configure --
     def configure(self, params: CrtParams, *, variant: str = "export", triad_cols="auto", vignette="auto",
                   text_rgba: Optional[np.ndarray] = None, text_after: bool = True, noise_mode: str = "inject",
-                  glitch_mode: str = "inject", seed: int = 0, policy: str = "auto", channel_order: str = "rgb") -> "CrtEngine":
+                  glitch_mode: str = "inject", seed: int = 0, policy: str = "auto", channel_order: str = "rgb", shards=1) -> "CrtEngine":
         """Upload parameters and host-built tables.
 
         triad_cols: "auto" builds the table from params.triad_strength/softness the
@@ -85,6 +85,8 @@ class CrtEngine:
             evaluated analytically on the device, anything else is uploaded; None = off.
         noise_mode / glitch_mode: "inject" = draws supplied per frame (the reference's
             own draws, for verification), "generate" = counter-based RNG on the device.
+        shards: intra-GPU temporal shards for long clips given to process() (crt_set_shards): 1 = strictly serial
+            (default), "auto" = up to 4 concurrent shards with a persistence warm-up each, k = at most k.
         channel_order: "rgb" = channel index 0 is R, as the reference assumes (crt_filter.py:289,
             :296-297, :573-575); "bgr" = frames (and state) are B,G,R: the R rules go to index 2.
         """
@@ -96,9 +98,14 @@ class CrtEngine:
         p = params
         self._check(self.lib.crt_set_params(self.ctx, C.byref(c)), "crt_set_params")
         self._check(self.lib.crt_set_policy(self.ctx, {"auto": 0, "staged": 1, "fused": 2}[policy]), "crt_set_policy")
+        self._check(self.lib.crt_set_shards(self.ctx, 0 if shards == "auto" else int(shards)), "crt_set_shards")
         self.params, self.variant, self.noise_mode, self.glitch_mode = p, variant, noise_mode, glitch_mode
         self._c_params = c
         return self
+
+    def set_shards(self, shards) -> None:
+        """Intra-GPU temporal shards for process() on long clips (crt_set_shards): 1 = serial, "auto", or at most k."""
+        self._check(self.lib.crt_set_shards(self.ctx, 0 if shards == "auto" else int(shards)), "crt_set_shards")
 
     # -------------------------------------------------------- frame records --
     def frame_records(self, n: int, *, first_index: int = 0, fps: float = 30.0, phases: Optional[Sequence[float]] = None,

@@ -345,3 +345,51 @@ class _Foreign:
     def __rmul__(self, k):
         from pythoncrt_b200 import effects
         return effects._Scaled(self.arr, k)
+
+
+# ------------------------------------------------------------------------------- intra-GPU temporal shards --
+@pytest.mark.parametrize("name,hw,n", [("cfg1_cli_default", (480, 640), 260), ("cfg2_gauss_grade", (270, 480), 230), ("cfg3_warp", (360, 640), 200),
+                                       ("cfg4_full", (240, 320), 210), ("no_persistence", (480, 640), 200)])
+def test_concurrent_temporal_shards_match_the_serial_run(name, hw, n):
+    """crt_set_shards: a long clip processed as concurrent temporal shards on ONE GPU (own stream + context each, persistence
+    warm-up per shard) against the strictly serial call: at most 1 LSB apart, in a tiny fraction of samples (identical with
+    persistence off), same final state; the generated noise / glitch draws are keyed by global frame index / phase."""
+    import torch
+    from pythoncrt_b200 import CrtEngine
+    import host_emu
+    h, w = hw
+    p = host_emu.oracle_to_product_params(CASES_BY_NAME[name].params)
+    g = torch.Generator(device="cuda").manual_seed(21)
+    frames = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+    kw = dict(variant="export", noise_mode="generate", glitch_mode="generate", seed=5)
+    serial, s_state = CrtEngine(w, h).configure(p, shards=1, **kw).process(frames, fps=30.0, first_index=7)
+    for shards in ("auto", 3):
+        eng = CrtEngine(w, h).configure(p, shards=shards, **kw)
+        out, state = eng.process(frames, fps=30.0, first_index=7)
+        torch.cuda.synchronize()
+        k = int(eng.last_info.reserved[0])
+        assert k == (4 if shards == "auto" else 3), k                     # the clips are long enough to be cut
+        d = (out.to(torch.int16) - serial.to(torch.int16)).abs()
+        if p.persistence == 0.0:
+            assert int(d.max()) == 0
+        else:
+            assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 1e-3, (int(d.max()), float((d > 0).float().mean()))
+            assert int(eng.last_info.reserved[1]) == 5                    # 0.2^5 <= 1/2040
+        assert float((state - s_state).abs().max()) < 1e-3
+        # a second call continues from the returned state like the serial engine does
+        out2, _ = eng.process(frames[:8], state=state, state_valid=True, fps=30.0, first_index=7 + n)
+        ref2, _ = CrtEngine(w, h).configure(p, shards=1, **kw).process(frames[:8], state=s_state.clone(), state_valid=True, fps=30.0, first_index=7 + n)
+        assert int((out2.to(torch.int16) - ref2.to(torch.int16)).abs().max()) <= 1
+        eng.close()
+
+
+def test_short_clips_are_never_sharded():
+    import torch
+    from pythoncrt_b200 import CrtEngine, CrtParams
+    eng = CrtEngine(128, 96).configure(CrtParams(noise_strength=0.0), shards="auto")
+    frames = torch.zeros((40, 96, 128, 3), dtype=torch.uint8, device="cuda")
+    eng.process(frames)
+    assert int(eng.last_info.reserved[0]) == 1
+    eng2 = CrtEngine(128, 96).configure(CrtParams(noise_strength=0.0, persistence=0.95), shards="auto")
+    eng2.process(torch.zeros((600, 96, 128, 3), dtype=torch.uint8, device="cuda"))
+    assert int(eng2.last_info.reserved[0]) == 1          # 149 warm-up frames per shard: not worth it at 600 frames
