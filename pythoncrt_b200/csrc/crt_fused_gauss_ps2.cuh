@@ -61,10 +61,14 @@ CRT_HD bool fused_gauss_ps2_supported(const Dev& d, bool glitch_on) {
 // warp-stall samples on the first use of the per-thread state loads (L2 latency: at 1080p the state lives in L2) and another
 // 10 % on the table staging at kernel entry; with TST the tables also arrive by bulk copies that are only waited for at their
 // first use, after the first tile's input loads are in flight.  24.5 KB more shared memory: still three CTAs per SM.
-template <int K, bool FAST, int MINB, bool TST>
-__global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+template <int K, bool FAST, int MINB, bool TST, int SPEC = 0>
+__global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, FrameDev f_arg, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                            float* __restrict__ state, float* __restrict__ q_out, int has_prev,
                                                            const __grid_constant__ CUtensorMap map_st) {
+    Dev d = d_arg;
+    FrameDev f = f_arg;
+    specialise<SPEC>(d, f);             // SPEC != 0: feature flags become compile-time constants (crt_fused_ps2.cuh)
+    if (SPEC) d.thr_on = 1;             // the specialised variants of this kernel are for a thresholded bloom
     constexpr int R = K / 2, HB = (R + 1) / 2, OFF = R & 1;
     constexpr int NBX = P2_TW / 2 + 2 * HB, NBY = P2_TH / 2 + 2 * HB;
     constexpr int PITCH = (NBY & 3) == 2 ? NBY : NBY + 2;
@@ -273,6 +277,9 @@ inline int launch_fused_gauss_ps2_t(LaunchEnv& env, const Dev& d, const FrameDev
     const size_t smem = fused_gauss_ps2_smem(K, tst);
     auto kern = tst ? (fast ? k_fused_gauss_ps2<K, true, MINB, true> : k_fused_gauss_ps2<K, false, MINB, true>)
                     : (fast ? k_fused_gauss_ps2<K, true, MINB, false> : k_fused_gauss_ps2<K, false, MINB, false>);
+    static const bool use_spec = env_int("CRT_SPEC", 1) != 0;
+    if (K == 9 && use_spec && tst && fast && d.thr_on && spec_matches(SPEC_GRADED, d, f.flicker_on != 0, fast))      // BASELINE configs[1]
+        kern = k_fused_gauss_ps2<K == 9 ? 9 : K, true, MINB, true, K == 9 ? SPEC_GRADED : 0>;
     // per context and kernel: opt-in shared-memory size, then the number of CTAs the device holds (persistent grid)
     auto it = env.memo.find((const void*)kern);
     if (it == env.memo.end()) {

@@ -24,6 +24,52 @@ constexpr int P2_TW = 64, P2_TH = 32;                 // output tile
 constexpr int P2_BW = P2_TW / 2 + 2, P2_BH = P2_TH / 2 + 2;   // blocks incl. one halo block each side (34 x 18)
 constexpr int P2_NT = 256;                            // 16 x 16 threads, 4 x 2 pixels each
 
+// ---- compile-time specialisation of the block kernels ---------------------------------------------------------------
+// The parameter block is generic: every stage is guarded by a run-time flag (colour grading on?, which scanline mode?,
+// analytic vignette or plane?, flicker?).  ncu (round 2, run 13) showed a fifth of the default-chain kernel's instructions
+// to be that generality — constant-bank loads of the flags, uniform compares, branches.  A kernel instantiated with a
+// non-zero SPEC overwrites those flags in its LOCAL copy of the parameter block with the constants of one common feature
+// set; constant propagation then deletes the tests (and the code of stages that are off).  The host launcher picks a SPEC
+// only when the clip's parameters match it exactly (ps2_spec below), so results are bit-identical to the generic kernel.
+enum : int {
+    SP_NOCOLOUR = 1,      // brightness / contrast / gamma / saturation / temperature all identity (:279-305 skipped)
+    SP_ALLCOLOUR = 2,     // all four colour stages on (BASELINE configs[1]'s grade)
+    SP_SCAN1 = 4,         // scanlines: per-row mask (angle 0, thickness 1)
+    SP_SCAN2 = 8,         // scanlines: slanted / shaped plane
+    SP_VIG1 = 16,         // analytic vignette
+    SP_NOFLICKER = 32,
+    SP_RGB = 64,          // channel order RGB
+    SP_FASTTAIL = 128,    // the specialised tail's feature set: triad through the composite LUT, no noise, no text layer
+};
+constexpr int SPEC_DEFAULT = SP_NOCOLOUR | SP_SCAN1 | SP_VIG1 | SP_NOFLICKER | SP_RGB | SP_FASTTAIL;       // the CLI's default chain
+constexpr int SPEC_SLANTED = SP_NOCOLOUR | SP_SCAN2 | SP_VIG1 | SP_NOFLICKER | SP_RGB | SP_FASTTAIL;       // ... with scanline angle / thickness
+constexpr int SPEC_GRADED = SP_ALLCOLOUR | SP_SCAN1 | SP_VIG1 | SP_NOFLICKER | SP_RGB | SP_FASTTAIL;       // ... with the full colour grade
+
+template <int SPEC>
+CRT_HD void specialise(Dev& d, FrameDev& f) {
+    if (SPEC & SP_NOCOLOUR) { d.col_sat = 0; d.col_temp = 0; d.col_bc = 0; d.col_gamma = 0; }
+    if (SPEC & SP_ALLCOLOUR) { d.col_sat = 1; d.col_temp = 1; d.col_bc = 1; d.col_gamma = 1; }
+    if (SPEC & SP_SCAN1) d.scan_mode = 1;
+    if (SPEC & SP_SCAN2) d.scan_mode = 2;
+    if (SPEC & SP_VIG1) d.vig_mode = 1;
+    if (SPEC & SP_NOFLICKER) f.flicker_on = 0;
+    if (SPEC & SP_RGB) d.bgr = 0;
+    if (SPEC & SP_FASTTAIL) { d.triad_mode = 2; d.noise_on = 0; d.text_mode = 0; }
+}
+// does the clip's parameter set match SPEC exactly?  (host; `flicker_on` is a per-clip property: strength > 0 and hz > 0)
+inline bool spec_matches(int spec, const Dev& d, bool flicker_on, bool fast_tail) {
+    const bool nocol = !d.col_sat && !d.col_temp && !d.col_bc && !d.col_gamma, allcol = d.col_sat && d.col_temp && d.col_bc && d.col_gamma;
+    if ((spec & SP_NOCOLOUR) && !nocol) return false;
+    if ((spec & SP_ALLCOLOUR) && !allcol) return false;
+    if ((spec & SP_SCAN1) && d.scan_mode != 1) return false;
+    if ((spec & SP_SCAN2) && d.scan_mode != 2) return false;
+    if ((spec & SP_VIG1) && d.vig_mode != 1) return false;
+    if ((spec & SP_NOFLICKER) && flicker_on) return false;
+    if ((spec & SP_RGB) && d.bgr) return false;
+    if ((spec & SP_FASTTAIL) && !(fast_tail && d.text_mode == 0)) return false;
+    return true;
+}
+
 CRT_HD bool fused_ps2_supported(const Dev& d, bool glitch_on) {
     return d.pix_uniform == 2 && d.even_dims && (d.W & 3) == 0 && !d.warp_on && !glitch_on && d.text_mode == 0 && d.bloom_mode != 2;
 }
@@ -329,11 +375,14 @@ struct Ps2Maps {                 // host-encoded tensor maps (crt_abi.cu)
 };
 
 // THR: the bloom threshold is on (a second block array for the thresholded source; 3 CTAs per SM instead of 4)
-template <bool BLOOM, bool FAST, bool THR>
-__global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+template <bool BLOOM, bool FAST, bool THR, int SPEC = 0>
+__global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg, FrameDev f_arg, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                           float* __restrict__ state, float* __restrict__ q_out, int has_prev,
                                                           const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_st,
                                                           int frame) {
+    Dev d = d_arg;
+    FrameDev f = f_arg;
+    specialise<SPEC>(d, f);             // SPEC != 0: feature flags become compile-time constants (see above)
     extern __shared__ __align__(128) unsigned char dsm[];
     float* s_state = reinterpret_cast<float*>(dsm);                                 // [TH][TW*3]
     uint8_t* s_raw = dsm + P2_ST_BYTES;                                               // [2][18][256]
@@ -514,6 +563,11 @@ inline int run_fused_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const 
         auto kern = !thr ? (d.bloom_mode == 1 ? (fast ? k_fused_ps2_pipe<true, true, false> : k_fused_ps2_pipe<true, false, false>)
                                               : (fast ? k_fused_ps2_pipe<false, true, false> : k_fused_ps2_pipe<false, false, false>))
                          : (fast ? k_fused_ps2_pipe<true, true, true> : k_fused_ps2_pipe<true, false, true>);
+        static const bool use_spec = env_int("CRT_SPEC", 1) != 0;
+        if (use_spec && !thr && d.bloom_mode == 1 && fast) {            // feature sets with a compile-time specialisation
+            if (spec_matches(SPEC_DEFAULT, d, f.flicker_on != 0, fast)) kern = k_fused_ps2_pipe<true, true, false, SPEC_DEFAULT>;
+            else if (spec_matches(SPEC_SLANTED, d, f.flicker_on != 0, fast)) kern = k_fused_ps2_pipe<true, true, false, SPEC_SLANTED>;
+        }
         // the opt-in shared-memory size is a per-device, per-kernel attribute: set once per context and kernel
         if (env.raise((const void*)kern, P2_PIPE_SMEM) &&
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM) != cudaSuccess) return 2;
