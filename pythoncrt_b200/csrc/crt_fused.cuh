@@ -168,6 +168,8 @@ __device__ __forceinline__ uint32_t quantise_fast(float v) { return quantise_bit
 __device__ __forceinline__ uint32_t pack4(float a, float b, float c, float e) {
     return __byte_perm(__byte_perm(quantise_bits(a), quantise_bits(b), 0x0040), __byte_perm(quantise_bits(c), quantise_bits(e), 0x0040), 0x5410);
 }
+// the same with a table offset folded into the magic number (2^23 + offset, offset + 1024 < 4096)
+__device__ __forceinline__ int lut_index_magic(float v01, float magic) { return (int)(__float_as_uint(__fmaf_rz(v01, 1024.0f, magic)) & 0xfffu); }
 __device__ __forceinline__ int lut_index_fast(float v01) { return (int)(__float_as_uint(__fmaf_rz(v01, 1024.0f, 8388608.0f)) & 0x7ffu); }
 
 // L2 prefetch of a tile's persistence-state rows (one 128-byte line per thread).  MEASURED (round 1, run 23):

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
     constexpr int MC = ((2 * R + 1 + OFF) >> 1) + 1;              // distinct block rows under 2 output rows' taps
     extern __shared__ __align__(128) float sm[];
     __shared__ __align__(16) float s_lut[2 * 1028];
-    __shared__ __align__(16) int s_sel[3][12];
+    __shared__ __align__(16) float s_sel[3][12];
     float* const s_fwd = s_lut;
     float* const s_inv = s_lut + 1028;
     __shared__ float s_unit[256];

@@ -81,7 +81,7 @@ CRT_HD bool fused_ps2_supported(const Dev& d, bool glitch_on) {
 struct NoRowHook { __device__ __forceinline__ void operator()(int) const {} };
 template <bool BLOOM, bool FAST, typename BloomFn, typename RowFn = NoRowHook>
 __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, const MaskTabs& mt, const float* s_fwd, const float* s_inv,
-                                               const int (*s_sel)[12], float* __restrict__ state, uint8_t* __restrict__ out, float* __restrict__ q_out, int has_prev,
+                                               const float (*s_sel)[12], float* __restrict__ state, uint8_t* __restrict__ out, float* __restrict__ q_out, int has_prev,
                                                int ox0, int oy0, int ox1, int oy1, int xb, int y0, const float (&t1)[2][3], BloomFn&& bloom,
                                                float* s_prev = nullptr, bool state_in_smem = false, RowFn&& row_begin = RowFn(),
                                                int s_pitch = P2_TW * 3) {
@@ -128,12 +128,15 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
     const bool fast = FAST && ox0 >= d.comp_x0 && ox1 <= d.comp_x1;        // block-uniform
     if (fast) {
         float cvig[4], cscan[4];
-        // composite table (bright: s_fwd, dim: s_inv == s_fwd + 1028) per column and channel, as index offsets
+        // composite table (bright: s_fwd, dim: s_inv == s_fwd + 1028) per column and channel: the table offset rides on the magic
+        // number of the index computation (2^23 + offset: the mantissa of fma.rz(v, 1024, magic) is offset + floor(1024 v)),
         // looked up by the quad's mask phase (s_sel, filled once per CTA by ps2_fill_sel)
+        // (measured and NOT adopted, runs 16-17: folding the blend factor (1 - p) into the mask multiplier and the unclipped
+        // vignette into one fma per pixel — five instructions per pixel fewer, but 50-200 bytes of spills at 64 registers: slower)
         const int ph0 = xb - 3 * (int)__umulhi((unsigned)xb, 0x55555556u);     // xb % 3
-        const int4* selp = reinterpret_cast<const int4*>(s_sel[ph0]);
-        const int4 sa = selp[0], sb = selp[1], sc = selp[2];
-        const int off[4][3] = {{sa.x, sa.y, sa.z}, {sa.w, sb.x, sb.y}, {sb.z, sb.w, sc.x}, {sc.y, sc.z, sc.w}};
+        const float4* selp = reinterpret_cast<const float4*>(s_sel[ph0]);
+        const float4 sa = selp[0], sb = selp[1], sc = selp[2];
+        const float mg[4][3] = {{sa.x, sa.y, sa.z}, {sa.w, sb.x, sb.y}, {sb.z, sb.w, sc.x}, {sc.y, sc.z, sc.w}};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             cvig[k] = d.vig_mode ? mt.col_vig[xb - ox0 + k] : 0.f;
@@ -159,9 +162,9 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
                     const float shaped = (d.scan_inv_sharp == 1.0f) ? sv : __powf(sv, d.scan_inv_sharp);
                     m *= __fmaf_rn(-d.scan_strength, shaped, 1.0f);
                 }
-                v.x = __saturatef(s_fwd[lut_index_fast(__saturatef(v.x)) + off[k][0]] * m);
-                v.y = __saturatef(s_fwd[lut_index_fast(__saturatef(v.y)) + off[k][1]] * m);
-                v.z = __saturatef(s_fwd[lut_index_fast(__saturatef(v.z)) + off[k][2]] * m);
+                v.x = __saturatef(s_fwd[lut_index_magic(__saturatef(v.x), mg[k][0])] * m);
+                v.y = __saturatef(s_fwd[lut_index_magic(__saturatef(v.y), mg[k][1])] * m);
+                v.z = __saturatef(s_fwd[lut_index_magic(__saturatef(v.z), mg[k][2])] * m);
                 return v;
             };
             finish(r, y, pixel);
@@ -181,11 +184,11 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
     }
 }
 
-// s_sel[p][3 k + ch]: index offset of the table column k (0..3) of a quad with xb % 3 == p uses for channel ch
-__device__ __forceinline__ void ps2_fill_sel(int (*s_sel)[12], int tid, int bgr) {
+// s_sel[p][3 k + ch]: index magic (2^23 + table offset) column k (0..3) of a quad with xb % 3 == p uses for channel ch
+__device__ __forceinline__ void ps2_fill_sel(float (*s_sel)[12], int tid, int bgr) {
     if (tid < 36) {
         const int p = tid / 12, e = tid - 12 * p, k = e / 3, ch = e - 3 * k;
-        s_sel[p][e] = ((p + k) % 3 == (bgr ? 2 - ch : ch)) ? 0 : 1028;
+        s_sel[p][e] = ((p + k) % 3 == (bgr ? 2 - ch : ch)) ? 8388608.0f : 8388608.0f + 1028.0f;      // 2^23 (+ offset of the dim table)
     }
 }
 
@@ -197,7 +200,7 @@ template <bool BLOOM, bool FAST, int MINB>
 __global__ void __launch_bounds__(P2_NT, MINB) k_fused_ps2(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                      float* __restrict__ state, float* __restrict__ q_out, int has_prev) {
     __shared__ __align__(16) float s_lut[2 * 1028];
-    __shared__ __align__(16) int s_sel[3][12];
+    __shared__ __align__(16) float s_sel[3][12];
     float* const s_fwd = s_lut;
     float* const s_inv = s_lut + 1028;
     __shared__ float s_unit[256];
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
     float* s_state = reinterpret_cast<float*>(dsm);                                 // [TH][TW*3]
     uint8_t* s_raw = dsm + P2_ST_BYTES;                                               // [2][18][256]
     __shared__ __align__(16) float s_lut[2 * 1028];
-    __shared__ __align__(16) int s_sel[3][12];
+    __shared__ __align__(16) float s_sel[3][12];
     float* const s_fwd = s_lut;
     float* const s_inv = s_lut + 1028;
     __shared__ float s_unit[256];

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(WP_NT, 2) k_warp_ps2(Dev d, FrameDev f, const 
                                                        float* __restrict__ state, int has_prev, WarpPs2Geo g) {
     extern __shared__ __align__(16) float wsm[];
     __shared__ __align__(16) float s_lut[2 * 1028];
-    __shared__ __align__(16) int s_sel[3][12];
+    __shared__ __align__(16) float s_sel[3][12];
     float* const s_fwd = s_lut;
     float* const s_inv = s_lut + 1028;
     __shared__ float s_unit[256];
