@@ -68,7 +68,6 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
     Dev d = d_arg;
     FrameDev f = f_arg;
     specialise<SPEC>(d, f);             // SPEC != 0: feature flags become compile-time constants (crt_fused_ps2.cuh)
-    if (SPEC) d.thr_on = 1;             // the specialised variants of this kernel are for a thresholded bloom
     constexpr int R = K / 2, HB = (R + 1) / 2, OFF = R & 1;
     constexpr int NBX = P2_TW / 2 + 2 * HB, NBY = P2_TH / 2 + 2 * HB;
     constexpr int PITCH = (NBY & 3) == 2 ? NBY : NBY + 2;
@@ -268,7 +267,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
 template <int K, int MINB>
 inline int launch_fused_gauss_ps2_t(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
                                     int has_prev, cudaStream_t st, bool pdl, const Ps2Maps* maps) {
-    const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1 && !d.noise_on;
+    const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1;
     // state tile by TMA: needs the tensor map of the state buffer (or of the pre-warp image) and the tile to fit beside three CTAs
     static const bool use_tst = env_int("CRT_GPS2_TMA_STATE", 1) != 0;
     // (measured, run 9: 30.1 -> 29.0 us per 1080p frame with a state to blend; the pre-warp image of the two-pass path is 2 % faster
@@ -278,8 +277,11 @@ inline int launch_fused_gauss_ps2_t(LaunchEnv& env, const Dev& d, const FrameDev
     auto kern = tst ? (fast ? k_fused_gauss_ps2<K, true, MINB, true> : k_fused_gauss_ps2<K, false, MINB, true>)
                     : (fast ? k_fused_gauss_ps2<K, true, MINB, false> : k_fused_gauss_ps2<K, false, MINB, false>);
     static const bool use_spec = env_int("CRT_SPEC", 1) != 0;
-    if (K == 9 && use_spec && tst && fast && d.thr_on && spec_matches(SPEC_GRADED, d, f.flicker_on != 0, fast))      // BASELINE configs[1]
+    if (K == 9 && use_spec && tst && fast && spec_matches(SPEC_GRADED, d, f.flicker_on != 0, fast))      // BASELINE configs[1]
         kern = k_fused_gauss_ps2<K == 9 ? 9 : K, true, MINB, true, K == 9 ? SPEC_GRADED : 0>;
+    // first pass of the two-pass path with every stage on: BASELINE configs[3] (K = 9) and [4] (K = 25)
+    if ((K == 9 || K == 25) && use_spec && !tst && q_out && fast && spec_matches(SPEC_FULL | SP_THR * (K == 9), d, f.flicker_on != 0, fast))
+        kern = k_fused_gauss_ps2<(K == 9 || K == 25) ? K : 9, true, MINB, false, (K == 9 || K == 25) ? (SPEC_FULL | SP_THR * (K == 9)) : 0>;
     // per context and kernel: opt-in shared-memory size, then the number of CTAs the device holds (persistent grid)
     auto it = env.memo.find((const void*)kern);
     if (it == env.memo.end()) {

@@ -39,11 +39,16 @@ enum : int {
     SP_VIG1 = 16,         // analytic vignette
     SP_NOFLICKER = 32,
     SP_RGB = 64,          // channel order RGB
-    SP_FASTTAIL = 128,    // the specialised tail's feature set: triad through the composite LUT, no noise, no text layer
+    SP_FASTTAIL = 128,    // the specialised tail's feature set: triad through the composite LUT, no text layer
+    SP_NONOISE = 256,
+    SP_GRAIN = 512,       // noise on, grain_size > 1 (bilinear up-scale of the draw plane)
+    SP_FLICKER = 1024,
+    SP_THR = 2048,        // bloom threshold on
 };
-constexpr int SPEC_DEFAULT = SP_NOCOLOUR | SP_SCAN1 | SP_VIG1 | SP_NOFLICKER | SP_RGB | SP_FASTTAIL;       // the CLI's default chain
-constexpr int SPEC_SLANTED = SP_NOCOLOUR | SP_SCAN2 | SP_VIG1 | SP_NOFLICKER | SP_RGB | SP_FASTTAIL;       // ... with scanline angle / thickness
-constexpr int SPEC_GRADED = SP_ALLCOLOUR | SP_SCAN1 | SP_VIG1 | SP_NOFLICKER | SP_RGB | SP_FASTTAIL;       // ... with the full colour grade
+constexpr int SPEC_DEFAULT = SP_NOCOLOUR | SP_SCAN1 | SP_VIG1 | SP_NOFLICKER | SP_RGB | SP_FASTTAIL | SP_NONOISE;      // the CLI's default chain
+constexpr int SPEC_SLANTED = SP_NOCOLOUR | SP_SCAN2 | SP_VIG1 | SP_NOFLICKER | SP_RGB | SP_FASTTAIL | SP_NONOISE;      // ... with scanline angle / thickness
+constexpr int SPEC_GRADED = SP_ALLCOLOUR | SP_SCAN1 | SP_VIG1 | SP_NOFLICKER | SP_RGB | SP_FASTTAIL | SP_NONOISE | SP_THR;     // BASELINE configs[1]
+constexpr int SPEC_FULL = SP_ALLCOLOUR | SP_SCAN2 | SP_VIG1 | SP_FLICKER | SP_RGB | SP_FASTTAIL | SP_GRAIN;             // BASELINE configs[3], [4]: everything on
 
 template <int SPEC>
 CRT_HD void specialise(Dev& d, FrameDev& f) {
@@ -54,7 +59,11 @@ CRT_HD void specialise(Dev& d, FrameDev& f) {
     if (SPEC & SP_VIG1) d.vig_mode = 1;
     if (SPEC & SP_NOFLICKER) f.flicker_on = 0;
     if (SPEC & SP_RGB) d.bgr = 0;
-    if (SPEC & SP_FASTTAIL) { d.triad_mode = 2; d.noise_on = 0; d.text_mode = 0; }
+    if (SPEC & SP_FASTTAIL) { d.triad_mode = 2; d.text_mode = 0; }
+    if (SPEC & SP_NONOISE) d.noise_on = 0;
+    if (SPEC & SP_GRAIN) d.noise_on = 1;
+    if (SPEC & SP_FLICKER) f.flicker_on = 1;
+    if (SPEC & SP_THR) d.thr_on = 1;
 }
 // does the clip's parameter set match SPEC exactly?  (host; `flicker_on` is a per-clip property: strength > 0 and hz > 0)
 inline bool spec_matches(int spec, const Dev& d, bool flicker_on, bool fast_tail) {
@@ -67,6 +76,10 @@ inline bool spec_matches(int spec, const Dev& d, bool flicker_on, bool fast_tail
     if ((spec & SP_NOFLICKER) && flicker_on) return false;
     if ((spec & SP_RGB) && d.bgr) return false;
     if ((spec & SP_FASTTAIL) && !(fast_tail && d.text_mode == 0)) return false;
+    if ((spec & SP_NONOISE) && d.noise_on) return false;
+    if ((spec & SP_GRAIN) && !(d.noise_on && d.nz_x)) return false;
+    if ((spec & SP_FLICKER) && !flicker_on) return false;
+    if ((spec & SP_THR) && !d.thr_on) return false;
     return true;
 }
 
@@ -165,6 +178,10 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
                 v.x = __saturatef(s_fwd[lut_index_magic(__saturatef(v.x), mg[k][0])] * m);
                 v.y = __saturatef(s_fwd[lut_index_magic(__saturatef(v.y), mg[k][1])] * m);
                 v.z = __saturatef(s_fwd[lut_index_magic(__saturatef(v.z), mg[k][2])] * m);
+                if (d.noise_on) {                   // the same draw on all three channels (:646-648)
+                    const float n = noise_at(d, f, y, xb + k);
+                    v.x = __saturatef(v.x + n); v.y = __saturatef(v.y + n); v.z = __saturatef(v.z + n);
+                }
                 return v;
             };
             finish(r, y, pixel);
@@ -557,7 +574,7 @@ inline int run_fused_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const 
                          cudaStream_t st, int* launches, bool pdl = false, const Ps2Maps* maps = nullptr) {
     dim3 grid((d.W + P2_TW - 1) / P2_TW, (d.H + P2_TH - 1) / P2_TH);
     const int ntiles = (int)(grid.x * grid.y);
-    const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1 && !d.noise_on;
+    const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1;
     // TMA-pipelined variant (4 CTAs per SM, 3 with the bloom threshold on): pays off when there is a state to fetch and
     // every CTA walks over several tiles
     static const int pipe_min_tiles = env_int("CRT_PIPE_MIN_TILES", 256);      // measured: wins at 720p (460 tiles, +1.5 %), 1080p (+15 %) and 4K, neutral at VGA (150)

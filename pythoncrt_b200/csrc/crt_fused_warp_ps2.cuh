@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(WP_NT, 2) k_warp_ps2(Dev d, FrameDev f, const 
 #if defined(CRT_TU_WARP_PS2)      // launcher: compiled only in crt_tu_warp_ps2.cu
 inline int run_warp_ps2(LaunchEnv& env, const WarpPs2Plan& pl, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state,
                         int has_prev, cudaStream_t st, int* launches, bool pdl) {
-    const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1 && !d.noise_on;
+    const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1;
     const bool thr = d.bloom_mode == 1 && d.thr_on;
     auto kern = d.bloom_mode == 1 ? (thr ? (fast ? k_warp_ps2<true, true, true> : k_warp_ps2<true, false, true>)
                                          : (fast ? k_warp_ps2<true, true, false> : k_warp_ps2<true, false, false>))
