@@ -96,48 +96,56 @@ __device__ __forceinline__ float uniform_at(uint64_t seed, uint64_t frame_index,
 
 // Glitch offsets with the distribution of the reference's generators
 // (gui: crt_filter.py:672-679, export: :845-853), drawn from Philox instead of
-// numpy's PCG64.  One block; the export variant's random walk is a block scan.
-constexpr int GLITCH_THREADS = 1024;
+// numpy's PCG64, keyed by the reference's own seed (crt_abi.cu glitch_key).
+// gui: one offset per row, rows spread over the grid.  export: offset = rint(walk[row] + N(row, segment) * 0.7 amp) with
+// walk = clip(cumsum(N(0,1)) * 0.1, +-0.4 amp) a random walk down the band.  Every CTA owns GLITCH_ROWS rows; it first
+// rebuilds the walk's prefix for rows [0, its last row] (one N(0,1) per row, a block scan: at most ~2000 draws) and then
+// fills its rows' segments.  Round 1 ran this on ONE CTA: 63 us per 4K frame, 241 us at 8K (ncu launch list, run 20) —
+// a quarter of the full chain's frame; spread over the grid it is a few microseconds.
+constexpr int GLITCH_THREADS = 256;
+constexpr int GLITCH_ROWS = 8;
 __global__ void __launch_bounds__(GLITCH_THREADS) k_glitch_gen(int32_t* __restrict__ offs, int rows, int nseg, int variant, float amp_px,
-                                                               uint64_t seed, uint64_t frame_index) {
-    extern __shared__ float walk[];          // [rows]
-    __shared__ float warp_tot[32];
+                                                               uint64_t seed, uint64_t key) {
+    extern __shared__ float walk[];          // [rows up to this CTA's last row]
+    __shared__ float warp_tot[GLITCH_THREADS / 32];
     const int t = threadIdx.x;
     const float frows = fmaxf(1.0f, (float)rows);
     if (variant == 0) {                      // gui: one offset per row
-        for (int rr = t; rr < rows; rr += GLITCH_THREADS) {
+        const int rr = blockIdx.x * GLITCH_THREADS + t;
+        if (rr < rows) {
             float amp = amp_px * expf(-3.0f * ((float)rr / frows));
-            float base = clampf(0.5f * normal_at(seed, frame_index, rr, 0, 1), -1.0f, 1.0f);
-            if (uniform_at(seed, frame_index, rr, 2) < 0.03f) base += uniform_at(seed, frame_index, rr, 3) < 0.5f ? -1.0f : 1.0f;
+            float base = clampf(0.5f * normal_at(seed, key, rr, 0, 1), -1.0f, 1.0f);
+            if (uniform_at(seed, key, rr, 2) < 0.03f) base += uniform_at(seed, key, rr, 3) < 0.5f ? -1.0f : 1.0f;
             offs[rr] = (int)rintf(clampf(base * amp, -amp, amp));
         }
         return;
     }
-    // export: walk = clip(cumsum(N(0,1)) * 0.1, +-0.4 amp)
-    const int per = (rows + GLITCH_THREADS - 1) / GLITCH_THREADS;
-    const int r0 = t * per, r1 = imin(rows, r0 + per);
+    // export: prefix of the walk for rows [0, r1), each thread a contiguous run of rows
+    const int r0 = blockIdx.x * GLITCH_ROWS, r1 = imin(rows, r0 + GLITCH_ROWS);
+    const int per = (r1 + GLITCH_THREADS - 1) / GLITCH_THREADS;
+    const int a = t * per, b = imin(r1, a + per);
     float local = 0.f;
-    for (int rr = r0; rr < r1; ++rr) { local += normal_at(seed, frame_index, rr, 0, 1); walk[rr] = local; }
+    for (int rr = a; rr < b; ++rr) { local += normal_at(seed, key, rr, 0, 1); walk[rr] = local; }
     float incl = local;
     for (int o = 1; o < 32; o <<= 1) { float n = __shfl_up_sync(0xffffffffu, incl, o); if ((t & 31) >= o) incl += n; }
     if ((t & 31) == 31) warp_tot[t >> 5] = incl;
     __syncthreads();
     if (t < 32) {
-        float w = warp_tot[t], wi = w;
+        float w = t < GLITCH_THREADS / 32 ? warp_tot[t] : 0.f, wi = w;
         for (int o = 1; o < 32; o <<= 1) { float n = __shfl_up_sync(0xffffffffu, wi, o); if (t >= o) wi += n; }
-        warp_tot[t] = wi - w;                // exclusive prefix over warps
+        if (t < GLITCH_THREADS / 32) warp_tot[t] = wi - w;       // exclusive prefix over warps
     }
     __syncthreads();
     const float base = warp_tot[t >> 5] + (incl - local);
-    for (int rr = r0; rr < r1; ++rr) {
+    for (int rr = imax(a, r0); rr < b; ++rr) {                   // only this CTA's rows are needed below
         float amp = amp_px * (1.0f - (float)rr / frows);
         walk[rr] = clampf((walk[rr] + base) * 0.1f, -amp * 0.4f, amp * 0.4f);
     }
     __syncthreads();
-    for (int e = t; e < rows * nseg; e += GLITCH_THREADS) {
-        int rr = e / nseg, sg = e - rr * nseg;
+    for (int e = t; e < (r1 - r0) * nseg; e += GLITCH_THREADS) {
+        const int rr = r0 + e / nseg, sg = e - (e / nseg) * nseg;
         float amp = amp_px * (1.0f - (float)rr / frows);
-        offs[e] = (int)rintf(walk[rr] + normal_at(seed, frame_index, rr, sg + 1, 4) * (amp * 0.7f));
+        offs[(size_t)rr * nseg + sg] = (int)rintf(walk[rr] + normal_at(seed, key, rr, sg + 1, 4) * (amp * 0.7f));
     }
 }
 

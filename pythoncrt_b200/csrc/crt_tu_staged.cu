@@ -31,7 +31,8 @@ int launch_noise_gen(float* plane, int n_cells, uint64_t seed, uint64_t frame_in
 }
 
 int launch_glitch_gen(int32_t* offs, int rows, int nseg, int variant, float amp_px, uint64_t seed, uint64_t key, cudaStream_t st) {
-    k_glitch_gen<<<1, GLITCH_THREADS, (size_t)rows * sizeof(float), st>>>(offs, rows, nseg, variant, amp_px, seed, key);
+    const int grid = variant == 0 ? (rows + GLITCH_THREADS - 1) / GLITCH_THREADS : (rows + GLITCH_ROWS - 1) / GLITCH_ROWS;
+    k_glitch_gen<<<grid, GLITCH_THREADS, (size_t)rows * sizeof(float), st>>>(offs, rows, nseg, variant, amp_px, seed, key);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
