@@ -169,7 +169,7 @@ def run_reference_arm(args, wl):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": info["cpu_count"], "kind": info["kind"], "sample": sample,
                              "worker_threads": info["workers"], "cv2_threads": info["cv2_threads"], "numpy": info["numpy"], "cv2": info["cv2"]},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     return 0
 
 
@@ -381,9 +381,13 @@ def main() -> int:
         }
         from pythoncrt_b200 import clip as _clip
         line["halo_frames_rank_gt0"] = _clip.halo_frames(product_params(wl["over"]).persistence)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)       # flushed before any teardown: the line must survive whatever the exit path does
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
     return 0
 
 
