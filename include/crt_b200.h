@@ -201,6 +201,14 @@ int crt_process_host(crt_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, const cr
                      crt_launch_info* info);
 int crt_reset_state(crt_ctx* ctx);
 
+/*
+ * Persistence state kept from frames of another size (the GUI's preview window was resized): apply_crt_effect resizes it
+ * with cv2.resize(prev, (w, h), INTER_LINEAR) before the blend (:689-690).  d_src float32 [src_height][src_width][3] ->
+ * d_dst float32 [H][W][3] of this context, OpenCV's bilinear arithmetic (half-pixel centres, edge clamp, rows first).
+ * Synchronous on `stream`.
+ */
+int crt_resize_state(crt_ctx* ctx, const float* d_src, int src_width, int src_height, float* d_dst, void* stream);
+
 /* Timing hooks for bench.py: while enabled, CUDA events are recorded (on the
  * launch stream) around ALL kernels of a frame (generators, first pass, gather),
  * up to max_samples frames.  crt_profile_end synchronises them and returns the

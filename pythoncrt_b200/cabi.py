@@ -21,7 +21,7 @@ POLICY_AUTO, POLICY_STAGED, POLICY_FUSED = 0, 1, 2
 
 # every symbol include/crt_b200.h declares
 EXPORTS = ("crt_abi_version", "crt_create", "crt_destroy", "crt_last_error", "crt_set_params", "crt_set_table",
-           "crt_set_policy", "crt_set_shards", "crt_process", "crt_process_static", "crt_process_host", "crt_reset_state",
+           "crt_set_policy", "crt_set_shards", "crt_process", "crt_process_static", "crt_process_host", "crt_reset_state", "crt_resize_state",
            "crt_generate_noise", "crt_generate_glitch", "crt_profile_begin", "crt_profile_end", "crt_profile_sample_every")
 
 
@@ -106,6 +106,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.crt_process_host.argtypes = [vp, vp, vp, C.POINTER(CrtFrameC), i32, C.POINTER(CrtLaunchInfoC)]
     lib.crt_reset_state.restype = C.c_int
     lib.crt_reset_state.argtypes = [vp]
+    lib.crt_resize_state.restype = C.c_int
+    lib.crt_resize_state.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.crt_generate_noise.restype = C.c_int
     lib.crt_generate_noise.argtypes = [vp, u64, vp, vp]
     lib.crt_generate_glitch.restype = C.c_int

@@ -706,6 +706,21 @@ int crt_process_host(crt_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, const cr
     return CRT_OK;
 }
 
+int crt_resize_state(crt_ctx* ctx, const float* d_src, int src_width, int src_height, float* d_dst, void* stream) {
+    if (!ctx || !d_src || !d_dst || src_width < 1 || src_height < 1) return CRT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const std::vector<Lerp1> hx = linear_coords(ctx->W, src_width), hy = linear_coords(ctx->H, src_height);
+    Lerp1* d_c = nullptr;                       // [W + H] coordinate tables; rare call (the preview window was resized): allocate and free
+    CU(cudaMallocAsync((void**)&d_c, (hx.size() + hy.size()) * sizeof(Lerp1), st));
+    CU(cudaMemcpyAsync(d_c, hx.data(), hx.size() * sizeof(Lerp1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_c + hx.size(), hy.data(), hy.size() * sizeof(Lerp1), cudaMemcpyHostToDevice, st));
+    const int rc = launch_resize_state(d_src, src_width, d_dst, ctx->W, ctx->H, d_c, d_c + hx.size(), st);
+    CU(cudaStreamSynchronize(st));              // the host tables are locals: the copies must have left them
+    CU(cudaFreeAsync(d_c, st));
+    return rc ? fail(ctx, CRT_ERR_CUDA, std::string("state resize launch failed: ") + cudaGetErrorString(cudaGetLastError())) : CRT_OK;
+}
+
 int crt_profile_begin(crt_ctx* ctx, int max_samples) {
     if (!ctx || max_samples < 1) return CRT_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));

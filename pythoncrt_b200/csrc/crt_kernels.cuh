@@ -69,6 +69,24 @@ __global__ void __launch_bounds__(256) k_output(Dev d, FrameDev f, const uint8_t
     finish_pixel(d, v, has_prev, state, out, y, x);
 }
 
+// ---- persistence state of another frame size -> this frame size (GUI: cv2.resize INTER_LINEAR, crt_filter.py:689-690) ----
+// cv2's arithmetic (oracle/cv_restated.py resize_linear): coordinates in double, float32 weights, rows first, every lerp
+// fma(q - p, w, p).  cx / cy are the per-axis coordinate tables (crt_derive.h linear_coords).
+__global__ void __launch_bounds__(256) k_resize_state(const float* __restrict__ src, int sw, float* __restrict__ dst, int dw, int dh,
+                                                      const Lerp1* __restrict__ cx, const Lerp1* __restrict__ cy) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const Lerp1 ax = cx[x], ay = cy[y];
+    const float* r0 = src + (size_t)ay.s0 * sw * 3;
+    const float* r1 = src + (size_t)ay.s1 * sw * 3;
+    float* o = dst + ((size_t)y * dw + x) * 3;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float a = lerp_cv(r0[ax.s0 * 3 + ch], r0[ax.s1 * 3 + ch], ax.w), b = lerp_cv(r1[ax.s0 * 3 + ch], r1[ax.s1 * 3 + ch], ax.w);
+        o[ch] = lerp_cv(a, b, ay.w);
+    }
+}
+
 // ---- counter-based generators ---------------------------------------------------------------
 // N(0,1) plane [gh][gw] keyed (seed, frame_index, cell): four cells per Philox call.
 __global__ void __launch_bounds__(256) k_noise_gen(float* __restrict__ plane, int n_cells, uint64_t seed, uint64_t frame_index) {

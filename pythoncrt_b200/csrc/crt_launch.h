@@ -53,6 +53,7 @@ int launch_gather_box(LaunchEnv& env, const Dev& d, const FrameDev& f, const flo
 // staged kernels: bloom plane(s), pre-warp image, output; *dominant_first = launches before the output kernel
 int launch_staged(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, int has_prev, float* img,
                   const Scratch& s, cudaStream_t st, int* launches);
+int launch_resize_state(const float* src, int sw, float* dst, int dw, int dh, const Lerp1* cx, const Lerp1* cy, cudaStream_t st);
 int launch_noise_gen(float* plane, int n_cells, uint64_t seed, uint64_t frame_index, cudaStream_t st);
 int launch_glitch_gen(int32_t* offs, int rows, int nseg, int variant, float amp_px, uint64_t seed, uint64_t key, cudaStream_t st);
 

@@ -25,6 +25,11 @@ int launch_staged(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
+int launch_resize_state(const float* src, int sw, float* dst, int dw, int dh, const Lerp1* cx, const Lerp1* cy, cudaStream_t st) {
+    k_resize_state<<<dim3((dw + 31) / 32, (dh + 7) / 8), dim3(32, 8), 0, st>>>(src, sw, dst, dw, dh, cx, cy);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
 int launch_noise_gen(float* plane, int n_cells, uint64_t seed, uint64_t frame_index, cudaStream_t st) {
     k_noise_gen<<<((n_cells + 3) / 4 + 255) / 256, 256, 0, st>>>(plane, n_cells, seed, frame_index);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;

@@ -154,11 +154,11 @@ def apply_crt_effect(frame, scanline_strength, triad_mask, triad_gamma, triad_pr
     if isinstance(state_prev, DeviceState) and state_prev.shape == (h, w, 3):
         state, valid = state_prev.tensor, True
     elif state_prev is not None:
-        prev = np.asarray(state_prev, dtype=np.float32)
-        if prev.shape != (h, w, 3):
-            import cv2  # the reference resizes a stale state on the host (:689-690)
-            prev = cv2.resize(prev, (w, h), interpolation=cv2.INTER_LINEAR)
-        state, valid = torch.from_numpy(np.ascontiguousarray(prev)).to(eng._dev_in.device), True
+        prev = state_prev.tensor if isinstance(state_prev, DeviceState) else \
+            torch.from_numpy(np.ascontiguousarray(np.asarray(state_prev, dtype=np.float32))).to(eng._dev_in.device)
+        if tuple(prev.shape) != (h, w, 3):       # a stale state of another preview size: cv2.resize(INTER_LINEAR) (:689-690), on the device
+            prev = eng.resize_state(prev)
+        state, valid = prev, True
     else:
         state, valid = eng.new_state(), False
     eng._pin_in.numpy()[...] = frame

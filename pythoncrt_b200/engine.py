@@ -218,6 +218,17 @@ class CrtEngine:
         self.kernels_launched += self.last_info.kernels_launched
         return out
 
+    def resize_state(self, state):
+        """A float32 CUDA state [h0][w0][3] of another frame size -> this engine's size, as the reference's GUI chain does
+        with cv2.resize(INTER_LINEAR) (crt_filter.py:689-690); on the device (crt_resize_state)."""
+        torch = _torch()
+        src = state.contiguous().to(torch.float32)
+        dst = self.new_state()
+        stream = torch.cuda.current_stream(dst.device).cuda_stream
+        self._check(self.lib.crt_resize_state(self.ctx, src.data_ptr(), int(src.shape[1]), int(src.shape[0]), dst.data_ptr(),
+                                              C.c_void_p(stream)), "crt_resize_state")
+        return dst
+
     def reset_state(self) -> None:
         """'state_prev = None' for the host-buffer path (crt_filter.py:1765)."""
         self._check(self.lib.crt_reset_state(self.ctx), "crt_reset_state")

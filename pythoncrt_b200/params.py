@@ -124,39 +124,19 @@ class CrtParams:
     # ------------------------------------------------------------ CLI side --
     @staticmethod
     def cli_parser() -> argparse.ArgumentParser:
-        """The effect flags of parse_args (crt_filter.py:1160-1205), same names and defaults."""
+        """The effect flags of parse_args (crt_filter.py:1160-1205): same names, types and defaults, from CLI_SURFACE."""
         p = argparse.ArgumentParser(add_help=False)
-        p.add_argument("--scanline-strength", type=float, default=0.6)
-        p.add_argument("--triad-strength", type=float, default=0.35)
-        p.add_argument("--triad-gamma", type=float, default=2.2)
-        p.add_argument("--triad-preserve-luma", action="store_true")
-        p.add_argument("--triad-softness", type=float, default=0.5)
-        p.add_argument("--aberration-px", type=int, default=1)
-        p.add_argument("--bloom-sigma", type=float, default=1.2)
-        p.add_argument("--bloom-strength", type=float, default=0.25)
-        p.add_argument("--bloom-threshold", type=float, default=0.0)
-        p.add_argument("--noise-strength", type=float, default=1.5)
-        p.add_argument("--vignette-strength", type=float, default=0.25)
-        p.add_argument("--persistence", type=float, default=0.2)
-        p.add_argument("--scanline-speed", type=float, default=30.0)
-        p.add_argument("--scanline-period", type=float, default=2.0)
-        p.add_argument("--fast-bloom", action="store_true")
-        p.add_argument("--no-fast-bloom", dest="fast_bloom", action="store_false")
-        p.set_defaults(fast_bloom=True)
-        p.add_argument("--pixel-size", type=int, default=2)
-        p.add_argument("--brightness", type=float, default=0.0)
-        p.add_argument("--contrast", type=float, default=1.0)
-        p.add_argument("--gamma", type=float, default=1.0)
-        p.add_argument("--saturation", type=float, default=1.0)
-        p.add_argument("--temperature", type=float, default=0.0)
-        p.add_argument("--flicker-strength", type=float, default=0.0)
-        p.add_argument("--flicker-hz", type=float, default=0.0)
-        p.add_argument("--grain-size", type=int, default=1)
-        p.add_argument("--scanline-angle", type=float, default=0.0)
-        p.add_argument("--scanline-thickness", type=float, default=1.0)
-        p.add_argument("--warp-strength", type=float, default=0.0)
-        p.add_argument("--glitch-amp", type=int, default=0)
-        p.add_argument("--glitch-height", type=float, default=0.0)
+        for field, flag, kind, lo, hi in CLI_SURFACE:
+            default = getattr(CrtParams, field)
+            if kind is bool:
+                if field == "fast_bloom":                 # a --flag / --no-flag pair defaulting to on (:1176-1178)
+                    p.add_argument(flag, dest=field, action="store_true")
+                    p.add_argument("--no-" + flag[2:], dest=field, action="store_false")
+                    p.set_defaults(**{field: default})
+                else:
+                    p.add_argument(flag, dest=field, action="store_true")
+            else:
+                p.add_argument(flag, dest=field, type=kind, default=default)
         return p
 
     @classmethod
@@ -164,37 +144,15 @@ class CrtParams:
         """Parse the reference's flags (unknown flags such as --input are left
         alone) and apply main()'s clamps (crt_filter.py:1225-1260)."""
         a, _ = cls.cli_parser().parse_known_args(list(argv) if argv is not None else None)
-        return cls(
-            scanline_strength=float(max(0.0, min(1.0, a.scanline_strength))),
-            triad_strength=float(max(0.0, min(1.0, a.triad_strength))),
-            triad_gamma=float(max(0.1, a.triad_gamma)),
-            triad_preserve_luma=bool(a.triad_preserve_luma),
-            triad_softness=float(max(0.0, a.triad_softness)),
-            aberration_px=int(max(-8, min(8, a.aberration_px))),
-            bloom_sigma=max(0.0, a.bloom_sigma),
-            bloom_strength=max(0.0, a.bloom_strength),
-            noise_strength=max(0.0, a.noise_strength),
-            vignette_strength=float(max(0.0, min(1.0, a.vignette_strength))),
-            persistence=float(max(0.0, min(0.95, a.persistence))),
-            scanline_speed_px_s=float(a.scanline_speed),
-            scanline_period_px=max(1.0, float(a.scanline_period)),
-            fast_bloom=bool(a.fast_bloom),
-            pixel_size=max(1, int(a.pixel_size)),
-            glitch_amp_px=max(0, int(a.glitch_amp)),
-            glitch_height_frac=float(max(0.0, min(1.0, a.glitch_height))),
-            bloom_threshold=float(max(0.0, min(1.0, a.bloom_threshold))),
-            brightness=float(a.brightness),
-            contrast=float(a.contrast),
-            gamma=float(max(1e-3, a.gamma)),
-            saturation=float(max(0.0, a.saturation)),
-            temperature=float(max(-1.0, min(1.0, a.temperature))),
-            flicker_strength=float(max(0.0, min(1.0, a.flicker_strength))),
-            flicker_hz=float(max(0.0, a.flicker_hz)),
-            grain_size=max(1, int(a.grain_size)),
-            scanline_angle=float(a.scanline_angle),
-            scanline_thickness=float(max(0.1, a.scanline_thickness)),
-            warp_strength=float(max(-1.0, min(1.0, a.warp_strength))),
-        )
+        out = {}
+        for field, _flag, kind, lo, hi in CLI_SURFACE:
+            v = kind(getattr(a, field))
+            if lo is not None:
+                v = max(kind(lo), v)
+            if hi is not None:
+                v = min(kind(hi), v)
+            out[field] = v
+        return cls(**out)
 
     # ------------------------------------------------------- frame scalars --
     def phase_px(self, frame_index: int, fps: float) -> float:
@@ -205,3 +163,38 @@ class CrtParams:
     def time_sec(frame_index: int, fps: float) -> float:
         """flicker time of frame i (crt_filter.py:1064)."""
         return frame_index / float(fps)
+
+
+# The reference's CLI surface for the effect chain as data: (CrtParams field, flag (:1160-1205), type, clamp low, clamp high
+# (:1225-1260; None = unclamped)).  Defaults are the dataclass defaults.  Drives cli_parser() and from_cli().
+CLI_SURFACE = (
+    ("scanline_strength", "--scanline-strength", float, 0.0, 1.0),
+    ("triad_strength", "--triad-strength", float, 0.0, 1.0),
+    ("triad_gamma", "--triad-gamma", float, 0.1, None),
+    ("triad_preserve_luma", "--triad-preserve-luma", bool, None, None),
+    ("triad_softness", "--triad-softness", float, 0.0, None),
+    ("aberration_px", "--aberration-px", int, -8, 8),
+    ("bloom_sigma", "--bloom-sigma", float, 0.0, None),
+    ("bloom_strength", "--bloom-strength", float, 0.0, None),
+    ("bloom_threshold", "--bloom-threshold", float, 0.0, 1.0),
+    ("noise_strength", "--noise-strength", float, 0.0, None),
+    ("vignette_strength", "--vignette-strength", float, 0.0, 1.0),
+    ("persistence", "--persistence", float, 0.0, 0.95),
+    ("scanline_speed_px_s", "--scanline-speed", float, None, None),
+    ("scanline_period_px", "--scanline-period", float, 1.0, None),
+    ("fast_bloom", "--fast-bloom", bool, None, None),
+    ("pixel_size", "--pixel-size", int, 1, None),
+    ("glitch_amp_px", "--glitch-amp", int, 0, None),
+    ("glitch_height_frac", "--glitch-height", float, 0.0, 1.0),
+    ("brightness", "--brightness", float, None, None),
+    ("contrast", "--contrast", float, None, None),
+    ("gamma", "--gamma", float, 1e-3, None),
+    ("saturation", "--saturation", float, 0.0, None),
+    ("temperature", "--temperature", float, -1.0, 1.0),
+    ("flicker_strength", "--flicker-strength", float, 0.0, 1.0),
+    ("flicker_hz", "--flicker-hz", float, 0.0, None),
+    ("grain_size", "--grain-size", int, 1, None),
+    ("scanline_angle", "--scanline-angle", float, None, None),
+    ("scanline_thickness", "--scanline-thickness", float, 0.1, None),
+    ("warp_strength", "--warp-strength", float, -1.0, 1.0),
+)

@@ -393,3 +393,17 @@ def test_short_clips_are_never_sharded():
     eng2 = CrtEngine(128, 96).configure(CrtParams(noise_strength=0.0, persistence=0.95), shards="auto")
     eng2.process(torch.zeros((600, 96, 128, 3), dtype=torch.uint8, device="cuda"))
     assert int(eng2.last_info.reserved[0]) == 1          # 149 warm-up frames per shard: not worth it at 600 frames
+
+
+def test_state_resize_is_cv2_resize():
+    """crt_resize_state (GUI chain, crt_filter.py:689-690) against cv2.resize(INTER_LINEAR) itself: bit for bit on float32."""
+    import cv2
+    import torch
+    from pythoncrt_b200 import CrtEngine
+    eng = CrtEngine(128, 96)
+    rng = np.random.default_rng(8)
+    for h0, w0 in ((48, 72), (200, 300), (97, 131), (96, 128), (30, 500)):
+        src = rng.random((h0, w0, 3)).astype(np.float32)
+        got = eng.resize_state(torch.from_numpy(src).cuda()).cpu().numpy()
+        want = cv2.resize(src, (128, 96), interpolation=cv2.INTER_LINEAR)
+        assert got.shape == (96, 128, 3) and np.array_equal(got, want), (h0, w0, float(np.abs(got - want).max()))
