@@ -13,6 +13,7 @@
 #include "crt_derive.h"
 #include "crt_fused_ps2.cuh"      // types and constants only: the kernels are instantiated in the crt_tu_*.cu units
 #include "crt_fused_warp_ps2.cuh"
+#include "crt_fused_gauss_ps2.cuh"
 #include "crt_gather_box.cuh"
 #include "crt_launch.h"
 
@@ -73,6 +74,8 @@ struct crt_ctx {
     const void* map_gather_ptr = nullptr;
     Ps2Maps maps{};                     // tensor maps of the TMA-pipelined block kernel, valid for (maps_in, maps_frames, maps_st)
     const void* maps_in = nullptr; const void* maps_st = nullptr; int maps_frames = 0;
+    CUtensorMap map_gin{};              // block gaussian kernel: the clip's even rows with a 256 x NBY(K) box
+    const void* map_gin_ptr = nullptr; int map_gin_frames = 0, map_gin_k = 0;
     FusedPlan plan{};                   // single-pass fused kernel
     FusedPlan plan_q{};                 // two-pass: fused first pass without warp/glitch/text-after, then k_gather
     WarpPs2Plan plan_w{};               // single-pass warp on the block kernels (crt_fused_warp_ps2.cuh)
@@ -247,6 +250,7 @@ bool prepare_ps2_maps(crt_ctx* ctx, const Dev& d, const uint8_t* d_in, int n_fra
 struct Call {
     bool want_warp = false, want_fused = false, want_two_pass = false, pipe = false, gather_box = false, persist = false;
     const CUtensorMap* gather_map = nullptr;
+    const CUtensorMap* gauss_in = nullptr;      // input-tile map of the block gaussian kernel, when usable
     GlitchGeom gg{};
     size_t frame_px = 0;
     int fused_used = 0;
@@ -311,6 +315,20 @@ int prepare_call(crt_ctx* ctx, const uint8_t* d_in, int n_frames, const uint8_t*
     // TMA-pipelined block kernels: tensor maps of the clip and of this context's state buffer (or pre-warp image)
     c->pipe = (c->want_fused && ctx->plan.ps2 && c->persist && prepare_ps2_maps(ctx, d, d_in, n_frames, d_state)) ||
               (c->want_two_pass && ctx->plan_q.ps2 && prepare_ps2_maps(ctx, ctx->dev_q, d_in, n_frames, ctx->scratch.q));
+    // block gaussian kernel: input tile by TMA (a K-specific box over the clip's even rows)
+    c->gauss_in = nullptr;
+    if (c->pipe && c->want_fused && ctx->plan.gauss_k && fused_gauss_ps2_tin_ok(d, ctx->plan.gauss_k) && !((uintptr_t)d_in & 15)) {
+        const int K = ctx->plan.gauss_k;
+        if (ctx->map_gin_ptr != d_in || ctx->map_gin_frames != n_frames || ctx->map_gin_k != K) {
+            const uint64_t W3 = (uint64_t)d.W * 3;
+            const uint64_t dims[2] = {W3, (uint64_t)(d.H / 2) * n_frames}, strides[1] = {2 * W3};
+            const uint32_t box[2] = {(uint32_t)P2_RAW_W, (uint32_t)gauss_ps2_geo(K).nby};
+            if (tma_encode(&ctx->map_gin, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d_in, dims, strides, box)) {
+                ctx->map_gin_ptr = d_in; ctx->map_gin_frames = n_frames; ctx->map_gin_k = K;
+            } else ctx->map_gin_ptr = nullptr;
+        }
+        if (ctx->map_gin_ptr == d_in) c->gauss_in = &ctx->map_gin;
+    }
     return CRT_OK;
 }
 
@@ -362,14 +380,14 @@ int launch_frame(crt_ctx* ctx, const Call& c, int index, const uint8_t* in_i, ui
         rc = launch_warp_ps2(ctx->env, ctx->plan_w, d, f, in_i, out_i, state_i, has_prev, st, &launches, pdl);
     } else if (c.want_fused) {
         const Ps2Maps* maps = c.pipe ? &ctx->maps : nullptr;
-        rc = (ctx->plan.ps2 && ctx->plan.gauss_k) ? launch_fused_gauss_ps2(ctx->env, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches, pdl, maps)
+        rc = (ctx->plan.ps2 && ctx->plan.gauss_k) ? launch_fused_gauss_ps2(ctx->env, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches, pdl, maps, c.gauss_in)
            : ctx->plan.ps2 ? launch_fused_ps2(ctx->env, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches, pdl, maps)
            : ctx->plan.gauss_k ? launch_fused_gauss(ctx->env, ctx->plan.th, ctx->plan.nt, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches)
                                : launch_fused(ctx->env, ctx->plan, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches);
     } else if (c.want_two_pass) {
         const FusedPlan& pq = ctx->plan_q;
         const Ps2Maps* maps = c.pipe ? &ctx->maps : nullptr;
-        rc = (pq.ps2 && pq.gauss_k) ? launch_fused_gauss_ps2(ctx->env, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl, maps)
+        rc = (pq.ps2 && pq.gauss_k) ? launch_fused_gauss_ps2(ctx->env, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl, maps, nullptr)
            : pq.ps2 ? launch_fused_ps2(ctx->env, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches, pdl, maps)
            : pq.gauss_k ? launch_fused_gauss(ctx->env, pq.th, pq.nt, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches)
                         : launch_fused(ctx->env, pq, ctx->dev_q, f, in_i, nullptr, nullptr, ctx->scratch.q, 0, st, &launches);

@@ -44,10 +44,16 @@ CRT_HD GaussPs2Geo gauss_ps2_geo(int K) {
     g.pitch = (g.nby & 3) == 2 ? g.nby : g.nby + 2;
     return g;
 }
-inline size_t fused_gauss_ps2_smem(int K, bool state_tile = false) {
+inline size_t fused_gauss_ps2_smem(int K, bool state_tile = false, bool input_tile = false) {
     const GaussPs2Geo g = gauss_ps2_geo(K);
     return sizeof(float) * ((size_t)3 * g.nbx * g.pitch + (size_t)3 * g.nby * P2_TW + (size_t)3 * (P2_TH / 2) * (P2_TW / 2) +
-                            (state_tile ? (size_t)P2_TH * P2_TW * 3 : 0));
+                            (state_tile ? (size_t)P2_TH * P2_TW * 3 : 0)) + (input_tile ? (size_t)g.nby * 256 : 0);
+}
+// input tile by TMA: one 256-byte box must cover the tile's blocks, the aberration shift and the 16-byte alignment slack
+inline bool fused_gauss_ps2_tin_ok(const Dev& d, int K) {
+    const GaussPs2Geo g = gauss_ps2_geo(K);
+    const int a0 = d.aberr != 0 ? d.aberr_mod : 0, as = a0 > (d.W >> 1) ? a0 - d.W : a0, aa = as < 0 ? -as : as;
+    return (d.W & 7) == 0 && 6 * g.nbx + 6 * aa + 15 <= 256;
 }
 CRT_HD bool fused_gauss_ps2_supported(const Dev& d, bool glitch_on) {
     return d.bloom_mode == 2 && d.pix_uniform == 2 && d.even_dims && (d.W & 3) == 0 && !d.warp_on && !glitch_on && d.text_mode == 0;
@@ -61,10 +67,16 @@ CRT_HD bool fused_gauss_ps2_supported(const Dev& d, bool glitch_on) {
 // warp-stall samples on the first use of the per-thread state loads (L2 latency: at 1080p the state lives in L2) and another
 // 10 % on the table staging at kernel entry; with TST the tables also arrive by bulk copies that are only waited for at their
 // first use, after the first tile's input loads are in flight.  24.5 KB more shared memory: still three CTAs per SM.
-template <int K, bool FAST, int MINB, bool TST, int SPEC = 0>
+// TIN (with TST): the tile's input bytes — NBY even rows x 256 bytes around what its blocks read — arrive by one tensor-map
+// copy per tile as well, issued one tile ahead into a single buffer (the copy for tile t + 1 starts when phase 1 of tile t has
+// read the buffer; for the first tile at kernel entry, before the previous frame's kernel has finished).  ncu (run 25) put
+// 9 % of the stall samples on the first use of the per-thread byte loads.  Tiles on the left / right frame edge, where the
+// chromatic aberration wraps around (np.roll), keep the per-thread loads.
+template <int K, bool FAST, int MINB, bool TST, int SPEC = 0, bool TIN = false>
 __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, FrameDev f_arg, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                            float* __restrict__ state, float* __restrict__ q_out, int has_prev,
-                                                           const __grid_constant__ CUtensorMap map_st) {
+                                                           const __grid_constant__ CUtensorMap map_st, const __grid_constant__ CUtensorMap map_in,
+                                                           int frame) {
     Dev d = d_arg;
     FrameDev f = f_arg;
     specialise<SPEC>(d, f);             // SPEC != 0: feature flags become compile-time constants (crt_fused_ps2.cuh)
@@ -81,9 +93,11 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
     __shared__ float s_unit[256];
     __shared__ __align__(16) float s_pow[POW_TAB_FLOATS];
     __shared__ float s_rows[2 * P2_TH], s_cols[2 * P2_TW];
-    __shared__ __align__(8) uint64_t bar_tab, bar_st;
+    __shared__ __align__(8) uint64_t bar_tab, bar_st, bar_in;
+    constexpr int RAW_BYTES = TIN ? NBY * P2_RAW_W : 0;
     float* const s_state = sm;                      // [TH][TW*3]        state tile (TST only; first: TMA wants 128-byte alignment)
-    float* Sb = sm + (TST ? P2_TH * P2_TW * 3 : 0); // [3][NBX][PITCH]   thresholded bloom source per block, transposed
+    uint8_t* const s_raw = reinterpret_cast<uint8_t*>(sm + (TST ? P2_TH * P2_TW * 3 : 0));      // [NBY][256] input bytes (TIN only)
+    float* Sb = sm + (TST ? P2_TH * P2_TW * 3 : 0) + RAW_BYTES / 4;      // [3][NBX][PITCH]   thresholded bloom source per block, transposed
     float* Rp = Sb + 3 * NBX * PITCH;               // [3][NBY][P2_TW]   row-pass result per block row
     float* T1 = Rp + 3 * NBY * P2_TW;               // [3][TH/2][TW/2]   graded block values of the tile
     const int tid = threadIdx.x;
@@ -94,7 +108,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
     const bool tile_out = TST && (state || q_out);  // the result leaves through the shared-memory tile
     if (TST) {
         if (tid == 0) {                             // tables by bulk copies (16-byte multiples; element 1024 of each LUT below)
-            mbar_init(&bar_tab, 1); mbar_init(&bar_st, 1);
+            mbar_init(&bar_tab, 1); mbar_init(&bar_st, 1); mbar_init(&bar_in, 1);
             fence_mbar_init();
             const uint32_t bytes = (d.triad_mode >= 2 ? 2 * 4096 : 0) + (d.col_gamma ? POW_TAB_FLOATS * 4 : 0);
             mbar_expect_tx(&bar_tab, bytes);
@@ -120,6 +134,13 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
     const int tiles_x = (d.W + P2_TW - 1) / P2_TW, ntiles = tiles_x * ((d.H + P2_TH - 1) / P2_TH);
     const int step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;      // tile += gridDim.x without a division per tile
     int tby = blockIdx.x / tiles_x, tbx = blockIdx.x - tby * tiles_x;
+    const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
+    const int as = a0 > (d.W >> 1) ? a0 - d.W : a0;                 // signed aberration shift (aberr_mod is taken modulo W)
+    const int aa = as < 0 ? -as : as;
+    if (TIN && tid == 0 && (int)blockIdx.x < ntiles) {              // first tile's input: independent of the previous kernel
+        mbar_expect_tx(&bar_in, RAW_BYTES);
+        tma_load_2d_hint(s_raw, &map_in, (6 * ((tbx * P2_TW >> 1) - HB) - 3 * aa) & ~15, frame * d.hh + (tby * P2_TH >> 1) - HB, &bar_in, L2_EVICT_FIRST);
+    }
     int iter = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {    // persistent CTAs, tables staged once
         const int ox0 = tbx * P2_TW, oy0 = tby * P2_TH;
@@ -146,12 +167,24 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
         {
             constexpr int NIT = (NBX * NBY + P2_NT - 1) / P2_NT;
             uint32_t raw[NIT][3];                                 // 32-bit: a byte array would live in local memory
-            const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
             // all loads first: their latencies overlap.  Tiles away from the left / right frame edge need neither the
             // block clamp nor the aberration wrap in x: one 32-bit offset per block, byte offsets per channel.
-            const int as = a0 > (d.W >> 1) ? a0 - d.W : a0;                 // signed shift (aberr_mod is taken modulo W)
-            const int aa = as < 0 ? -as : as;
-            if (2 * gbx0 - aa >= 0 && 2 * (gbx0 + NBX - 1) + aa < d.W) {    // tile-uniform
+            const bool x_inside = 2 * gbx0 - aa >= 0 && 2 * (gbx0 + NBX - 1) + aa < d.W;       // tile-uniform
+            if (TIN) mbar_wait(&bar_in, iter & 1);                // this tile's input bytes have landed
+            if (TIN && x_inside) {
+                // byte 0 of the buffer is byte (6 gbx0 - 3 aa) & ~15 of the frame row; buffer row = (clamped) block row - gby0
+                const int xoff = 6 * gbx0 - ((6 * gbx0 - 3 * aa) & ~15);
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    if ((tid & ~31) + it * P2_NT >= NBX * NBY) break;
+                    const int u = imin(tid + it * P2_NT, NBX * NBY - 1);
+                    const int bj = u / NBX, bi = u - bj * NBX;
+                    const uint8_t* p = s_raw + (imin(imax(gby0 + bj, 0), d.hh - 1) - gby0) * P2_RAW_W + 6 * bi + xoff;
+                    raw[it][0] = p[-3 * as];
+                    raw[it][1] = p[1];
+                    raw[it][2] = p[3 * as + 2];
+                }
+            } else if (x_inside) {
                 const int W3 = d.W * 3;
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
@@ -195,6 +228,12 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
             }
         }
         __syncthreads();
+        if (TIN && tid == 0 && tile + (int)gridDim.x < ntiles) {      // the buffer has been read: fetch the next tile's input bytes
+            int nbx = tbx + step_x, nby = tby + step_y;
+            if (nbx >= tiles_x) { nbx -= tiles_x; ++nby; }
+            mbar_expect_tx(&bar_in, RAW_BYTES);
+            tma_load_2d_hint(s_raw, &map_in, (6 * ((nbx * P2_TW >> 1) - HB) - 3 * aa) & ~15, frame * d.hh + (nby * P2_TH >> 1) - HB, &bar_in, L2_EVICT_FIRST);
+        }
 
         // ---- phase 2: row pass over block rows; a task = 4 outputs along x for a pair of block rows ----
         for (int u = tid; u < 3 * (NBY / 2) * (P2_TW / 4); u += P2_NT) {
@@ -266,19 +305,23 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
 #if defined(CRT_TU_GAUSS_PS2)      // launcher: compiled only in the translation unit that owns these kernels (build.py)
 template <int K, int MINB>
 inline int launch_fused_gauss_ps2_t(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
-                                    int has_prev, cudaStream_t st, bool pdl, const Ps2Maps* maps) {
+                                    int has_prev, cudaStream_t st, bool pdl, const Ps2Maps* maps, const CUtensorMap* gmap_in) {
     const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1;
     // state tile by TMA: needs the tensor map of the state buffer (or of the pre-warp image) and the tile to fit beside three CTAs
     static const bool use_tst = env_int("CRT_GPS2_TMA_STATE", 1) != 0;
     // (measured, run 9: 30.1 -> 29.0 us per 1080p frame with a state to blend; the pre-warp image of the two-pass path is 2 % faster
     // through per-thread stores, as in round 1)
     const bool tst = maps && use_tst && state && !q_out && fused_gauss_ps2_smem(K, true) + 16 * 1024 <= 76 * 1024;
-    const size_t smem = fused_gauss_ps2_smem(K, tst);
+    static const bool use_tin = env_int("CRT_GPS2_TMA_INPUT", 1) != 0;
+    const bool tin = tst && use_tin && gmap_in && fused_gauss_ps2_tin_ok(d, K) && fused_gauss_ps2_smem(K, true, true) + 14 * 1024 <= 75 * 1024;
+    const size_t smem = fused_gauss_ps2_smem(K, tst, tin);
     auto kern = tst ? (fast ? k_fused_gauss_ps2<K, true, MINB, true> : k_fused_gauss_ps2<K, false, MINB, true>)
                     : (fast ? k_fused_gauss_ps2<K, true, MINB, false> : k_fused_gauss_ps2<K, false, MINB, false>);
     static const bool use_spec = env_int("CRT_SPEC", 1) != 0;
+    if (tin) kern = fast ? k_fused_gauss_ps2<K, true, MINB, true, 0, true> : k_fused_gauss_ps2<K, false, MINB, true, 0, true>;
     if (K == 9 && use_spec && tst && fast && spec_matches(SPEC_GRADED, d, f.flicker_on != 0, fast))      // BASELINE configs[1]
-        kern = k_fused_gauss_ps2<K == 9 ? 9 : K, true, MINB, true, K == 9 ? SPEC_GRADED : 0>;
+        kern = tin ? k_fused_gauss_ps2<K == 9 ? 9 : K, true, MINB, true, K == 9 ? SPEC_GRADED : 0, true>
+                   : k_fused_gauss_ps2<K == 9 ? 9 : K, true, MINB, true, K == 9 ? SPEC_GRADED : 0, false>;
     // first pass of the two-pass path with every stage on: BASELINE configs[3] (K = 9) and [4] (K = 25)
     if ((K == 9 || K == 25) && use_spec && !tst && q_out && fast && spec_matches(SPEC_FULL | SP_THR * (K == 9), d, f.flicker_on != 0, fast))
         kern = k_fused_gauss_ps2<(K == 9 || K == 25) ? K : 9, true, MINB, false, (K == 9 || K == 25) ? (SPEC_FULL | SP_THR * (K == 9)) : 0>;
@@ -295,20 +338,21 @@ inline int launch_fused_gauss_ps2_t(LaunchEnv& env, const Dev& d, const FrameDev
     const int ntiles = ((d.W + P2_TW - 1) / P2_TW) * ((d.H + P2_TH - 1) / P2_TH);
     const dim3 grid(ntiles < resident ? ntiles : resident);
     static const CUtensorMap no_map{};
-    const cudaError_t e = launch_pdl(kern, grid, dim3(P2_NT), smem, st, pdl, d, f, in, out, state, q_out, has_prev, tst ? maps->st : no_map);
+    const cudaError_t e = launch_pdl(kern, grid, dim3(P2_NT), smem, st, pdl, d, f, in, out, state, q_out, has_prev, tst ? maps->st : no_map,
+                                     tin ? *gmap_in : no_map, maps ? maps->frame : 0);
     return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
 }
 
 inline int run_fused_gauss_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
-                               cudaStream_t st, int* launches, bool pdl = false, const Ps2Maps* maps = nullptr) {
+                               cudaStream_t st, int* launches, bool pdl = false, const Ps2Maps* maps = nullptr, const CUtensorMap* gmap_in = nullptr) {
     int rc = 4;
     switch (d.ksize) {
-        case 5: rc = launch_fused_gauss_ps2_t<5, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps); break;
-        case 7: rc = launch_fused_gauss_ps2_t<7, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps); break;
-        case 9: rc = launch_fused_gauss_ps2_t<9, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps); break;
-        case 11: rc = launch_fused_gauss_ps2_t<11, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps); break;
-        case 13: rc = launch_fused_gauss_ps2_t<13, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps); break;
-        case 25: rc = launch_fused_gauss_ps2_t<25, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps); break;
+        case 5: rc = launch_fused_gauss_ps2_t<5, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps, gmap_in); break;
+        case 7: rc = launch_fused_gauss_ps2_t<7, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps, gmap_in); break;
+        case 9: rc = launch_fused_gauss_ps2_t<9, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps, gmap_in); break;
+        case 11: rc = launch_fused_gauss_ps2_t<11, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps, gmap_in); break;
+        case 13: rc = launch_fused_gauss_ps2_t<13, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps, gmap_in); break;
+        case 25: rc = launch_fused_gauss_ps2_t<25, 3>(env, d, f, in, out, state, q_out, has_prev, st, pdl, maps, gmap_in); break;
         default: break;
     }
     if (rc != 4) ++*launches;        // an unsupported tap count launches nothing

@@ -4,7 +4,7 @@
 
 namespace crt {
 int launch_fused_gauss_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
-                           int has_prev, cudaStream_t st, int* launches, bool pdl, const Ps2Maps* maps) {
-    return run_fused_gauss_ps2(env, d, f, in, out, state, q_out, has_prev, st, launches, pdl, maps);
+                           int has_prev, cudaStream_t st, int* launches, bool pdl, const Ps2Maps* maps, const CUtensorMap* gmap_in) {
+    return run_fused_gauss_ps2(env, d, f, in, out, state, q_out, has_prev, st, launches, pdl, maps, gmap_in);
 }
 }  // namespace crt
