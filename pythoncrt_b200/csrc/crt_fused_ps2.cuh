@@ -44,9 +44,10 @@ enum : int {
     SP_GRAIN = 512,       // noise on, grain_size > 1 (bilinear up-scale of the draw plane)
     SP_FLICKER = 1024,
     SP_THR = 2048,        // bloom threshold on
+    SP_NOTHR = 4096,      // ... off
 };
-constexpr int SPEC_DEFAULT = SP_NOCOLOUR | SP_SCAN1 | SP_VIG1 | SP_NOFLICKER | SP_RGB | SP_FASTTAIL | SP_NONOISE;      // the CLI's default chain
-constexpr int SPEC_SLANTED = SP_NOCOLOUR | SP_SCAN2 | SP_VIG1 | SP_NOFLICKER | SP_RGB | SP_FASTTAIL | SP_NONOISE;      // ... with scanline angle / thickness
+constexpr int SPEC_DEFAULT = SP_NOCOLOUR | SP_SCAN1 | SP_VIG1 | SP_NOFLICKER | SP_RGB | SP_FASTTAIL | SP_NONOISE | SP_NOTHR;      // the CLI's default chain
+constexpr int SPEC_SLANTED = SP_NOCOLOUR | SP_SCAN2 | SP_VIG1 | SP_NOFLICKER | SP_RGB | SP_FASTTAIL | SP_NONOISE | SP_NOTHR;      // ... with scanline angle / thickness
 constexpr int SPEC_GRADED = SP_ALLCOLOUR | SP_SCAN1 | SP_VIG1 | SP_NOFLICKER | SP_RGB | SP_FASTTAIL | SP_NONOISE | SP_THR;     // BASELINE configs[1]
 constexpr int SPEC_FULL = SP_ALLCOLOUR | SP_SCAN2 | SP_VIG1 | SP_FLICKER | SP_RGB | SP_FASTTAIL | SP_GRAIN;             // BASELINE configs[3], [4]: everything on
 
@@ -64,6 +65,7 @@ CRT_HD void specialise(Dev& d, FrameDev& f) {
     if (SPEC & SP_GRAIN) d.noise_on = 1;
     if (SPEC & SP_FLICKER) f.flicker_on = 1;
     if (SPEC & SP_THR) d.thr_on = 1;
+    if (SPEC & SP_NOTHR) d.thr_on = 0;
 }
 // does the clip's parameter set match SPEC exactly?  (host; `flicker_on` is a per-clip property: strength > 0 and hz > 0)
 inline bool spec_matches(int spec, const Dev& d, bool flicker_on, bool fast_tail) {
@@ -80,6 +82,7 @@ inline bool spec_matches(int spec, const Dev& d, bool flicker_on, bool fast_tail
     if ((spec & SP_GRAIN) && !(d.noise_on && d.nz_x)) return false;
     if ((spec & SP_FLICKER) && !flicker_on) return false;
     if ((spec & SP_THR) && !d.thr_on) return false;
+    if ((spec & SP_NOTHR) && d.thr_on) return false;
     return true;
 }
 
@@ -213,9 +216,12 @@ __device__ __forceinline__ void ps2_fill_sel(float (*s_sel)[12], int tid, int bg
 // through the composite tables, per-row scanlines (or none), analytic vignette (or none), optional
 // flicker folded into the row factor, no noise.  Tiles that touch the mask's irregular edge columns
 // and every other feature set take the general tail (after_bloom_fast).
-template <bool BLOOM, bool FAST, int MINB>
-__global__ void __launch_bounds__(P2_NT, MINB) k_fused_ps2(Dev d, FrameDev f, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+template <bool BLOOM, bool FAST, int MINB, int SPEC = 0>
+__global__ void __launch_bounds__(P2_NT, MINB) k_fused_ps2(Dev d_arg, FrameDev f_arg, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                      float* __restrict__ state, float* __restrict__ q_out, int has_prev) {
+    Dev d = d_arg;
+    FrameDev f = f_arg;
+    specialise<SPEC>(d, f);             // SPEC != 0: feature flags become compile-time constants (see above)
     __shared__ __align__(16) float s_lut[2 * 1028];
     __shared__ __align__(16) float s_sel[3][12];
     float* const s_fwd = s_lut;
@@ -604,6 +610,11 @@ inline int run_fused_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const 
     const dim3 pgrid(ntiles < resident ? ntiles : resident);       // persistent 1-D grid
     auto kern = d.bloom_mode == 1 ? (fast ? (minb == 3 ? k_fused_ps2<true, true, 3> : k_fused_ps2<true, true, 4>) : k_fused_ps2<true, false, 4>)
                                   : (fast ? k_fused_ps2<false, true, 4> : k_fused_ps2<false, false, 4>);
+    static const bool use_spec_plain = env_int("CRT_SPEC", 1) != 0;
+    if (use_spec_plain && minb != 3 && d.bloom_mode == 1 && !d.thr_on && fast) {      // small frames (VGA: BASELINE configs[0]) and first frames
+        if (spec_matches(SPEC_DEFAULT, d, f.flicker_on != 0, fast)) kern = k_fused_ps2<true, true, 4, SPEC_DEFAULT>;
+        else if (spec_matches(SPEC_SLANTED, d, f.flicker_on != 0, fast)) kern = k_fused_ps2<true, true, 4, SPEC_SLANTED>;
+    }
     const cudaError_t e = launch_pdl(kern, pgrid, dim3(P2_NT), 0, st, pdl, d, f, in, out, state, q_out, has_prev);
     ++*launches;
     return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
