@@ -17,6 +17,8 @@
 // Glitch rows (horizontal shifts of up to a few glitch_amp, wrapping around the frame, crt_filter.py:852-857) move taps
 // out of the box: those pixels (and every pixel of a clip whose footprint does not fit) take the global-memory path
 // of k_gather, per pixel.  ~39 KB shared memory per CTA -> five 256-thread CTAs per SM.
+// Measured and NOT adopted (round 2, run 30): launching this kernel with programmatic stream serialisation and computing the
+// taps before griddepcontrol.wait (so that they overlap the first pass's last wave): 10 158 vs 10 596 frames/s on configs[2].
 #pragma once
 #include "crt_fused.cuh"
 #include "crt_tma.cuh"
