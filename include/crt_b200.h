@@ -159,7 +159,7 @@ int crt_set_policy(crt_ctx* ctx, int policy);
  * (the only cross-frame dependency is the blend at :1092) and the one used across GPUs (pythoncrt_b200/clip.py).  The result
  * differs from the strictly serial run by at most persistence^warm-up <= 1/8 LSB before quantisation (identical when
  * persistence == 0).  1 = off (default: every call is strictly serial), 0 = automatic (up to 4 shards, each at least 48 frames
- * and 8 warm-ups long), k = at most k.  Calls shorter than that, and crt_process_static / crt_process_host, stay serial.
+ * and 8 warm-ups long; none for frames of 24 Mpixel and more, which fill the GPU on their own), k = at most k.  Calls shorter than that, and crt_process_static / crt_process_host, stay serial.
  */
 int crt_set_shards(crt_ctx* ctx, int shards);
 

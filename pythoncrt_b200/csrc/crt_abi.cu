@@ -440,6 +440,9 @@ int choose_shards(const crt_ctx* ctx, int n_frames) {
     static const int forced = env_int("CRT_SHARDS", -1);
     const int wanted = forced >= 0 ? forced : ctx->shards_wanted;
     if (wanted == 1 || n_frames < 2) return 1;
+    // automatic mode: an 8K frame fills the GPU on its own (16 000+ tiles per kernel); concurrent shards only thrash L2 there
+    // (measured, run 33: BASELINE configs[4] 1 245 frames/s on one stream, 1 203 with three shards)
+    if (wanted == 0 && (size_t)ctx->W * ctx->H >= (size_t)24 << 20) return 1;
     const int halo = halo_frames(ctx->p.persistence);
     // a shard must be worth its warm-up: at least 8 halos (<= 12.5 % extra frames) and 48 frames long
     const int min_chunk = halo * 8 > 48 ? halo * 8 : 48;
