@@ -13,6 +13,7 @@
 #include "crt_derive.h"
 #include "crt_fused_ps2.cuh"      // types and constants only: the kernels are instantiated in the crt_tu_*.cu units
 #include "crt_fused_warp_ps2.cuh"
+#include "crt_fused_warp_src.cuh"
 #include "crt_fused_gauss_ps2.cuh"
 #include "crt_gather_box.cuh"
 #include "crt_launch.h"
@@ -72,6 +73,7 @@ struct crt_ctx {
     LaunchEnv env;                      // per-context launch state (SM count, configured kernels): no process-wide statics
     CUtensorMap map_gather{};           // float32 [H][W*3] map of the state buffer with the gather kernel's 192 x 16 box
     const void* map_gather_ptr = nullptr;
+    int tile_h = 32;                    // tile height of the single-pass block kernels when a frame runs alone (choose_tile_h)
     Ps2Maps maps{};                     // tensor maps of the TMA-pipelined block kernel, valid for (maps_in, maps_frames, maps_st)
     const void* maps_in = nullptr; const void* maps_st = nullptr; int maps_frames = 0;
     CUtensorMap map_gin{};              // block gaussian kernel: the clip's even rows with a 256 x NBY(K) box
@@ -79,6 +81,8 @@ struct crt_ctx {
     FusedPlan plan{};                   // single-pass fused kernel
     FusedPlan plan_q{};                 // two-pass: fused first pass without warp/glitch/text-after, then k_gather
     WarpPs2Plan plan_w{};               // single-pass warp on the block kernels (crt_fused_warp_ps2.cuh)
+    WarpSrcPlan plan_s{};               // source-driven single-pass warp (crt_fused_warp_src.cuh)
+    WsTile* d_ws_tiles = nullptr;       // device copy of plan_s.tiles
     GatherBoxPlan plan_g{};             // second pass with the footprint staged by TMA (crt_gather_box.cuh)
     int* d_origin = nullptr;            // device copy of plan_g.origin
     CUtensorMap map_gq{}, map_gst{};    // tensor maps of the pre-warp image (box of plan_g) and of the state (96 x 32 box)
@@ -117,6 +121,8 @@ int upload(crt_ctx* ctx, Lerp1** dst, const std::vector<Lerp1>& v) {
 }
 
 // Derive the device parameter block (crt_derive.h) from the context's parameters and tables.
+int choose_tile_h(int W, int H, int sms, int per_sm, int halo_blocks);
+
 int build_dev(crt_ctx* ctx) {
     const crt_params& p = ctx->p;
     if (p.noise_strength > 0.0 && p.grain_size > 1 && ctx->nz_grain != p.grain_size) {
@@ -158,10 +164,30 @@ int build_dev(crt_ctx* ctx) {
     hd.dn_x = ctx->h_dn_x.data(); hd.dn_y = ctx->h_dn_y.data(); hd.up_x = ctx->h_up_x.data(); hd.up_y = ctx->h_up_y.data();
     ctx->plan = plan_fused(hd, glitch_active(p));
     ctx->plan_q = FusedPlan{};
+    ctx->tile_h = P2_TH;
+    if (ctx->plan.ok && ctx->plan.ps2 && ctx->plan.gauss_k <= 13) {
+        // measured (run 41, 1080p): default chain 21.5 -> 20.5 us and 58 954 -> 63 215 frames/s on one stream with 28 rows; the
+        // gaussian kernel LOSES with any lower tile (28.4 us at 32 rows, 30.6 at 26, 30.3 at 28, 28.9 at 30: its per-tile fixed
+        // cost — four barriers, the state tile's load behind the previous store — outweighs the partial round) -> 32 unless forced
+        const bool thr = ctx->dev.bloom_mode == 1 && ctx->dev.thr_on;
+        ctx->tile_h = ctx->plan.gauss_k ? choose_tile_h(ctx->W, ctx->H, ctx->env.sms, 3, -1)
+                                        : choose_tile_h(ctx->W, ctx->H, ctx->env.sms, thr ? 3 : 4, 1);
+    }
     // measured (round 2, run 3): the single-pass warp block kernel is slower than the two-pass path on BASELINE configs[2]
     // (152 vs 125 us at 4K: the aligned footprint of a 64 x 32 tile holds 1.6-1.8x its pixels) -> opt-in only
     ctx->plan_w = env_int("CRT_WARP_PS2", 0) ? plan_warp_ps2(hd, glitch_active(p)) : WarpPs2Plan{};
     ctx->plan_g = GatherBoxPlan{};
+    ctx->plan_s = WarpSrcPlan{};
+    // measured (round 2, runs 36-39): the source-driven single pass (crt_fused_warp_src.cuh) halves the DRAM traffic of the
+    // two-pass path but runs 120.5 us against 106.8 us at 4K (ownership tests + cut quads + phase barriers) -> opt-in only
+    if (ctx->dev.warp_on && env_int("CRT_WARP_SRC", 0) && !ctx->plan_w.ok) {
+        ctx->plan_s = plan_warp_src(hd, glitch_active(p));
+        if (ctx->plan_s.ok) {
+            if (ctx->d_ws_tiles) { cudaFree(ctx->d_ws_tiles); ctx->d_ws_tiles = nullptr; }
+            CU(cudaMalloc((void**)&ctx->d_ws_tiles, ctx->plan_s.tiles.size() * sizeof(WsTile)));
+            CU(cudaMemcpy(ctx->d_ws_tiles, ctx->plan_s.tiles.data(), ctx->plan_s.tiles.size() * sizeof(WsTile), cudaMemcpyHostToDevice));
+        }
+    }
     const bool gather_needed = ctx->dev.warp_on || glitch_active(p) || ctx->dev.text_mode == 2;
     if (!ctx->plan.ok || gather_needed || env_int("CRT_TWO_PASS", 0)) {
         Dev hq = hd;
@@ -228,27 +254,47 @@ int run_staged(crt_ctx* ctx, const FrameDev& f, const uint8_t* d_in, uint8_t* d_
     return launch_staged(ctx->env, ctx->dev, f, d_in, d_out, d_state, has_prev, d_img, ctx->scratch, st, launches);
 }
 
+// Tile height of the single-pass block kernels for a frame processed ALONE on the GPU.  Their CTAs are persistent and walk the
+// tiles with a fixed stride, so a frame costs ceil(tiles / resident CTAs) tile times: 1080p in 64 x 32 tiles is 1020 tiles for
+// 444 (gaussian bloom, 3 CTAs per SM) or 592 (4 per SM) CTAs = 3 resp. 2 rounds of which the last is 30 % resp. 72 % full.
+// A lower tile (26 rows: 1260 tiles, 2.84 rounds) fills the rounds; the cost model is rounds x (rows + a), a = the rows' worth
+// of halo and per-tile overhead, and 32 rows stay unless the model gains 6 %.  4K: 6.9 rounds, nothing to gain.  Concurrent
+// temporal shards fill each other's partial rounds and keep 32 rows (process_sharded).  CRT_TILE_H overrides.
+int choose_tile_h(int W, int H, int sms, int per_sm, int halo_blocks) {
+    const int forced = env_int("CRT_TILE_H", 0);
+    if (forced >= 8 && forced <= P2_TH && !(forced & 1)) return forced;
+    if (forced < 0 || halo_blocks < 0) return P2_TH;       // halo_blocks < 0: only on request
+    const int tiles_x = (W + P2_TW - 1) / P2_TW, slots = sms * per_sm;
+    const double a = 2.0 + 1.2 * halo_blocks;
+    auto cost = [&](int th) { return (double)((tiles_x * ((H + th - 1) / th) + slots - 1) / slots) * (th + a); };
+    int best = P2_TH;
+    for (int th = P2_TH - 2; th >= 20; th -= 2)
+        if (cost(th) < cost(best)) best = th;
+    return cost(best) <= 0.94 * cost(P2_TH) ? best : P2_TH;
+}
+
 // Tensor maps for k_fused_ps2_pipe: the clip as uint8 [frames * H/2 even rows][W*3] (box 256 x 18) and the
 // persistence state as float32 [H][W*3] (box 192 x 32).  Returns false when the variant cannot be used.
-bool prepare_ps2_maps(crt_ctx* ctx, const Dev& d, const uint8_t* d_in, int n_frames, const float* d_state) {
+bool prepare_ps2_maps(crt_ctx* ctx, const Dev& d, const uint8_t* d_in, int n_frames, const float* d_state, int th = P2_TH) {
     if (!d_state || !fused_ps2_pipe_supported(d)) return false;
     if (((uintptr_t)d_in & 15) || ((uintptr_t)d_state & 15)) return false;
-    if (ctx->maps_in == d_in && ctx->maps_frames == n_frames && ctx->maps_st == d_state) return true;
+    if (ctx->maps_in == d_in && ctx->maps_frames == n_frames && ctx->maps_st == d_state && ctx->maps.th == th) return true;
+    ctx->maps_in = nullptr;
     const uint64_t W3 = (uint64_t)d.W * 3;
     // even rows of all frames as one 2-D tensor: the frame pitch W3 * H is (H / 2) row pitches of 2 * W3
     const uint64_t in_dims[2] = {W3, (uint64_t)(d.H / 2) * n_frames}, in_strides[1] = {2 * W3};
     const uint32_t in_box[2] = {(uint32_t)P2_RAW_W, (uint32_t)P2_BH};
     if (!tma_encode(&ctx->maps.in, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d_in, in_dims, in_strides, in_box)) return false;
     const uint64_t st_dims[2] = {W3, (uint64_t)d.H}, st_strides[1] = {W3 * 4};
-    const uint32_t st_box[2] = {(uint32_t)P2_TW * 3, (uint32_t)P2_TH};
+    const uint32_t st_box[2] = {(uint32_t)P2_TW * 3, (uint32_t)th};
     if (!tma_encode(&ctx->maps.st, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_state, st_dims, st_strides, st_box)) return false;
-    ctx->maps_in = d_in; ctx->maps_frames = n_frames; ctx->maps_st = d_state;
+    ctx->maps_in = d_in; ctx->maps_frames = n_frames; ctx->maps_st = d_state; ctx->maps.th = th;
     return true;
 }
 
 // ---- one call = prepare (validation, path selection, tensor maps) + one launch_frame per frame ----------------------
 struct Call {
-    bool want_warp = false, want_fused = false, want_two_pass = false, pipe = false, gather_box = false, persist = false;
+    bool want_warp = false, want_warp_src = false, want_fused = false, want_two_pass = false, pipe = false, gather_box = false, persist = false;
     const CUtensorMap* gather_map = nullptr;
     const CUtensorMap* gauss_in = nullptr;      // input-tile map of the block gaussian kernel, when usable
     GlitchGeom gg{};
@@ -258,7 +304,8 @@ struct Call {
 
 // d_in / n_frames describe the whole clip the frames of this call are taken from (the TMA-pipelined kernels address the
 // clip as ONE tensor: a frame is selected by its index), d_state the state buffer THIS context blends against.
-int prepare_call(crt_ctx* ctx, const uint8_t* d_in, int n_frames, const uint8_t* d_out, float* d_state, const float* d_img, Call* c) {
+int prepare_call(crt_ctx* ctx, const uint8_t* d_in, int n_frames, const uint8_t* d_out, float* d_state, const float* d_img, Call* c,
+                 bool concurrent = false) {
     if (!ctx->have_params) return fail(ctx, CRT_ERR_INVALID, "crt_set_params has not been called");
     if (!ctx->dev_ok) { int rc = build_dev(ctx); if (rc) return rc; }
     if (n_frames < 0 || (n_frames > 0 && (!d_in || (!d_out && !d_img)))) return fail(ctx, CRT_ERR_INVALID, "null buffer");
@@ -275,12 +322,15 @@ int prepare_call(crt_ctx* ctx, const uint8_t* d_in, int n_frames, const uint8_t*
     c->gg = glitch_geom(p, d.W, d.H);
     // crt_process_static (d_img) takes the same kernels: the float image leaves through the path the pre-warp image of the
     // two-pass path takes (q_out), or is what the gather writes as "state" when no previous state is blended in
-    c->want_warp = ctx->policy != 1 && ctx->plan_w.ok && !d_img;          // single-pass warp block kernel
-    c->want_fused = ctx->policy != 1 && !c->want_warp && ctx->plan.ok;
-    c->want_two_pass = ctx->policy != 1 && !c->want_warp && !c->want_fused && ctx->plan_q.ok;
-    if (ctx->policy == 2 && !c->want_warp && !c->want_fused && !c->want_two_pass)
+    c->want_warp = ctx->policy != 1 && ctx->plan_w.ok && !d_img;          // single-pass warp block kernel (output-driven, opt-in)
+    // source-driven single-pass warp: needs the clip's tensor map (16-byte aligned clip) and, for its 16-byte state accesses, an aligned state
+    c->want_warp_src = ctx->policy != 1 && !c->want_warp && ctx->plan_s.ok && !d_img && d_out && d_state && !((uintptr_t)d_in & 15) &&
+                       prepare_ps2_maps(ctx, d, d_in, n_frames, d_state);
+    c->want_fused = ctx->policy != 1 && !c->want_warp && !c->want_warp_src && ctx->plan.ok;
+    c->want_two_pass = ctx->policy != 1 && !c->want_warp && !c->want_warp_src && !c->want_fused && ctx->plan_q.ok;
+    if (ctx->policy == 2 && !c->want_warp && !c->want_warp_src && !c->want_fused && !c->want_two_pass)
         return fail(ctx, CRT_ERR_UNSUPPORTED, std::string("fused kernel not available: ") + ctx->plan.why);
-    c->fused_used = (c->want_warp || c->want_fused) ? 1 : c->want_two_pass ? 2 : 0;
+    c->fused_used = (c->want_warp || c->want_warp_src || c->want_fused) ? 1 : c->want_two_pass ? 2 : 0;
     if (c->want_two_pass && !ctx->scratch.q) CU(cudaMalloc((void**)&ctx->scratch.q, c->frame_px * 3 * sizeof(float)));
     // second pass of the two-pass path with the state moved by TMA: needs a tensor map of the state buffer (192 x 16 box)
     static const bool use_gather_tile = env_int("CRT_GATHER_TILE", 1) != 0;
@@ -313,7 +363,9 @@ int prepare_call(crt_ctx* ctx, const uint8_t* d_in, int n_frames, const uint8_t*
         c->gather_box = ok;
     }
     // TMA-pipelined block kernels: tensor maps of the clip and of this context's state buffer (or pre-warp image)
-    c->pipe = (c->want_fused && ctx->plan.ps2 && c->persist && prepare_ps2_maps(ctx, d, d_in, n_frames, d_state)) ||
+    // (single pass, frames one after the other on the GPU: tile height matched to the number of resident CTAs)
+    const int th = (c->want_fused && !concurrent) ? ctx->tile_h : P2_TH;
+    c->pipe = (c->want_fused && ctx->plan.ps2 && c->persist && prepare_ps2_maps(ctx, d, d_in, n_frames, d_state, th)) ||
               (c->want_two_pass && ctx->plan_q.ps2 && prepare_ps2_maps(ctx, ctx->dev_q, d_in, n_frames, ctx->scratch.q));
     // block gaussian kernel: input tile by TMA (a K-specific box over the clip's even rows)
     c->gauss_in = nullptr;
@@ -378,6 +430,9 @@ int launch_frame(crt_ctx* ctx, const Call& c, int index, const uint8_t* in_i, ui
     int rc;
     if (c.want_warp) {
         rc = launch_warp_ps2(ctx->env, ctx->plan_w, d, f, in_i, out_i, state_i, has_prev, st, &launches, pdl);
+    } else if (c.want_warp_src) {
+        rc = launch_warp_src(ctx->env, d, f, in_i, out_i, state_i, has_prev, st, &launches, pdl, ctx->d_ws_tiles, (int)ctx->plan_s.tiles.size(),
+                             ctx->plan_s.ntx, ctx->plan_s.nty, &ctx->maps);
     } else if (c.want_fused) {
         const Ps2Maps* maps = c.pipe ? &ctx->maps : nullptr;
         rc = (ctx->plan.ps2 && ctx->plan.gauss_k) ? launch_fused_gauss_ps2(ctx->env, d, f, in_i, out_i, state_i, q_i, has_prev, st, &launches, pdl, maps, c.gauss_in)
@@ -503,7 +558,7 @@ int process_sharded(crt_ctx* ctx, int K, const uint8_t* d_in, uint8_t* d_out, fl
             }
             pt.c = s.kid; pt.st = s.stream; pt.state = s.state; pt.halo_out = s.halo_out;
         }
-        rc = prepare_call(pt.c, d_in, n_frames, d_out, pt.state, nullptr, &pt.call);
+        rc = prepare_call(pt.c, d_in, n_frames, d_out, pt.state, nullptr, &pt.call, true);
         if (rc) return k == 0 ? rc : fail(ctx, rc, std::string("shard: ") + crt_last_error(pt.c));
         if (pt.b - pt.warm > longest) longest = pt.b - pt.warm;
     }
@@ -584,6 +639,7 @@ int crt_destroy(crt_ctx* ctx) {
     if (ctx->state) cudaFree(ctx->state);
     if (ctx->comp_lut) cudaFree(ctx->comp_lut);
     if (ctx->d_origin) cudaFree(ctx->d_origin);
+    if (ctx->d_ws_tiles) cudaFree(ctx->d_ws_tiles);
     for (Shard& sh : ctx->shards) {
         if (sh.stream) { cudaStreamSynchronize(sh.stream); cudaStreamDestroy(sh.stream); }
         if (sh.done) cudaEventDestroy(sh.done);

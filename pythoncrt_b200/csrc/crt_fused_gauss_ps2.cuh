@@ -76,7 +76,7 @@ template <int K, bool FAST, int MINB, bool TST, int SPEC = 0, bool TIN = false>
 __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, FrameDev f_arg, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                            float* __restrict__ state, float* __restrict__ q_out, int has_prev,
                                                            const __grid_constant__ CUtensorMap map_st, const __grid_constant__ CUtensorMap map_in,
-                                                           int frame) {
+                                                           int frame, int th) {
     Dev d = d_arg;
     FrameDev f = f_arg;
     specialise<SPEC>(d, f);             // SPEC != 0: feature flags become compile-time constants (crt_fused_ps2.cuh)
@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
     for (int i = 0; i <= R; ++i) { taps[R + i] = d.taps[R + i]; taps[R - i] = taps[R + i]; }
     MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
     __syncthreads();
-    const int tiles_x = (d.W + P2_TW - 1) / P2_TW, ntiles = tiles_x * ((d.H + P2_TH - 1) / P2_TH);
+    const int tiles_x = (d.W + P2_TW - 1) / P2_TW, ntiles = tiles_x * ((d.H + th - 1) / th);
+    const int nby_t = (th >> 1) + 2 * HB, nblk = NBX * nby_t;      // block rows / blocks of a tile of th rows + halo (th <= P2_TH: the buffers hold NBY rows)
+    const uint32_t st_bytes = (uint32_t)th * P2_TW * 3 * 4;
     const int step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;      // tile += gridDim.x without a division per tile
     int tby = blockIdx.x / tiles_x, tbx = blockIdx.x - tby * tiles_x;
     const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
@@ -139,17 +141,17 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
     const int aa = as < 0 ? -as : as;
     if (TIN && tid == 0 && (int)blockIdx.x < ntiles) {              // first tile's input: independent of the previous kernel
         mbar_expect_tx(&bar_in, RAW_BYTES);
-        tma_load_2d_hint(s_raw, &map_in, (6 * ((tbx * P2_TW >> 1) - HB) - 3 * aa) & ~15, frame * d.hh + (tby * P2_TH >> 1) - HB, &bar_in, L2_EVICT_FIRST);
+        tma_load_2d_hint(s_raw, &map_in, (6 * ((tbx * P2_TW >> 1) - HB) - 3 * aa) & ~15, frame * d.hh + (tby * th >> 1) - HB, &bar_in, L2_EVICT_FIRST);
     }
     int iter = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {    // persistent CTAs, tables staged once
-        const int ox0 = tbx * P2_TW, oy0 = tby * P2_TH;
-        const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + P2_TH, d.H) - 1;
+        const int ox0 = tbx * P2_TW, oy0 = tby * th;
+        const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + th, d.H) - 1;
         if (TST && tile_out && tid == 0) {
             // The previous tile's TMA store must have drained the tile buffer; then fetch this tile's state.  The first tile
             // waits for the previous kernel of the stream first (this thread only: the other warps start their grading).
             if (iter > 0) bulk_wait_read(); else griddep_wait();
-            if (use_state) { mbar_expect_tx(&bar_st, P2_ST_BYTES); tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st); }
+            if (use_state) { mbar_expect_tx(&bar_st, st_bytes); tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st); }
         }
         if (tid < P2_TH) {
             const int y = oy0 + tid;
@@ -176,8 +178,8 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
                 const int xoff = 6 * gbx0 - ((6 * gbx0 - 3 * aa) & ~15);
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
-                    if ((tid & ~31) + it * P2_NT >= NBX * NBY) break;
-                    const int u = imin(tid + it * P2_NT, NBX * NBY - 1);
+                    if ((tid & ~31) + it * P2_NT >= nblk) break;
+                    const int u = imin(tid + it * P2_NT, nblk - 1);
                     const int bj = u / NBX, bi = u - bj * NBX;
                     const uint8_t* p = s_raw + (imin(imax(gby0 + bj, 0), d.hh - 1) - gby0) * P2_RAW_W + 6 * bi + xoff;
                     raw[it][0] = p[-3 * as];
@@ -188,8 +190,8 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
                 const int W3 = d.W * 3;
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
-                    if ((tid & ~31) + it * P2_NT >= NBX * NBY) break;        // warp-uniform: whole surplus warps skip the iteration
-                    const int u = imin(tid + it * P2_NT, NBX * NBY - 1);     // surplus lanes repeat the last block (no divergence)
+                    if ((tid & ~31) + it * P2_NT >= nblk) break;        // warp-uniform: whole surplus warps skip the iteration
+                    const int u = imin(tid + it * P2_NT, nblk - 1);     // surplus lanes repeat the last block (no divergence)
                     const int bj = u / NBX, bi = u - bj * NBX;
                     const int sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
                     const uint8_t* p = in + (unsigned)(sy * W3 + 6 * (gbx0 + bi));      // < 2^31 (checked by plan_fused)
@@ -200,8 +202,8 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
             } else {
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
-                    if ((tid & ~31) + it * P2_NT >= NBX * NBY) break;
-                    const int u = imin(tid + it * P2_NT, NBX * NBY - 1);
+                    if ((tid & ~31) + it * P2_NT >= nblk) break;
+                    const int u = imin(tid + it * P2_NT, nblk - 1);
                     const int bj = u / NBX, bi = u - bj * NBX;
                     const int sx = 2 * imin(imax(gbx0 + bi, 0), d.hw - 1), sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
                     const uint8_t* row = in + (size_t)sy * d.W * 3;
@@ -213,8 +215,8 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
             if (TST && iter == 0) mbar_wait(&bar_tab, 0);   // the tables have landed (the loads above are already in flight)
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
-                if ((tid & ~31) + it * P2_NT >= NBX * NBY) break;
-                const int u = imin(tid + it * P2_NT, NBX * NBY - 1);
+                if ((tid & ~31) + it * P2_NT >= nblk) break;
+                const int u = imin(tid + it * P2_NT, nblk - 1);
                 const int bj = u / NBX, bi = u - bj * NBX;
                 const F3 v1 = colour(d, mk3(s_unit[raw[it][0]], s_unit[raw[it][1]], s_unit[raw[it][2]]), s_pow);
                 const F3 sv = bloom_src(d, v1);
@@ -232,13 +234,14 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
             int nbx = tbx + step_x, nby = tby + step_y;
             if (nbx >= tiles_x) { nbx -= tiles_x; ++nby; }
             mbar_expect_tx(&bar_in, RAW_BYTES);
-            tma_load_2d_hint(s_raw, &map_in, (6 * ((nbx * P2_TW >> 1) - HB) - 3 * aa) & ~15, frame * d.hh + (nby * P2_TH >> 1) - HB, &bar_in, L2_EVICT_FIRST);
+            tma_load_2d_hint(s_raw, &map_in, (6 * ((nbx * P2_TW >> 1) - HB) - 3 * aa) & ~15, frame * d.hh + (nby * th >> 1) - HB, &bar_in, L2_EVICT_FIRST);
         }
 
         // ---- phase 2: row pass over block rows; a task = 4 outputs along x for a pair of block rows ----
-        for (int u = tid; u < 3 * (NBY / 2) * (P2_TW / 4); u += P2_NT) {
+        const int nyp = (nby_t + 1) >> 1;                                    // pairs of block rows
+        for (int u = tid; u < 3 * nyp * (P2_TW / 4); u += P2_NT) {
             const int xblk = u & (P2_TW / 4 - 1), t = u >> 4;                // P2_TW / 4 == 16
-            const int ch = t / (NBY / 2), yp = t - ch * (NBY / 2);
+            const int ch = (t >= nyp) + (t >= 2 * nyp), yp = t - ch * nyp;
             const float2* src = reinterpret_cast<const float2*>(Sb + (ch * NBX + 2 * xblk) * PITCH) + yp;
             float2 v[MR];
 #pragma unroll
@@ -335,11 +338,12 @@ inline int launch_fused_gauss_ps2_t(LaunchEnv& env, const Dev& d, const FrameDev
     }
     static const bool persist = env_int("CRT_PS2_PERSIST", 1) != 0;
     const int resident = persist ? it->second : (1 << 30);
-    const int ntiles = ((d.W + P2_TW - 1) / P2_TW) * ((d.H + P2_TH - 1) / P2_TH);
+    const int th = maps ? maps->th : P2_TH;          // tile height of this call (the state map's box has th rows)
+    const int ntiles = ((d.W + P2_TW - 1) / P2_TW) * ((d.H + th - 1) / th);
     const dim3 grid(ntiles < resident ? ntiles : resident);
     static const CUtensorMap no_map{};
     const cudaError_t e = launch_pdl(kern, grid, dim3(P2_NT), smem, st, pdl, d, f, in, out, state, q_out, has_prev, tst ? maps->st : no_map,
-                                     tin ? *gmap_in : no_map, maps ? maps->frame : 0);
+                                     tin ? *gmap_in : no_map, maps ? maps->frame : 0, th);
     return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
 }
 

@@ -86,6 +86,12 @@ inline bool spec_matches(int spec, const Dev& d, bool flicker_on, bool fast_tail
     return true;
 }
 
+// the TMA-pipelined variants' input box: 256 bytes must cover the tile's blocks, the aberration shift and the alignment slack
+inline bool fused_ps2_pipe_supported(const Dev& d) {
+    const int a0 = d.aberr != 0 ? d.aberr_mod : 0, as = a0 > (d.W >> 1) ? a0 - d.W : a0;
+    return (d.W & 7) == 0 && as >= -6 && as <= 6 && env_int("CRT_PIPE", 1) != 0;
+}
+
 CRT_HD bool fused_ps2_supported(const Dev& d, bool glitch_on) {
     return d.pix_uniform == 2 && d.even_dims && (d.W & 3) == 0 && !d.warp_on && !glitch_on && d.text_mode == 0 && d.bloom_mode != 2;
 }
@@ -100,7 +106,7 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
                                                const float (*s_sel)[12], float* __restrict__ state, uint8_t* __restrict__ out, float* __restrict__ q_out, int has_prev,
                                                int ox0, int oy0, int ox1, int oy1, int xb, int y0, const float (&t1)[2][3], BloomFn&& bloom,
                                                float* s_prev = nullptr, bool state_in_smem = false, RowFn&& row_begin = RowFn(),
-                                               int s_pitch = P2_TW * 3) {
+                                               int s_pitch = P2_TW * 3, bool allow_fast = true) {
     // row_begin(r) runs before row r of the patch is evaluated (e.g. to compute that row's bloom values only then)
     // Both rows of the patch are inside the frame (even frame height, even y0), so the two rows' arithmetic is one
     // straight-line block the scheduler can interleave.
@@ -141,7 +147,7 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
             finish_quad(d, state, out, q_out, has_prev, y, xb, 4, pixel);
         }
     };
-    const bool fast = FAST && ox0 >= d.comp_x0 && ox1 <= d.comp_x1;        // block-uniform
+    const bool fast = FAST && allow_fast && ox0 >= d.comp_x0 && ox1 <= d.comp_x1;        // block-uniform
     if (fast) {
         float cvig[4], cscan[4];
         // composite table (bright: s_fwd, dim: s_inv == s_fwd + 1028) per column and channel: the table offset rides on the magic
@@ -195,6 +201,8 @@ __device__ __forceinline__ void ps2_patch_tail(const Dev& d, const FrameDev& f, 
             const int y = y0 + r;
             row_begin(r);
             auto pixel = [&](int yy, int x, int k) -> F3 {
+                // (tiles of the source-driven warp kernel reach over the frame's edge: nothing to evaluate out there)
+                if ((unsigned)x >= (unsigned)d.W || (unsigned)yy >= (unsigned)d.H) return mk3(0.f, 0.f, 0.f);
                 F3 v = mk3(t1[k >> 1][0], t1[k >> 1][1], t1[k >> 1][2]);
                 if (BLOOM) v = add_bloom(d, v, bloom(r, k));
                 return after_bloom_fast(d, f, v, yy, x, s_fwd, s_inv, mt, yy - oy0, x - ox0);
@@ -398,6 +406,8 @@ struct Ps2Maps {                 // host-encoded tensor maps (crt_abi.cu)
     CUtensorMap in;              // uint8 [frames * H/2 even rows][W*3] (row pitch 2 W*3), box 256 x 18
     CUtensorMap st;              // float32 [H][W*3], box 192 x 32: the state buffer, or the pre-warp image in the two-pass path
     int frame;                   // index of this launch's frame inside `in`
+    int th = 32;                 // tile height of the single-pass block kernels (even, <= P2_TH) = rows of st's box: chosen per
+                                 // call so that the tiles of a frame fill whole waves of resident CTAs (choose_tile_h, crt_abi.cu)
 };
 
 // THR: the bloom threshold is on (a second block array for the thresholded source; 3 CTAs per SM instead of 4)
@@ -405,7 +415,7 @@ template <bool BLOOM, bool FAST, bool THR, int SPEC = 0>
 __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg, FrameDev f_arg, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                           float* __restrict__ state, float* __restrict__ q_out, int has_prev,
                                                           const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_st,
-                                                          int frame) {
+                                                          int frame, int th) {
     Dev d = d_arg;
     FrameDev f = f_arg;
     specialise<SPEC>(d, f);             // SPEC != 0: feature flags become compile-time constants (see above)
@@ -429,7 +439,8 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
     const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
     const int as = a0 > (d.W >> 1) ? a0 - d.W : a0;                         // signed shift (aberr_mod is taken modulo W)
     const int aa = as < 0 ? -as : as;
-    const int tiles_x = (d.W + P2_TW - 1) / P2_TW, ntiles = tiles_x * ((d.H + P2_TH - 1) / P2_TH);
+    const int tiles_x = (d.W + P2_TW - 1) / P2_TW, ntiles = tiles_x * ((d.H + th - 1) / th);
+    const uint32_t st_bytes = (uint32_t)th * P2_TW * 3 * 4;      // the state box: th rows
     const int step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;
     int tby = blockIdx.x / tiles_x, tbx = blockIdx.x - tby * tiles_x;
     if (tid == 0) {
@@ -437,7 +448,7 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
         fence_mbar_init();
         // first tile's input: independent of the previous kernel
         mbar_expect_tx(&bar_in[0], P2_RAW_BYTES);
-        tma_load_2d_hint(s_raw, &map_in, (6 * ((tbx * P2_TW >> 1) - 1) - 3 * aa) & ~15, frame * d.hh + (tby * P2_TH >> 1) - 1, &bar_in[0], L2_EVICT_FIRST);
+        tma_load_2d_hint(s_raw, &map_in, (6 * ((tbx * P2_TW >> 1) - 1) - 3 * aa) & ~15, frame * d.hh + (tby * th >> 1) - 1, &bar_in[0], L2_EVICT_FIRST);
     }
     const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
     const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
@@ -452,8 +463,8 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
     MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int ox0 = tbx * P2_TW, oy0 = tby * P2_TH;
-        const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + P2_TH, d.H) - 1;
+        const int ox0 = tbx * P2_TW, oy0 = tby * th;
+        const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + th, d.H) - 1;
         const int gbx0 = (ox0 >> 1) - 1, gby0 = (oy0 >> 1) - 1;
         // next tile of this CTA
         int nbx = tbx + step_x, nby = tby + step_y;
@@ -462,12 +473,12 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
         if (tid == 0) {
             if (it > 0 && tile_out) {            // the previous tile's TMA store must have drained the buffer; then fetch this tile's state
                 bulk_wait_read();
-                if (use_state) { mbar_expect_tx(&bar_st, P2_ST_BYTES); tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st); }
+                if (use_state) { mbar_expect_tx(&bar_st, st_bytes); tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st); }
             }
             if (tile + (int)gridDim.x < ntiles) {      // next tile's input into the other buffer (last read two barriers ago)
                 mbar_expect_tx(&bar_in[buf ^ 1], P2_RAW_BYTES);
                 tma_load_2d_hint(s_raw + (buf ^ 1) * P2_RAW_BYTES, &map_in, (6 * ((nbx * P2_TW >> 1) - 1) - 3 * aa) & ~15,
-                                 frame * d.hh + (nby * P2_TH >> 1) - 1, &bar_in[buf ^ 1], L2_EVICT_FIRST);
+                                 frame * d.hh + (nby * th >> 1) - 1, &bar_in[buf ^ 1], L2_EVICT_FIRST);
             }
         }
         if (tid < P2_TH) {
@@ -492,7 +503,7 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
 #pragma unroll
             for (int i = 0; i < NIT; ++i) {
                 const int u = tid + i * P2_NT;
-                if (u < P2_BW * P2_BH) {
+                if (u < P2_BW * ((th >> 1) + 2)) {
                     const int bj = u / P2_BW, bi = u - bj * P2_BW;
                     uint32_t r0, r1, r2;
                     if (x_inside) {
@@ -517,7 +528,7 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
         griddep_wait();         // previous kernel of the stream complete: state / pre-warp image / noise may be touched from here on
         if (use_state) {
             if (it == 0 && tid == 0) {           // first tile: the state may only be fetched now
-                mbar_expect_tx(&bar_st, P2_ST_BYTES);
+                mbar_expect_tx(&bar_st, st_bytes);
                 tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st);
             }
             mbar_wait(&bar_st, it & 1);
@@ -570,10 +581,6 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
     if (tile_out && tid == 0) bulk_wait_all();      // the last tile's store has completed before the CTA exits
 }
 
-inline bool fused_ps2_pipe_supported(const Dev& d) {
-    const int a0 = d.aberr != 0 ? d.aberr_mod : 0, as = a0 > (d.W >> 1) ? a0 - d.W : a0;
-    return (d.W & 7) == 0 && as >= -6 && as <= 6 && env_int("CRT_PIPE", 1) != 0;
-}
 
 #if defined(CRT_TU_PS2)      // launcher: compiled only in the translation unit that owns these kernels (build.py)
 inline int run_fused_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
@@ -598,8 +605,9 @@ inline int run_fused_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const 
         if (env.raise((const void*)kern, P2_PIPE_SMEM) &&
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM) != cudaSuccess) return 2;
         const int resident_pipe = env.sms * (thr ? 3 : 4);
-        const cudaError_t e = launch_pdl(kern, dim3(ntiles < resident_pipe ? ntiles : resident_pipe), dim3(P2_NT), (size_t)P2_PIPE_SMEM, st, pdl,
-                                         d, f, in, out, state, q_out, has_prev, maps->in, maps->st, maps->frame);
+        const int ntiles_th = (int)grid.x * ((d.H + maps->th - 1) / maps->th);      // tiles of maps->th rows
+        const cudaError_t e = launch_pdl(kern, dim3(ntiles_th < resident_pipe ? ntiles_th : resident_pipe), dim3(P2_NT), (size_t)P2_PIPE_SMEM, st, pdl,
+                                         d, f, in, out, state, q_out, has_prev, maps->in, maps->st, maps->frame, maps->th);
         ++*launches;
         return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
     }

@@ -33,6 +33,7 @@ struct LaunchEnv {
 
 struct FusedPlan;
 struct WarpPs2Plan;
+struct WsTile;
 struct Ps2Maps;
 struct Scratch;
 
@@ -40,6 +41,8 @@ int launch_fused_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint
                      cudaStream_t st, int* launches, bool pdl, const Ps2Maps* maps);
 int launch_warp_ps2(LaunchEnv& env, const WarpPs2Plan& pl, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state,
                     int has_prev, cudaStream_t st, int* launches, bool pdl);
+int launch_warp_src(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, int has_prev, cudaStream_t st,
+                    int* launches, bool pdl, const WsTile* d_tiles, int ntiles, int ntx, int nty, const Ps2Maps* maps);
 int launch_fused_gauss_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out,
                            int has_prev, cudaStream_t st, int* launches, bool pdl, const Ps2Maps* maps, const CUtensorMap* gmap_in);
 int launch_fused_gauss(LaunchEnv& env, int th, int nt, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state,

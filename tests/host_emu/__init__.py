@@ -30,7 +30,8 @@ def _stale() -> bool:
     if not os.path.isfile(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("crt_math.cuh", "crt_stages.cuh", "crt_derive.h", "crt_fused.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("crt_math.cuh", "crt_stages.cuh", "crt_derive.h", "crt_fused.cuh", "crt_fused_ps2.cuh",
+                                                   "crt_fused_warp_src.cuh", "crt_launch.h", "crt_tma.cuh")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -123,3 +124,22 @@ def plan(params: CrtParams, W: int, H: int, variant: str = "export"):
     if rc:
         raise RuntimeError(why.value.decode())
     return dict(ok=bool(out[0]), th=out[1], cap_px=out[2], cap_aux=out[3], smem=out[4], why=why.value.decode())
+
+
+def check_warp_src(params: CrtParams, W: int, H: int, variant: str = "export"):
+    """Planner of the source-driven warp kernel on the host: dict(ok, tiles, violations, max_quads, box_px, why)."""
+    L = lib()
+    c, tabs = build_config(params, W, H, variant=variant)
+    ptrs = (C.c_void_p * 8)()
+    sizes = (C.c_size_t * 8)()
+    for k, a in tabs.items():
+        ptrs[k] = a.ctypes.data
+        sizes[k] = a.nbytes
+    ps = int(params.pixel_size)
+    uni = ps if ps > 1 and W % ps == 0 and H % ps == 0 else 0
+    out = (C.c_longlong * 5)()
+    why = C.create_string_buffer(256)
+    rc = L.emu_check_warp_src(C.byref(c), W, H, ptrs, sizes, uni, out, why, 256)
+    if rc:
+        raise RuntimeError(why.value.decode())
+    return dict(ok=bool(out[0]), tiles=out[1], violations=out[2], max_quads=out[3], box_px=out[4], why=why.value.decode())

@@ -13,6 +13,7 @@
 #include "../../pythoncrt_b200/csrc/crt_derive.h"
 #include "../../pythoncrt_b200/csrc/crt_stages.cuh"
 #include "../../pythoncrt_b200/csrc/crt_fused.cuh"   // host-side tile planner only
+#include "../../pythoncrt_b200/csrc/crt_fused_warp_src.cuh"   // host-side planner of the source-driven warp kernel
 
 using namespace crt;
 
@@ -104,6 +105,69 @@ extern "C" int emu_plan(const crt_params* p, int W, int H, const void* const* ta
     FusedPlan pl = plan_fused(d, glitch_active(*p));
     out[0] = pl.ok; out[1] = pl.th; out[2] = pl.cap_px; out[3] = pl.cap_aux; out[4] = (long long)pl.smem;
     strncpy(why, pl.why, whylen - 1); why[whylen - 1] = 0;
+    return 0;
+}
+
+// Planner of the source-driven warp kernel (csrc/crt_fused_warp_src.cuh): build the tile list, then check the partition the
+// kernel relies on for EVERY output pixel — its owner tile exists, the tile's box of output quads contains it, and every tap
+// that lies inside the frame lies inside the owner's 64 x 32 source tile; pixels whose taps all fall outside the frame belong
+// to exactly one border item.  out = {ok, tiles, violations, largest box in quads, pixels covered by boxes}.
+extern "C" int emu_check_warp_src(const crt_params* p, int W, int H, const void* const* tabs, const size_t* tab_bytes, int pix_uniform,
+                                  long long* out, char* why, int whylen) {
+    TablePtrs t{};
+    for (int i = 0; i < CRT_TABLE_COUNT; ++i) { t.tab[i] = tabs[i]; t.bytes[i] = tab_bytes[i]; }
+    const int hw = W / 2 > 1 ? W / 2 : 1, hh = H / 2 > 1 ? H / 2 : 1;
+    std::vector<Lerp1> dn_x = linear_coords(hw, W), dn_y = linear_coords(hh, H), up_x = linear_coords(W, hw), up_y = linear_coords(H, hh);
+    std::vector<Lerp1> nz(1);
+    t.dn_x = dn_x.data(); t.dn_y = dn_y.data(); t.up_x = up_x.data(); t.up_y = up_y.data(); t.nz_x = nz.data(); t.nz_y = nz.data();
+    t.pix_uniform = pix_uniform;
+    Dev d{};
+    std::string e;
+    int rc = derive_dev(*p, W, H, t, &d, &e);
+    if (rc) { strncpy(why, e.c_str(), whylen - 1); why[whylen - 1] = 0; return rc; }
+    const WarpSrcPlan pl = plan_warp_src(d, glitch_active(*p));
+    strncpy(why, pl.why, whylen - 1); why[whylen - 1] = 0;
+    out[0] = pl.ok; out[1] = (long long)pl.tiles.size(); out[2] = 0; out[3] = 0; out[4] = 0;
+    if (!pl.ok) return 0;
+    const int otx = (W + P2_TW - 1) / P2_TW;
+    std::vector<int> index((size_t)pl.ntx * pl.nty, -1);
+    std::vector<std::vector<int>> border((size_t)otx * ((H + P2_TH - 1) / P2_TH));
+    for (size_t i = 0; i < pl.tiles.size(); ++i) {
+        const WsTile& tl = pl.tiles[i];
+        if (tl.kind == WS_BORDER) border[(size_t)(tl.by0 / P2_TH) * otx + tl.bx0 / P2_TW].push_back((int)i);
+        else index[(size_t)((tl.y0 - WS_ORG) / WS_SY) * pl.ntx + (tl.x0 - WS_ORG) / WS_SX] = (int)i;
+        if ((long long)tl.bw4 * tl.bh > out[3]) out[3] = (long long)tl.bw4 * tl.bh;
+        out[4] += (long long)tl.bw4 * 4 * tl.bh;
+        if (tl.kind != WS_BORDER && (tl.x0 % 2 || tl.y0 % 2)) ++out[2];
+        if (tl.bx0 % 4) ++out[2];
+        if ((tl.kind == WS_BORDER) != ((int)i >= pl.n_source)) ++out[2];          // border items come last
+    }
+    long long bad = 0;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const Taps tp = warp_taps_n(d, warp_norm((float)x, d.warp_cx, d.warp_dx), warp_norm((float)y, d.warp_cy, d.warp_dy));
+            if (ws_outside(tp.ix, tp.iy, W, H)) {                // exactly one border item: the pixel's output tile, box containing it
+                const std::vector<int>& v = border[(size_t)(y / P2_TH) * otx + x / P2_TW];
+                if (v.size() != 1) { ++bad; continue; }
+                const WsTile& tl = pl.tiles[v[0]];
+                if (x < tl.bx0 || x >= tl.bx0 + 4 * tl.bw4 || y < tl.by0 || y >= tl.by0 + tl.bh) ++bad;
+                for (int j = 0; j < 4; ++j) {
+                    const int ty = tp.iy + (j >> 1), tx = tp.ix + (j & 1);
+                    if (ty >= 0 && ty < H && tx >= 0 && tx < W) ++bad;          // "outside" means all four taps
+                }
+                continue;
+            }
+            const int k = index[(size_t)ws_owner(tp.iy, WS_SY) * pl.ntx + ws_owner(tp.ix, WS_SX)];
+            if (k < 0) { ++bad; continue; }
+            const WsTile& tl = pl.tiles[k];
+            if (x < tl.bx0 || x >= tl.bx0 + 4 * tl.bw4 || y < tl.by0 || y >= tl.by0 + tl.bh) ++bad;
+            for (int j = 0; j < 4; ++j) {
+                const int ty = tp.iy + (j >> 1), tx = tp.ix + (j & 1);
+                if (ty < 0 || ty >= H || tx < 0 || tx >= W) { if (tl.kind == WS_INTERIOR) ++bad; continue; }
+                if (tx < tl.x0 || tx >= tl.x0 + P2_TW || ty < tl.y0 || ty >= tl.y0 + P2_TH) ++bad;
+            }
+        }
+    out[2] += bad;
     return 0;
 }
 

@@ -407,3 +407,45 @@ def test_state_resize_is_cv2_resize():
         got = eng.resize_state(torch.from_numpy(src).cuda()).cpu().numpy()
         want = cv2.resize(src, (128, 96), interpolation=cv2.INTER_LINEAR)
         assert got.shape == (96, 128, 3) and np.array_equal(got, want), (h0, w0, float(np.abs(got - want).max()))
+
+
+# ------------------------------------------------------------------------- opt-in single-pass warp kernels --
+@pytest.mark.parametrize("env", ["CRT_WARP_SRC", "CRT_WARP_PS2"])
+@pytest.mark.parametrize("name", ["cfg3_warp", "cfg3_warp_structured", "warp_negative", "text_after_warp"])
+def test_opt_in_single_pass_warp_kernels_match_the_oracle(env, name, monkeypatch):
+    """csrc/crt_fused_warp_src.cuh (source-driven) and csrc/crt_fused_warp_ps2.cuh (output-driven) are measured slower than
+    the two-pass path and therefore opt-in (the variable is read when a context is configured); they stay under the same
+    parity bar as the default path: +-1 LSB against the oracle of crt_filter.py:678-690, and against the default path."""
+    case = CASES_BY_NAME[name]
+    base_out, base_state, _ = run_case_gpu(case, "export")
+    monkeypatch.setenv(env, "1")
+    outs, state, fused = run_case_gpu(case, "export")
+    want, _ = harness.run_oracle(case, "export", backend="cv2")
+    worst = max(int(np.abs(o.astype(np.int16) - w.astype(np.int16)).max()) for o, w in zip(outs, want))
+    assert worst <= 1, (env, name, worst)
+    drift = max(int(np.abs(o.astype(np.int16) - b.astype(np.int16)).max()) for o, b in zip(outs, base_out))
+    assert drift <= 1, (env, name, drift)
+    assert np.abs(state - base_state).max() <= 1.0 / 255 + 1e-6
+
+
+@pytest.mark.parametrize("env", ["CRT_WARP_SRC", "CRT_WARP_PS2"])
+def test_opt_in_single_pass_warp_kernels_at_4k(env, monkeypatch):
+    """At BASELINE configs[2]'s size the opt-in kernels take their tiled fast paths (interior tiles, border items): same
+    bytes as the default two-pass path within 1 LSB over a persistence chain."""
+    import torch
+    from pythoncrt_b200.engine import CrtEngine
+    import host_emu
+    p = host_emu.oracle_to_product_params(CASES_BY_NAME["cfg3_warp"].params).but(noise_strength=0.0, glitch_amp_px=0)
+    g = torch.Generator(device="cuda").manual_seed(77)
+    fr = torch.randint(0, 256, (4, 2160, 3840, 3), dtype=torch.uint8, device="cuda", generator=g)
+    res = []
+    for on in (False, True):
+        if on:
+            monkeypatch.setenv(env, "1")
+        eng = CrtEngine(3840, 2160).configure(p)
+        out, state = eng.process(fr, fps=30.0)
+        res.append((out.clone(), state.clone(), int(eng.last_info.kernels_launched)))
+        eng.close()
+    assert res[1][2] < res[0][2]                                     # one kernel per frame instead of two
+    assert int((res[0][0].to(torch.int16) - res[1][0].to(torch.int16)).abs().max()) <= 1
+    assert float((res[0][1] - res[1][1]).abs().max()) <= 1.0 / 255 + 1e-6

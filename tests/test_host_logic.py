@@ -301,3 +301,18 @@ def test_reference_drain_is_what_the_lazy_export_intercepts():
     assert src.count("blended = np.clip(persistence * prev_state + (1.0 - persistence) * static_img, 0.0, 1.0)") == 2
     assert src.count("out_frame = cv2.convertScaleAbs(blended, alpha=255.0, beta=0)") == 2
     assert "executor.submit(\n                    apply_static_effects," in src
+
+
+@pytest.mark.parametrize("w,h,warp", [(128, 96, 0.15), (640, 480, 0.15), (1920, 1080, 0.15), (200, 150, 0.4), (256, 130, -0.2), (1280, 720, 1.0),
+                                      (3840, 2160, 0.15)])
+def test_source_driven_warp_planner_partitions_the_output(w, h, warp):
+    """csrc/crt_fused_warp_src.cuh plan_warp_src: every output pixel has exactly one owner tile (the one holding its top-left
+    tap), lies inside that tile's box of output quads, and all its in-frame taps lie inside the owner's 64 x 32 source tile."""
+    import host_emu
+    r = host_emu.check_warp_src(CrtParams(noise_strength=0.0, warp_strength=warp), w, h)
+    assert r["ok"], r
+    assert r["violations"] == 0, r
+    assert r["box_px"] >= w * h and r["box_px"] <= 3.0 * w * h + 64 * r["tiles"], r      # boxes cover the frame, overlap is bounded
+    # glitch / non-monotone maps / odd sizes are left to the two-pass path
+    assert not host_emu.check_warp_src(CrtParams(noise_strength=0.0, warp_strength=0.15, glitch_amp_px=8, glitch_height_frac=0.5), 128, 96)["ok"]
+    assert not host_emu.check_warp_src(CrtParams(noise_strength=0.0, warp_strength=-0.9), 128, 96)["ok"]
