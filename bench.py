@@ -228,6 +228,7 @@ def measure(workload: str, wl: dict, steps: int, warmup: int, policy: str, time_
     serial_ms = timed(steps)
     kern_ms, kern_n = eng.profile_end()
     fused = int(eng.last_info.fused)
+    clip_frames = int(eng.last_info.reserved[2])          # frames of a step that went through clip-mode launches (<= 64 frames each)
     serial_value = world * N * steps / (serial_ms * 1e-3)
     kern_avg_ms = kern_ms / max(1, kern_n)
     achieved = (W * H * bpp) / (kern_avg_ms * 1e-3) / 1e9 if kern_n else None
@@ -251,9 +252,12 @@ def measure(workload: str, wl: dict, steps: int, warmup: int, policy: str, time_
                              "frac_sustained": serial_value / world * W * H * bpp / 1e9 / peak},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                         "traffic": None, "peak_source": peak_src, "kernel": KERNELS.get(fused),
-                        "scope": "all kernels of one frame, timed alone on one stream (event-fenced, no other shard running)",
-                        "kernel_avg_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "kernel_timed_every": time_every,
-                        "kernel_share_of_step": (kern_ms * time_every / serial_ms) if serial_ms else None,
+                        "scope": ("clip-mode launches (one launch = a run of up to 64 frames chained tile by tile), timed alone on one stream: "
+                                  "launch duration / frames of the launch; algorithmic bytes per launch = bytes per frame x frames")
+                        if clip_frames else "all kernels of one frame, timed alone on one stream (event-fenced, no other shard running)",
+                        "clip_mode_frames_per_step": clip_frames,
+                        "kernel_avg_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "kernel_timed_every": 1 if clip_frames else time_every,
+                        "kernel_share_of_step": (kern_ms * (1 if clip_frames else time_every) / serial_ms) if serial_ms else None,
                         "frac_sustained": sustained / peak,
                         "sustained_note": "per-GPU frames/s x algorithmic bytes / peak, with the intra-GPU temporal shards running concurrently"}}
     if keep:

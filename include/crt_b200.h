@@ -134,7 +134,8 @@ typedef struct crt_frame {
 typedef struct crt_launch_info {
     int32_t kernels_launched;       /* kernels of this library launched by the call */
     int32_t fused;                  /* 1 = single fused tile kernel, 2 = two-pass (fused first pass + gather), 0 = staged kernels */
-    int32_t reserved[6];            /* [0] = temporal shards the call ran concurrently (crt_set_shards), [1] = warm-up frames per shard */
+    int32_t reserved[6];            /* [0] = temporal shards the call ran concurrently (crt_set_shards), [1] = warm-up frames per shard,
+                                     * [2] = frames that went through clip-mode launches (one launch per run of up to 64 frames) */
 } crt_launch_info;
 
 int crt_abi_version(void);

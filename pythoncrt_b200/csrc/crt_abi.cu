@@ -73,6 +73,8 @@ struct crt_ctx {
     LaunchEnv env;                      // per-context launch state (SM count, configured kernels): no process-wide statics
     CUtensorMap map_gather{};           // float32 [H][W*3] map of the state buffer with the gather kernel's 192 x 16 box
     const void* map_gather_ptr = nullptr;
+    int* d_clip_sync = nullptr; int clip_sync_cap = 0;      // clip mode: item counter + per-tile frame counters
+    std::vector<int> prof_frames;       // frames covered by each profile sample (clip mode: a launch covers many)
     int tile_h = 32;                    // tile height of the single-pass block kernels when a frame runs alone (choose_tile_h)
     Ps2Maps maps{};                     // tensor maps of the TMA-pipelined block kernel, valid for (maps_in, maps_frames, maps_st)
     const void* maps_in = nullptr; const void* maps_st = nullptr; int maps_frames = 0;
@@ -244,7 +246,14 @@ void prof_mark(crt_ctx* ctx, cudaStream_t st, bool stop) {
     if (!stop) ctx->prof_open = (ctx->prof_tick++ % ctx->prof_every) == 0;
     if (!ctx->prof_open) return;
     cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + (stop ? 1 : 0)], st);
-    if (stop) { ++ctx->prof_n; ctx->prof_open = false; }
+    if (stop) { if ((int)ctx->prof_frames.size() <= ctx->prof_n) ctx->prof_frames.resize(ctx->prof_n + 1, 1); ctx->prof_frames[ctx->prof_n] = 1; ++ctx->prof_n; ctx->prof_open = false; }
+}
+
+// ... and around a clip-mode launch, which covers `frames` frames
+void prof_mark_clip(crt_ctx* ctx, cudaStream_t st, bool stop, int frames) {
+    if (!ctx->prof_on || ctx->prof_n >= ctx->prof_cap) return;
+    cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + (stop ? 1 : 0)], st);
+    if (stop) { if ((int)ctx->prof_frames.size() <= ctx->prof_n) ctx->prof_frames.resize(ctx->prof_n + 1, 1); ctx->prof_frames[ctx->prof_n++] = frames; }
 }
 
 // One frame through the staged kernels.
@@ -457,22 +466,81 @@ int launch_frame(crt_ctx* ctx, const Call& c, int index, const uint8_t* in_i, ui
     return rc;
 }
 
+// Clip mode applies to the single-pass block kernel with fast bloom / no bloom whose frames need nothing generated per frame
+// (no noise plane, no glitch table) — the CLI's default chain among them; the caller's state must be blended (persistence > 0).
+bool clip_wanted(crt_ctx* ctx, const uint8_t* d_out, const float* d_state, const float* d_img, int n_frames) {
+    const bool use_clip = env_int("CRT_CLIP", 1) != 0;      // read per call: tests switch it inside one process
+    if (!use_clip || !ctx || !ctx->have_params || n_frames < 2 || !d_out || !d_state || d_img || ctx->policy == 1) return false;
+    if (!ctx->dev_ok && build_dev(ctx)) return false;
+    const crt_params& p = ctx->p;
+    if (!(ctx->plan.ok && ctx->plan.ps2 && p.persistence > 0.0 && !ctx->dev.noise_on && !glitch_active(p) && !ctx->plan_w.ok && !ctx->plan_s.ok))
+        return false;
+    if (ctx->plan.gauss_k && !fused_gauss_ps2_clip_supported(ctx->dev, ctx->plan.gauss_k)) return false;
+    // A tile's frames are a serial chain: a frame takes at least one tile latency, whatever the size.  With fewer tiles than
+    // resident CTAs the chain is the bound (measured, run 43: 720p 11.0 us per frame = one tile latency, 90 k frames/s against
+    // 178 k with four temporal shards; VGA 106 k against 130 k) -> clip mode from one tile per resident CTA upwards.
+    const int ntiles = ((ctx->W + P2_TW - 1) / P2_TW) * ((ctx->H + P2_TH - 1) / P2_TH);
+    const int resident = ctx->env.sms * ((ctx->plan.gauss_k || (ctx->dev.bloom_mode == 1 && ctx->dev.thr_on)) ? 3 : 4);
+    return ntiles >= env_int("CRT_CLIP_MIN_TILES", resident);
+}
+
 int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_state, int state_valid, float* d_img,
                  const crt_frame* frames, int n_frames, cudaStream_t st, crt_launch_info* info) {
     if (!ctx) return CRT_ERR_INVALID;
     if (n_frames > 0 && !frames) return fail(ctx, CRT_ERR_INVALID, "null buffer");
     Call c;
-    int rc = prepare_call(ctx, d_in, n_frames, d_out, d_state, d_img, &c); if (rc) return rc;
+    const bool try_clip = clip_wanted(ctx, d_out, d_state, d_img, n_frames);
+    int rc = prepare_call(ctx, d_in, n_frames, d_out, d_state, d_img, &c, try_clip); if (rc) return rc;
     static const bool use_pdl = env_int("CRT_PDL", 1) != 0;
     const size_t fb = c.frame_px * 3;
-    int launches = 0;
-    for (int i = 0; i < n_frames; ++i) {
+    int launches = 0, i = 0, clip_frames = 0;
+    if (try_clip && c.pipe && c.want_fused && c.persist && (!ctx->plan.gauss_k || c.gauss_in)) {
+        // Clip mode (crt_fused_ps2.cuh, ClipArgs): runs of up to clip_max_frames() frames in ONE launch each, the frames of a
+        // run chained tile by tile through the persistence state.  A first frame without a valid state goes alone (no blend).
+        if (!state_valid) {
+            rc = launch_frame(ctx, c, 0, d_in, d_out, nullptr, d_state, 0, false, frames[0], st, &launches);
+            if (rc) return rc;
+            i = 1;
+        }
+        const Dev& d = ctx->dev;
+        const int ntiles = ((d.W + P2_TW - 1) / P2_TW) * ((d.H + ctx->maps.th - 1) / ctx->maps.th);
+        if (ctx->clip_sync_cap < 1 + ntiles) {
+            if (ctx->d_clip_sync) cudaFree(ctx->d_clip_sync);
+            ctx->d_clip_sync = nullptr; ctx->clip_sync_cap = 0;
+            CU(cudaMalloc((void**)&ctx->d_clip_sync, (size_t)(1 + ntiles) * sizeof(int)));
+            ctx->clip_sync_cap = 1 + ntiles;
+        }
+        const int max_run = clip_max_frames();
+        std::vector<FrameVar> fv;
+        while (n_frames - i >= 2) {
+            const int nf = n_frames - i < max_run ? n_frames - i : max_run;
+            fv.resize(nf);
+            FrameDev f0{};
+            for (int j = 0; j < nf; ++j) {
+                const FrameDev f = derive_frame(ctx->p, frames[i + j]);
+                if (j == 0) f0 = f;
+                fv[j].phase32 = f.phase32; fv[j].phase = f.phase; fv[j].flicker = f.flicker;
+            }
+            prof_mark_clip(ctx, st, false, nf);
+            CU(cudaMemsetAsync(ctx->d_clip_sync, 0, (size_t)(1 + ntiles) * sizeof(int), st));
+            ctx->maps.frame = i;
+            rc = ctx->plan.gauss_k ? launch_fused_gauss_ps2_clip(ctx->env, d, f0, d_in + (size_t)i * fb, d_out + (size_t)i * fb, d_state, st, &launches,
+                                                                 &ctx->maps, c.gauss_in, nf, fv.data(), ctx->d_clip_sync)
+                                   : launch_fused_ps2_clip(ctx->env, d, f0, d_in + (size_t)i * fb, d_out + (size_t)i * fb, d_state, st, &launches, &ctx->maps,
+                                                           nf, fv.data(), ctx->d_clip_sync);
+            prof_mark_clip(ctx, st, true, nf);
+            if (rc) return fail(ctx, rc == 4 ? CRT_ERR_UNSUPPORTED : CRT_ERR_CUDA, std::string("clip-mode launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+            i += nf; clip_frames += nf;
+        }
+    }
+    for (; i < n_frames; ++i) {
         // Frames after the first may overlap the previous frame's kernel tail (launch_pdl, crt_fused.cuh).  Never frame 0:
         // its input may come from the caller's immediately preceding kernel.
         rc = launch_frame(ctx, c, i, d_in + (size_t)i * fb, d_out ? d_out + (size_t)i * fb : nullptr, d_img ? d_img + (size_t)i * fb : nullptr, d_state,
-                          c.persist && (state_valid || i > 0), i > 0 && use_pdl, frames[i], st, &launches);
+                          c.persist && (state_valid || i > 0), i > 0 && use_pdl && clip_frames == 0, frames[i], st, &launches);
         if (rc) return rc;
     }
+    if (info) info->reserved[2] = clip_frames;
     if (info) { info->kernels_launched = launches; info->fused = c.fused_used; }
     return CRT_OK;
 }
@@ -640,6 +708,7 @@ int crt_destroy(crt_ctx* ctx) {
     if (ctx->comp_lut) cudaFree(ctx->comp_lut);
     if (ctx->d_origin) cudaFree(ctx->d_origin);
     if (ctx->d_ws_tiles) cudaFree(ctx->d_ws_tiles);
+    if (ctx->d_clip_sync) cudaFree(ctx->d_clip_sync);
     for (Shard& sh : ctx->shards) {
         if (sh.stream) { cudaStreamSynchronize(sh.stream); cudaStreamDestroy(sh.stream); }
         if (sh.done) cudaEventDestroy(sh.done);
@@ -712,7 +781,12 @@ int crt_set_policy(crt_ctx* ctx, int policy) {
 int crt_process(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_state, int state_valid, const crt_frame* frames, int n_frames,
                 void* stream, crt_launch_info* info) {
     if (!ctx) return CRT_ERR_INVALID;
-    const int K = (ctx->have_params && d_in && d_out && frames) ? choose_shards(ctx, n_frames) : 1;
+    int K = (ctx->have_params && d_in && d_out && frames) ? choose_shards(ctx, n_frames) : 1;
+    // Clip mode keeps one stream full on its own and is the serial recurrence exactly: for the fast-bloom / no-bloom kernel shards
+    // only on explicit request.  The gaussian kernel's clip mode is exact too but measures below four shards of per-frame launches
+    // (BASELINE configs[1], run 56: 53.0 k against 56-58 k frames/s) -> automatic mode shards it; crt_set_shards(1) gives clip mode.
+    if (K > 1 && ctx->shards_wanted == 0 && env_int("CRT_SHARDS", -1) < 0 && clip_wanted(ctx, d_out, d_state, nullptr, n_frames) &&
+        (!ctx->plan.gauss_k || env_int("CRT_CLIP_GAUSS_AUTO", 0))) K = 1;
     if (K > 1 && (d_state || !(ctx->p.persistence > 0.0)))
         return process_sharded(ctx, K, d_in, d_out, d_state, state_valid, frames, n_frames, (cudaStream_t)stream, info);
     if (info) { info->reserved[0] = 1; info->reserved[1] = 0; }
@@ -826,7 +900,9 @@ int crt_profile_end(crt_ctx* ctx, double* total_ms, int* samples) {
         CU(cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
         tot += ms;
     }
-    *total_ms = tot; *samples = ctx->prof_n;
+    int frames = 0;
+    for (int i = 0; i < ctx->prof_n; ++i) frames += ctx->prof_frames[i];
+    *total_ms = tot; *samples = frames;
     return CRT_OK;
 }
 

@@ -72,11 +72,13 @@ CRT_HD bool fused_gauss_ps2_supported(const Dev& d, bool glitch_on) {
 // read the buffer; for the first tile at kernel entry, before the previous frame's kernel has finished).  ncu (run 25) put
 // 9 % of the stall samples on the first use of the per-thread byte loads.  Tiles on the left / right frame edge, where the
 // chromatic aberration wraps around (np.roll), keep the per-thread loads.
-template <int K, bool FAST, int MINB, bool TST, int SPEC = 0, bool TIN = false>
+// CLIP (with TST): clip mode — a run of frames in one launch, (frame, tile) items from an atomic counter, a tile's frames chained
+// through per-tile flags (ClipArgs, crt_fused_ps2.cuh); `in` / `out` / `frame` describe the first frame of the run
+template <int K, bool FAST, int MINB, bool TST, int SPEC = 0, bool TIN = false, bool CLIP = false>
 __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, FrameDev f_arg, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                            float* __restrict__ state, float* __restrict__ q_out, int has_prev,
                                                            const __grid_constant__ CUtensorMap map_st, const __grid_constant__ CUtensorMap map_in,
-                                                           int frame, int th) {
+                                                           int frame, int th, const __grid_constant__ ClipArgs ca) {
     Dev d = d_arg;
     FrameDev f = f_arg;
     specialise<SPEC>(d, f);             // SPEC != 0: feature flags become compile-time constants (crt_fused_ps2.cuh)
@@ -130,24 +132,57 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
 #pragma unroll
     for (int i = 0; i <= R; ++i) { taps[R + i] = d.taps[R + i]; taps[R - i] = taps[R + i]; }
     MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
+    __shared__ int s_item[2], s_prev[2], s_hint;    // clip mode: the item of the next iteration; tile and frame of the item being stored;
+    if (CLIP && tid == 0) { s_hint = 0; s_item[0] = ca.static_items ? (int)blockIdx.x : atomicAdd(ca.sync, 1); }      // the item's flag as seen earlier
     __syncthreads();
     const int tiles_x = (d.W + P2_TW - 1) / P2_TW, ntiles = tiles_x * ((d.H + th - 1) / th);
+    const int nitems = CLIP ? ntiles * ca.nf : ntiles;
+    const unsigned magic_tx = make_magic(tiles_x);
+    int fr = 0;                                     // frame of the current item within the run
+    int hint = 0;                                   // clip mode, thread 0: the current item's flag as seen one iteration ago
+    auto split = [&](int item, int& ifr, int& iby, int& ibx) {      // ifr on entry: a frame not after the item's (items only grow)
+        int t = item - ifr * ntiles;
+        while (t >= ntiles) { t -= ntiles; ++ifr; }
+        iby = fastdiv(t, magic_tx); ibx = t - iby * tiles_x;
+    };
     const int nby_t = (th >> 1) + 2 * HB, nblk = NBX * nby_t;      // block rows / blocks of a tile of th rows + halo (th <= P2_TH: the buffers hold NBY rows)
     const uint32_t st_bytes = (uint32_t)th * P2_TW * 3 * 4;
     const int step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;      // tile += gridDim.x without a division per tile
     int tby = blockIdx.x / tiles_x, tbx = blockIdx.x - tby * tiles_x;
+    if (CLIP) split(s_item[0] < nitems ? s_item[0] : 0, fr, tby, tbx);
     const int a0 = d.aberr != 0 ? d.aberr_mod : 0;
     const int as = a0 > (d.W >> 1) ? a0 - d.W : a0;                 // signed aberration shift (aberr_mod is taken modulo W)
     const int aa = as < 0 ? -as : as;
-    if (TIN && tid == 0 && (int)blockIdx.x < ntiles) {              // first tile's input: independent of the previous kernel
+    if (TIN && tid == 0 && (CLIP ? s_item[0] : (int)blockIdx.x) < nitems) {      // first tile's input: independent of the previous kernel
         mbar_expect_tx(&bar_in, RAW_BYTES);
-        tma_load_2d_hint(s_raw, &map_in, (6 * ((tbx * P2_TW >> 1) - HB) - 3 * aa) & ~15, frame * d.hh + (tby * th >> 1) - HB, &bar_in, L2_EVICT_FIRST);
+        tma_load_2d_hint(s_raw, &map_in, (6 * ((tbx * P2_TW >> 1) - HB) - 3 * aa) & ~15, (frame + fr) * d.hh + (tby * th >> 1) - HB, &bar_in, L2_EVICT_FIRST);
     }
     int iter = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {    // persistent CTAs, tables staged once
+    for (int tile = CLIP ? s_item[0] : (int)blockIdx.x; tile < nitems; ++iter) {    // persistent CTAs, tables staged once
+        if (CLIP) {
+            split(tile, fr, tby, tbx);
+            const FrameVar fv = ca.fv[fr];
+            f.phase32 = fv.phase32; f.phase = fv.phase; f.flicker = fv.flicker;
+        }
         const int ox0 = tbx * P2_TW, oy0 = tby * th;
         const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + th, d.H) - 1;
-        if (TST && tile_out && tid == 0) {
+        const uint8_t* const in_f = CLIP ? in + fr * ca.frame_bytes : in;
+        uint8_t* const out_f = CLIP ? out + fr * ca.frame_bytes : out;
+        int next = tile + (int)gridDim.x, nfr = fr, nbx = tbx + step_x, nby = tby + step_y;      // next tile of this CTA
+        if (nbx >= tiles_x) { nbx -= tiles_x; ++nby; }
+        // clip mode's bookkeeping, split between thread 0 (state traffic) and thread CLIP_B (next item): see k_fused_ps2_pipe
+        bool owed = false;                   // thread 0: the previous item's completion is still to be published
+        if (CLIP && tid == CLIP_B) next = ca.static_items ? tile + (int)gridDim.x : atomicAdd(ca.sync, 1);
+        if (CLIP && tid == 0) {
+            if (iter > 0) bulk_wait_read(); else griddep_wait();
+            if (iter > 0) owed = true;
+            if (fr > 0 && (iter == 0 || s_hint < fr || (ca.release & 16))) {
+                if (owed) { bulk_wait_all(); clip_publish(ca.sync + 1 + s_prev[0], s_prev[1] + 1, ca.release); owed = false; }
+                clip_wait(ca.sync + 1 + tby * tiles_x + tbx, fr);
+            } else if (fr > 0) clip_acquire(ca.release);
+            mbar_expect_tx(&bar_st, st_bytes); tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st);
+        }
+        if (!CLIP && TST && tile_out && tid == 0) {
             // The previous tile's TMA store must have drained the tile buffer; then fetch this tile's state.  The first tile
             // waits for the previous kernel of the stream first (this thread only: the other warps start their grading).
             if (iter > 0) bulk_wait_read(); else griddep_wait();
@@ -168,6 +203,9 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
         const int gbx0 = (ox0 >> 1) - HB, gby0 = (oy0 >> 1) - HB;
         {
             constexpr int NIT = (NBX * NBY + P2_NT - 1) / P2_NT;
+            // blocks are dealt to the threads rotated by 224: the last, partial round skips warp 0 (and half of warp 7), which keeps
+            // the state traffic of the tile (waits, fences) and so reaches the barrier with the others
+            const int vt = (tid + 224) & (P2_NT - 1);
             uint32_t raw[NIT][3];                                 // 32-bit: a byte array would live in local memory
             // all loads first: their latencies overlap.  Tiles away from the left / right frame edge need neither the
             // block clamp nor the aberration wrap in x: one 32-bit offset per block, byte offsets per channel.
@@ -178,8 +216,8 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
                 const int xoff = 6 * gbx0 - ((6 * gbx0 - 3 * aa) & ~15);
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
-                    if ((tid & ~31) + it * P2_NT >= nblk) break;
-                    const int u = imin(tid + it * P2_NT, nblk - 1);
+                    if ((vt & ~31) + it * P2_NT >= nblk) break;
+                    const int u = imin(vt + it * P2_NT, nblk - 1);
                     const int bj = u / NBX, bi = u - bj * NBX;
                     const uint8_t* p = s_raw + (imin(imax(gby0 + bj, 0), d.hh - 1) - gby0) * P2_RAW_W + 6 * bi + xoff;
                     raw[it][0] = p[-3 * as];
@@ -190,11 +228,11 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
                 const int W3 = d.W * 3;
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
-                    if ((tid & ~31) + it * P2_NT >= nblk) break;        // warp-uniform: whole surplus warps skip the iteration
-                    const int u = imin(tid + it * P2_NT, nblk - 1);     // surplus lanes repeat the last block (no divergence)
+                    if ((vt & ~31) + it * P2_NT >= nblk) break;        // warp-uniform: whole surplus warps skip the iteration
+                    const int u = imin(vt + it * P2_NT, nblk - 1);     // surplus lanes repeat the last block (no divergence)
                     const int bj = u / NBX, bi = u - bj * NBX;
                     const int sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
-                    const uint8_t* p = in + (unsigned)(sy * W3 + 6 * (gbx0 + bi));      // < 2^31 (checked by plan_fused)
+                    const uint8_t* p = in_f + (unsigned)(sy * W3 + 6 * (gbx0 + bi));      // < 2^31 (checked by plan_fused)
                     raw[it][0] = p[-3 * as];
                     raw[it][1] = p[1];
                     raw[it][2] = p[3 * as + 2];
@@ -202,11 +240,11 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
             } else {
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
-                    if ((tid & ~31) + it * P2_NT >= nblk) break;
-                    const int u = imin(tid + it * P2_NT, nblk - 1);
+                    if ((vt & ~31) + it * P2_NT >= nblk) break;
+                    const int u = imin(vt + it * P2_NT, nblk - 1);
                     const int bj = u / NBX, bi = u - bj * NBX;
                     const int sx = 2 * imin(imax(gbx0 + bi, 0), d.hw - 1), sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
-                    const uint8_t* row = in + (size_t)sy * d.W * 3;
+                    const uint8_t* row = in_f + (size_t)sy * d.W * 3;
                     raw[it][0] = row[wrap(sx - a0, d.W) * 3 + 0];
                     raw[it][1] = row[sx * 3 + 1];
                     raw[it][2] = row[wrap(sx + a0, d.W) * 3 + 2];
@@ -215,8 +253,8 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
             if (TST && iter == 0) mbar_wait(&bar_tab, 0);   // the tables have landed (the loads above are already in flight)
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
-                if ((tid & ~31) + it * P2_NT >= nblk) break;
-                const int u = imin(tid + it * P2_NT, nblk - 1);
+                if ((vt & ~31) + it * P2_NT >= nblk) break;
+                const int u = imin(vt + it * P2_NT, nblk - 1);
                 const int bj = u / NBX, bi = u - bj * NBX;
                 const F3 v1 = colour(d, mk3(s_unit[raw[it][0]], s_unit[raw[it][1]], s_unit[raw[it][2]]), s_pow);
                 const F3 sv = bloom_src(d, v1);
@@ -229,12 +267,18 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
                 }
             }
         }
+        if (CLIP && tid == 0) {      // (in the slack the rotation above leaves warp 0; the store was issued a phase ago)
+            if (owed) { bulk_wait_all(); clip_publish(ca.sync + 1 + s_prev[0], s_prev[1] + 1, ca.release); }
+            s_prev[0] = tby * tiles_x + tbx; s_prev[1] = fr;
+        }
         __syncthreads();
-        if (TIN && tid == 0 && tile + (int)gridDim.x < ntiles) {      // the buffer has been read: fetch the next tile's input bytes
-            int nbx = tbx + step_x, nby = tby + step_y;
-            if (nbx >= tiles_x) { nbx -= tiles_x; ++nby; }
+        if (CLIP && tid == CLIP_B) {
+            s_item[(iter & 1) ^ 1] = next; split(next < nitems ? next : 0, nfr, nby, nbx);
+            if (next < nitems && nfr > 0) hint = clip_peek(ca.sync + 1 + nby * tiles_x + nbx);
+        }
+        if (TIN && tid == (CLIP ? CLIP_B : 0) && next < nitems) {      // the buffer has been read: fetch the next tile's input bytes
             mbar_expect_tx(&bar_in, RAW_BYTES);
-            tma_load_2d_hint(s_raw, &map_in, (6 * ((nbx * P2_TW >> 1) - HB) - 3 * aa) & ~15, frame * d.hh + (nby * th >> 1) - HB, &bar_in, L2_EVICT_FIRST);
+            tma_load_2d_hint(s_raw, &map_in, (6 * ((nbx * P2_TW >> 1) - HB) - 3 * aa) & ~15, (frame + nfr) * d.hh + (nby * th >> 1) - HB, &bar_in, L2_EVICT_FIRST);
         }
 
         // ---- phase 2: row pass over block rows; a task = 4 outputs along x for a pair of block rows ----
@@ -289,20 +333,24 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
                     }
                 }
             }
-            ps2_patch_tail<true, FAST>(d, f, mt, s_fwd, s_inv, s_sel, state, out, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
+            ps2_patch_tail<true, FAST>(d, f, mt, s_fwd, s_inv, s_sel, state, out_f, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
                                        [&](int r, int k) { return mk3(bl[r][k][0], bl[r][k][1], bl[r][k][2]); },
                                        tile_out ? s_state + (y0 - oy0) * (P2_TW * 3) + 12 * tx : nullptr, tile_out);
         }
+        if (CLIP && tid == CLIP_B) s_hint = hint;      // (the look's latency has passed behind the tail)
         if (tile_out) fence_proxy_async();      // the new state in shared memory -> visible to the TMA engine
         __syncthreads();        // everyone is done with this tile's tables (and state tile) before the next tile overwrites them
         if (tile_out && tid == 0) {             // one coalesced TMA store per tile (rows outside the frame are clipped); the pre-warp
             tma_store_2d_hint(&map_st, s_state, ox0 * 3, oy0, q_out ? L2_EVICT_LAST : L2_EVICT_NORMAL);      // image is read back by the next kernel
             bulk_commit();
         }
-        tbx += step_x; tby += step_y;
-        if (tbx >= tiles_x) { tbx -= tiles_x; ++tby; }
+        if (CLIP) tile = s_item[(iter & 1) ^ 1];      // written by thread 0 before this iteration's barriers
+        else { tile = next; tbx = nbx; tby = nby; }
     }
-    if (tile_out && tid == 0) bulk_wait_all();      // the last tile's store has completed before the CTA exits
+    if (tile_out && tid == 0) {
+        bulk_wait_all();      // the last tile's store has completed before the CTA exits
+        if (CLIP && iter > 0) clip_publish(ca.sync + 1 + s_prev[0], s_prev[1] + 1, ca.release);
+    }
 }
 
 #if defined(CRT_TU_GAUSS_PS2)      // launcher: compiled only in the translation unit that owns these kernels (build.py)
@@ -343,8 +391,63 @@ inline int launch_fused_gauss_ps2_t(LaunchEnv& env, const Dev& d, const FrameDev
     const dim3 grid(ntiles < resident ? ntiles : resident);
     static const CUtensorMap no_map{};
     const cudaError_t e = launch_pdl(kern, grid, dim3(P2_NT), smem, st, pdl, d, f, in, out, state, q_out, has_prev, tst ? maps->st : no_map,
-                                     tin ? *gmap_in : no_map, maps ? maps->frame : 0, th);
+                                     tin ? *gmap_in : no_map, maps ? maps->frame : 0, th, ClipArgs{});
     return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
+}
+
+// Clip mode (ClipArgs, crt_fused_ps2.cuh): instantiated for the common variant only — composite-LUT tail, state and input tiles by TMA.
+inline bool fused_gauss_ps2_clip_ok(const Dev& d, int K) {
+    const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1;
+    return fast && (K == 5 || K == 7 || K == 9) && fused_gauss_ps2_tin_ok(d, K) &&      // (wider kernels: no room for the input tile)
+           fused_gauss_ps2_smem(K, true) + 16 * 1024 <= 76 * 1024 && fused_gauss_ps2_smem(K, true, true) + 14 * 1024 <= 75 * 1024 &&
+           env_int("CRT_GPS2_TMA_STATE", 1) != 0 && env_int("CRT_GPS2_TMA_INPUT", 1) != 0;
+}
+template <int K, int MINB>
+inline int launch_fused_gauss_ps2_clip_t(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, cudaStream_t st,
+                                         const Ps2Maps* maps, const CUtensorMap* gmap_in, ClipArgs& ca) {
+    const size_t smem = fused_gauss_ps2_smem(K, true, true);
+    auto kern = k_fused_gauss_ps2<K, true, MINB, true, 0, true, true>;
+    static const bool use_spec = env_int("CRT_SPEC", 1) != 0;
+    if (K == 9 && use_spec && spec_matches(SPEC_GRADED, d, f.flicker_on != 0, true))      // BASELINE configs[1]
+        kern = k_fused_gauss_ps2<K == 9 ? 9 : K, true, MINB, true, K == 9 ? SPEC_GRADED : 0, true, true>;
+    auto it = env.memo.find((const void*)kern);
+    if (it == env.memo.end()) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P2_NT, smem);
+        it = env.memo.emplace((const void*)kern, env.sms * (per_sm > 0 ? per_sm : 1)).first;
+    }
+    const long long nitems = (long long)((d.W + P2_TW - 1) / P2_TW) * ((d.H + maps->th - 1) / maps->th) * ca.nf;
+    ca.frame_bytes = (unsigned long long)d.W * d.H * 3;
+    const dim3 grid((unsigned)(nitems < it->second ? nitems : it->second));
+    // items from the atomic counter: with a fixed stride (cooperative launch, as k_fused_ps2_pipe's clip mode) this kernel is 12 %
+    // slower (measured, run 50: 46.5 k against 52.8 k frames/s on BASELINE configs[1]) — its tiles differ in cost and a lagging CTA
+    // then holds up the tiles that wait for its flags
+    const bool use_coop = env_int("CRT_CLIP_COOP_GAUSS", 0) != 0;
+    cudaError_t e = cudaErrorNotSupported;
+    if (use_coop) {
+        ca.static_items = 1;
+        e = launch_coop(kern, grid, dim3(P2_NT), smem, st, d, f, in, out, state, (float*)nullptr, 1, maps->st, *gmap_in, maps->frame, maps->th, ca);
+        if (e != cudaSuccess) cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        ca.static_items = 0;
+        e = launch_pdl(kern, grid, dim3(P2_NT), smem, st, false, d, f, in, out, state, (float*)nullptr, 1, maps->st, *gmap_in, maps->frame, maps->th, ca);
+    }
+    return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
+}
+inline int run_fused_gauss_ps2_clip(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, cudaStream_t st,
+                                    int* launches, const Ps2Maps* maps, const CUtensorMap* gmap_in, ClipArgs& ca) {
+    if (!maps || !gmap_in || !fused_gauss_ps2_clip_ok(d, d.ksize) || ca.nf < 1 || ca.nf > CLIP_MAX_FRAMES) return 4;
+    int rc = 4;
+    switch (d.ksize) {
+        case 5: rc = launch_fused_gauss_ps2_clip_t<5, 3>(env, d, f, in, out, state, st, maps, gmap_in, ca); break;
+        case 7: rc = launch_fused_gauss_ps2_clip_t<7, 3>(env, d, f, in, out, state, st, maps, gmap_in, ca); break;
+        case 9: rc = launch_fused_gauss_ps2_clip_t<9, 3>(env, d, f, in, out, state, st, maps, gmap_in, ca); break;
+        default: break;
+    }
+    if (rc != 4) ++*launches;
+    return rc;
 }
 
 inline int run_fused_gauss_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,

@@ -410,12 +410,73 @@ struct Ps2Maps {                 // host-encoded tensor maps (crt_abi.cu)
                                  // call so that the tiles of a frame fill whole waves of resident CTAs (choose_tile_h, crt_abi.cu)
 };
 
+// ---- clip mode: ONE launch for a run of frames ------------------------------------------------------------------------
+// One launch per frame leaves a B200 half idle at 1080p: launch latency, table staging and — mostly — the last round of every
+// frame, in which a few CTAs run alone on their SMs (kernel alone 26.8 us per 1080p frame against 17.2 us when concurrent
+// temporal shards fill the gaps, round 2 run 33).  The only cross-frame dependency of these kernels is the persistence state of
+// the SAME tile (crt_filter.py:1092 is per pixel), so a run of frames is one queue of (frame, tile) items, frame-major, handed out
+// by an atomic counter to persistent CTAs; item (f, t) waits for done[t] >= f, published by whoever finished (f - 1, t) once its
+// state tile's TMA store has completed.  Items are handed out in order and only to running CTAs, so the owner of every item an
+// item waits for is resident: no deadlock whatever else shares the GPU.  The result is the serial recurrence exactly — no
+// warm-up halo as with temporal shards.  Per-frame scalars (scanline phase, flicker gain) come from a device array.
+constexpr int P1_ROT = 160;              // phase 1 of the TMA-pipelined kernel: rotation of the thread -> block assignment (see there)
+constexpr int CLIP_B = 224;              // the "next item" thread (warp 7: the lightest in phase 1); thread 0 keeps the state traffic
+constexpr int CLIP_MAX_FRAMES = 64;      // frames per launch: their scalars travel as kernel parameters (no copy to wait for)
+struct ClipArgs {
+    int nf = 1;                          // frames in this launch (1: the per-frame launch, everything below unused)
+    int* sync = nullptr;                 // [0]: item counter, [1 + t]: frames of tile t completed — zeroed before the launch
+    unsigned long long frame_bytes = 0;  // W * H * 3
+    int static_items = 0;                // 1: item = blockIdx.x + k * gridDim.x (the launch is cooperative: every CTA is resident); 0: atomic counter
+    int release = 1;                     // publication / acquisition mode bits (clip_publish; CRT_CLIP_RELEASE)
+    FrameVar fv[CLIP_MAX_FRAMES];
+};
+// mode bits (ClipArgs.release, CRT_CLIP_RELEASE): 1 = st.release.gpu, 2 = unqualified fence.proxy.async, 4 = fence.acq_rel.gpu on the
+// consumer's side, 16 = never trust the early look (always ld.acquire in clip_wait).  Default 1: wait_group, proxy fence, release
+// store.  MEASURED (round 2, runs 53-56): with neither 1 nor 2 — cp.async.bulk.wait_group 0, fence.proxy.async.global,
+// st.relaxed.gpu — another SM's TMA load of the tile returns stale 32-byte sectors now and then (10-20 thousand values per
+// 60-frame 1080p clip): the bulk group's completion makes the store visible to the waiting thread, not to the GPU; a
+// MEMBAR.ALL.GPU (either bit) must follow before the flag is raised.  Cost at 4K: 44.6 us per frame without, 47.8 with.
+__device__ __forceinline__ void clip_publish(int* flag, int value, int mode) {
+    // the TMA store of the state tile has completed (bulk_wait_all: its writes are visible to this thread); release them gpu-wide
+    // (SASS: fence.proxy.async without a space is MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC.S, the .global form FENCE.VIEW.ASYNC.G alone;
+    // st.release.gpu is MEMBAR.ALL.GPU + STG.STRONG.GPU)
+    if (mode & 2) asm volatile("fence.proxy.async;" ::: "memory");
+    else asm volatile("fence.proxy.async.global;" ::: "memory");
+    if (mode & 1) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+    else asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+// a look at a flag whose result is not needed yet (the load is in flight until its first use) ...
+__device__ __forceinline__ int clip_peek(const int* flag) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    return v;
+}
+// ... and what turns a successful look into an acquire, also for the TMA load (async proxy) that follows
+__device__ __forceinline__ void clip_acquire(int mode) {
+    if (mode & 4) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    else asm volatile("fence.acquire.gpu;" ::: "memory");            // SASS: CCTL.IVALL
+    if (mode & 2) asm volatile("fence.proxy.async;" ::: "memory");
+    else asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+__device__ __forceinline__ void clip_wait(const int* flag, int value) {
+    int v;
+    const long long t0 = clock64();
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= value) break;
+        __nanosleep(100);
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+    asm volatile("fence.proxy.async.global;" ::: "memory");      // the TMA load that follows reads through the async proxy
+}
+
 // THR: the bloom threshold is on (a second block array for the thresholded source; 3 CTAs per SM instead of 4)
-template <bool BLOOM, bool FAST, bool THR, int SPEC = 0>
-__global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg, FrameDev f_arg, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+// CLIP: clip mode (above); `in` / `out` / `frame` describe the first frame of the run
+template <bool BLOOM, bool FAST, bool THR, int SPEC = 0, bool CLIP = false>
+__global__ void __launch_bounds__(P2_NT, (THR || (CLIP && SPEC == 0)) ? 3 : 4) k_fused_ps2_pipe(Dev d_arg, FrameDev f_arg, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                           float* __restrict__ state, float* __restrict__ q_out, int has_prev,
                                                           const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_st,
-                                                          int frame, int th) {
+                                                          int frame, int th, const __grid_constant__ ClipArgs ca) {
     Dev d = d_arg;
     FrameDev f = f_arg;
     specialise<SPEC>(d, f);             // SPEC != 0: feature flags become compile-time constants (see above)
@@ -443,12 +504,27 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
     const uint32_t st_bytes = (uint32_t)th * P2_TW * 3 * 4;      // the state box: th rows
     const int step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;
     int tby = blockIdx.x / tiles_x, tbx = blockIdx.x - tby * tiles_x;
+    // clip mode: items = (frame, tile) pairs, frame-major, from the counter; s_item[] hands the item of the next iteration to the CTA
+    __shared__ int s_item[2];
+    const int nitems = CLIP ? ntiles * ca.nf : ntiles;
+    int fr = 0;                                     // frame of the current item within the run
+    const unsigned magic_tx = make_magic(tiles_x);
+    auto split = [&](int item, int& ifr, int& iby, int& ibx) {      // item -> frame, tile row, tile column (item < 2^31, tile < 2^16)
+        // ifr on entry: a frame not after the item's (items only grow) -> a compare or two instead of a division
+        int t = item - ifr * ntiles;
+        while (t >= ntiles) { t -= ntiles; ++ifr; }
+        iby = fastdiv(t, magic_tx); ibx = t - iby * tiles_x;
+    };
     if (tid == 0) {
         mbar_init(&bar_in[0], 1); mbar_init(&bar_in[1], 1); mbar_init(&bar_st, 1);
         fence_mbar_init();
+        int first = blockIdx.x;
+        if (CLIP) { first = ca.static_items ? (int)blockIdx.x : atomicAdd(ca.sync, 1); s_item[0] = first; split(first < nitems ? first : 0, fr, tby, tbx); }
         // first tile's input: independent of the previous kernel
-        mbar_expect_tx(&bar_in[0], P2_RAW_BYTES);
-        tma_load_2d_hint(s_raw, &map_in, (6 * ((tbx * P2_TW >> 1) - 1) - 3 * aa) & ~15, frame * d.hh + (tby * th >> 1) - 1, &bar_in[0], L2_EVICT_FIRST);
+        if (first < nitems) {
+            mbar_expect_tx(&bar_in[0], P2_RAW_BYTES);
+            tma_load_2d_hint(s_raw, &map_in, (6 * ((tbx * P2_TW >> 1) - 1) - 3 * aa) & ~15, (frame + fr) * d.hh + (tby * th >> 1) - 1, &bar_in[0], L2_EVICT_FIRST);
+        }
     }
     const float* lut_a = d.triad_comp ? d.triad_comp : d.lut_fwd;
     const float* lut_b = d.triad_comp ? d.triad_comp + 1028 : d.lut_inv;
@@ -461,21 +537,50 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
     ps2_fill_sel(s_sel, tid, d.bgr);
     if (d.col_gamma) for (int i = tid; i < POW_TAB_FLOATS; i += blockDim.x) s_pow[i] = d.pow_tab[i];
     MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
+    if (CLIP) __syncthreads();          // s_item[0] and the tables staged above (the per-frame kernel takes this barrier inside the loop)
     int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    __shared__ int s_prev[2], s_hint;   // clip mode: tile and frame of the item whose state store is in flight; the current item's flag
+    int hint = 0;                       // as thread CLIP_B saw it one iteration ago
+    if (CLIP && tid == 0) s_hint = 0;
+    for (int tile = CLIP ? s_item[0] : (int)blockIdx.x; tile < nitems; ++it) {
+        if (CLIP) {
+            split(tile, fr, tby, tbx);
+            const FrameVar fv = ca.fv[fr];
+            f.phase32 = fv.phase32; f.phase = fv.phase; f.flicker = fv.flicker;
+        }
         const int ox0 = tbx * P2_TW, oy0 = tby * th;
         const int ox1 = imin(ox0 + P2_TW, d.W) - 1, oy1 = imin(oy0 + th, d.H) - 1;
         const int gbx0 = (ox0 >> 1) - 1, gby0 = (oy0 >> 1) - 1;
+        const uint8_t* const in_f = CLIP ? in + fr * ca.frame_bytes : in;
+        uint8_t* const out_f = CLIP ? out + fr * ca.frame_bytes : out;
         // next tile of this CTA
-        int nbx = tbx + step_x, nby = tby + step_y;
+        int nbx = tbx + step_x, nby = tby + step_y, nfr = fr, next = tile + (int)gridDim.x;
         if (nbx >= tiles_x) { nbx -= tiles_x; ++nby; }
         const int buf = it & 1;
-        if (tid == 0) {
+        // Clip mode's bookkeeping is split between two threads of different warps and spread over the iteration so that no round
+        // trip to L2 sits on the tile's critical path.  Thread CLIP_B ("next item"): the counter's atomic is issued here and
+        // consumed after phase 1, where it also fetches the next item's input and takes a look at the next item's flag, which it
+        // hands to thread 0 (s_hint) at the end of the iteration.  Thread 0 ("state"): fetches this item's state at once when the
+        // flag was already set at that look (the normal case: the tile's previous frame is a whole frame of items behind), awaits
+        // the previous store's completion after phase 1, when it has long happened, and publishes it.  Blocking on another CTA's
+        // flag comes only after our own publication — no CTA waits while it owes one: no deadlock.
+        bool owed = false;                   // thread 0: the previous item's completion is still to be published
+        if (CLIP && tid == CLIP_B) next = ca.static_items ? tile + (int)gridDim.x : atomicAdd(ca.sync, 1);
+        if (CLIP && tid == 0 && it > 0) {
+            bulk_wait_read();                // the previous tile's TMA store has drained the buffer
+            owed = true;
+            if (fr > 0 && (s_hint < fr || (ca.release & 16))) {
+                bulk_wait_all(); clip_publish(ca.sync + 1 + s_prev[0], s_prev[1] + 1, ca.release); owed = false;
+                clip_wait(ca.sync + 1 + tby * tiles_x + tbx, fr);
+            } else if (fr > 0) clip_acquire(ca.release);
+            mbar_expect_tx(&bar_st, st_bytes); tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st);
+        }
+        if (!CLIP && tid == 0) {
             if (it > 0 && tile_out) {            // the previous tile's TMA store must have drained the buffer; then fetch this tile's state
                 bulk_wait_read();
                 if (use_state) { mbar_expect_tx(&bar_st, st_bytes); tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st); }
             }
-            if (tile + (int)gridDim.x < ntiles) {      // next tile's input into the other buffer (last read two barriers ago)
+            if (next < nitems) {      // next tile's input into the other buffer (last read two barriers ago)
                 mbar_expect_tx(&bar_in[buf ^ 1], P2_RAW_BYTES);
                 tma_load_2d_hint(s_raw + (buf ^ 1) * P2_RAW_BYTES, &map_in, (6 * ((nbx * P2_TW >> 1) - 1) - 3 * aa) & ~15,
                                  frame * d.hh + (nby * th >> 1) - 1, &bar_in[buf ^ 1], L2_EVICT_FIRST);
@@ -491,7 +596,7 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
             if (d.scan_mode == 2) { double t = (d.scan_tan * (double)x) * d.scan_inv_period; mt.col_scan[c] = (float)(t - floor(t)); }
             if (d.vig_mode == 1) { const float nx = ((float)x - d.vig_cx) * d.vig_irx; mt.col_vig[c] = nx * nx; }
         }
-        if (it == 0) __syncthreads();      // tables staged before the loop; later tiles need no barrier here (see k_fused_ps2)
+        if (!CLIP && it == 0) __syncthreads();      // tables staged before the loop; later tiles need no barrier here (see k_fused_ps2)
 
         // ---- phase 1: one graded value per 2x2 block ----
         mbar_wait(&bar_in[buf], (it >> 1) & 1);                 // this tile's input bytes have landed
@@ -502,7 +607,9 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
             const int xoff = 6 * gbx0 - ((6 * gbx0 - 3 * aa) & ~15);
 #pragma unroll
             for (int i = 0; i < NIT; ++i) {
-                const int u = tid + i * P2_NT;
+                // blocks are dealt to the threads rotated by P1_ROT: the last, partial round (100 of 612 blocks) then falls to warps 3-6
+                // and the two bookkeeping warps (thread 0, thread CLIP_B) reach the barrier early enough to absorb their waits
+                const int u = ((tid + P1_ROT) & (P2_NT - 1)) + i * P2_NT;
                 if (u < P2_BW * ((th >> 1) + 2)) {
                     const int bj = u / P2_BW, bi = u - bj * P2_BW;
                     uint32_t r0, r1, r2;
@@ -512,7 +619,7 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
                         r0 = p[-3 * as]; r1 = p[1]; r2 = p[3 * as + 2];
                     } else {
                         const int sx = 2 * imin(imax(gbx0 + bi, 0), d.hw - 1), sy = 2 * imin(imax(gby0 + bj, 0), d.hh - 1);
-                        const uint8_t* row = in + (size_t)sy * d.W * 3;
+                        const uint8_t* row = in_f + (size_t)sy * d.W * 3;
                         r0 = row[wrap(sx - a0, d.W) * 3 + 0]; r1 = row[sx * 3 + 1]; r2 = row[wrap(sx + a0, d.W) * 3 + 2];
                     }
                     const F3 v1 = colour(d, mk3(s_unit[r0], s_unit[r1], s_unit[r2]), s_pow);
@@ -524,10 +631,24 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
                 }
             }
         }
+        if (CLIP && tid == 0) {      // (in the slack the rotation above leaves warp 0; the store was issued a phase ago)
+            if (owed) { bulk_wait_all(); clip_publish(ca.sync + 1 + s_prev[0], s_prev[1] + 1, ca.release); }
+            s_prev[0] = tby * tiles_x + tbx; s_prev[1] = fr;
+        }
         __syncthreads();
+        if (CLIP && tid == CLIP_B) {
+            s_item[buf ^ 1] = next; split(next < nitems ? next : 0, nfr, nby, nbx);
+            if (next < nitems) {      // next item's input into the other buffer (last read in the previous iteration), and a look at its flag
+                mbar_expect_tx(&bar_in[buf ^ 1], P2_RAW_BYTES);
+                tma_load_2d_hint(s_raw + (buf ^ 1) * P2_RAW_BYTES, &map_in, (6 * ((nbx * P2_TW >> 1) - 1) - 3 * aa) & ~15,
+                                 (frame + nfr) * d.hh + (nby * th >> 1) - 1, &bar_in[buf ^ 1], L2_EVICT_FIRST);
+                if (nfr > 0) hint = clip_peek(ca.sync + 1 + nby * tiles_x + nbx);
+            }
+        }
         griddep_wait();         // previous kernel of the stream complete: state / pre-warp image / noise may be touched from here on
         if (use_state) {
             if (it == 0 && tid == 0) {           // first tile: the state may only be fetched now
+                if (CLIP && fr > 0) clip_wait(ca.sync + 1 + tby * tiles_x + tbx, fr);
                 mbar_expect_tx(&bar_st, st_bytes);
                 tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st);
             }
@@ -564,10 +685,11 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
                     for (int k = 0; k < 4; ++k) blr[k][ch] = ffma(fsub(h[1][k], h[0][k]), w, h[0][k]);
                 }
             };
-            ps2_patch_tail<BLOOM, FAST>(d, f, mt, s_fwd, s_inv, s_sel, state, out, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
+            ps2_patch_tail<BLOOM, FAST>(d, f, mt, s_fwd, s_inv, s_sel, state, out_f, q_out, has_prev, ox0, oy0, ox1, oy1, xb, y0, t1,
                                         [&](int, int k) { return mk3(blr[k][0], blr[k][1], blr[k][2]); },
                                         tile_out ? s_state + (y0 - oy0) * (P2_TW * 3) + 12 * tx : nullptr, tile_out, row_begin);
         }
+        if (CLIP && tid == CLIP_B) s_hint = hint;      // (the look's latency has passed behind phase 4)
         if (tile_out) fence_proxy_async();      // the new state in shared memory -> visible to the TMA engine
         __syncthreads();        // everyone is done with this tile's tables, block values and state tile
         if (tile_out && tid == 0) {            // the tile's new state leaves with one coalesced TMA store (rows outside the frame are clipped)
@@ -576,13 +698,74 @@ __global__ void __launch_bounds__(P2_NT, THR ? 3 : 4) k_fused_ps2_pipe(Dev d_arg
             tma_store_2d_hint(&map_st, s_state, ox0 * 3, oy0, q_out ? L2_EVICT_LAST : L2_EVICT_NORMAL);
             bulk_commit();
         }
-        tbx = nbx; tby = nby;
+        if (CLIP) tile = s_item[buf ^ 1];      // written by thread 0 before this iteration's barriers
+        else { tile += (int)gridDim.x; tbx = nbx; tby = nby; }
     }
-    if (tile_out && tid == 0) bulk_wait_all();      // the last tile's store has completed before the CTA exits
+    if (tile_out && tid == 0) {
+        bulk_wait_all();      // the last tile's store has completed before the CTA exits
+        if (CLIP && it > 0) clip_publish(ca.sync + 1 + s_prev[0], s_prev[1] + 1, ca.release);
+    }
 }
 
 
 #if defined(CRT_TU_PS2)      // launcher: compiled only in the translation unit that owns these kernels (build.py)
+using Ps2PipeKernel = void (*)(Dev, FrameDev, const uint8_t*, uint8_t*, float*, float*, int, const CUtensorMap, const CUtensorMap, int, int, const ClipArgs);
+template <bool CLIP>
+inline Ps2PipeKernel pick_ps2_pipe(const Dev& d, const FrameDev& f, bool fast, bool thr) {
+    Ps2PipeKernel kern = !thr ? (d.bloom_mode == 1 ? (fast ? k_fused_ps2_pipe<true, true, false, 0, CLIP> : k_fused_ps2_pipe<true, false, false, 0, CLIP>)
+                                                   : (fast ? k_fused_ps2_pipe<false, true, false, 0, CLIP> : k_fused_ps2_pipe<false, false, false, 0, CLIP>))
+                              : (fast ? k_fused_ps2_pipe<true, true, true, 0, CLIP> : k_fused_ps2_pipe<true, false, true, 0, CLIP>);
+    static const bool use_spec = env_int("CRT_SPEC", 1) != 0;
+    if (use_spec && !thr && d.bloom_mode == 1 && fast) {            // feature sets with a compile-time specialisation
+        if (spec_matches(SPEC_DEFAULT, d, f.flicker_on != 0, fast)) kern = k_fused_ps2_pipe<true, true, false, SPEC_DEFAULT, CLIP>;
+        else if (spec_matches(SPEC_SLANTED, d, f.flicker_on != 0, fast)) kern = k_fused_ps2_pipe<true, true, false, SPEC_SLANTED, CLIP>;
+    }
+    return kern;
+}
+
+// Clip mode (see ClipArgs): frames [maps->frame, maps->frame + ca.nf) of the clip in one launch; `in` / `out` point at the first of
+// them, every frame blends against the state its predecessor left (has_prev = 1).  ca.sync must be zeroed on the stream first.
+inline int run_fused_ps2_clip(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, cudaStream_t st,
+                              int* launches, const Ps2Maps* maps, ClipArgs& ca) {
+    const bool fast = d.triad_mode == 2 && d.triad_comp && d.vig_mode <= 1;
+    const bool thr = d.bloom_mode == 1 && d.thr_on;
+    auto kern = pick_ps2_pipe<true>(d, f, fast, thr);
+    if (env.raise((const void*)kern, P2_PIPE_SMEM) &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM) != cudaSuccess) return 2;
+    const int tiles_x = (d.W + P2_TW - 1) / P2_TW;
+    const long long nitems = (long long)tiles_x * ((d.H + maps->th - 1) / maps->th) * ca.nf;
+    if (ca.nf < 1 || ca.nf > CLIP_MAX_FRAMES) return 4;
+    // CTAs the device holds: every CTA of the grid must be able to become resident next to its peers (items wait for items)
+    int resident = 0;
+    {
+        const void* key = (const void*)((const char*)kern + 1);      // (the entry point itself keys the shared-memory opt-in)
+        auto it = env.memo.find(key);
+        if (it == env.memo.end()) {
+            int per_sm = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P2_NT, (size_t)P2_PIPE_SMEM);
+            it = env.memo.emplace(key, env.sms * (per_sm > 0 ? per_sm : 1)).first;
+        }
+        resident = it->second;
+    }
+    ca.frame_bytes = (unsigned long long)d.W * d.H * 3;
+    // cooperative launch (every CTA resident -> items by a fixed stride, no counter); if the device refuses it, the atomic counter
+    const bool use_coop = env_int("CRT_CLIP_COOP", 1) != 0;
+    const dim3 grid((unsigned)(nitems < resident ? nitems : resident));
+    cudaError_t e = cudaErrorNotSupported;
+    if (use_coop) {
+        ca.static_items = 1;
+        e = launch_coop(kern, grid, dim3(P2_NT), (size_t)P2_PIPE_SMEM, st, d, f, in, out, state, (float*)nullptr, 1, maps->in, maps->st, maps->frame, maps->th, ca);
+        if (e != cudaSuccess) cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        ca.static_items = 0;
+        e = launch_pdl(kern, grid, dim3(P2_NT), (size_t)P2_PIPE_SMEM, st, false, d, f, in, out, state, (float*)nullptr, 1, maps->in, maps->st, maps->frame,
+                       maps->th, ca);
+    }
+    ++*launches;
+    return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
+}
+
 inline int run_fused_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
                          cudaStream_t st, int* launches, bool pdl = false, const Ps2Maps* maps = nullptr) {
     dim3 grid((d.W + P2_TW - 1) / P2_TW, (d.H + P2_TH - 1) / P2_TH);
@@ -593,21 +776,14 @@ inline int run_fused_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const 
     static const int pipe_min_tiles = env_int("CRT_PIPE_MIN_TILES", 256);      // measured: wins at 720p (460 tiles, +1.5 %), 1080p (+15 %) and 4K, neutral at VGA (150)
     if (maps && (q_out || has_prev) && ntiles >= pipe_min_tiles) {
         const bool thr = d.bloom_mode == 1 && d.thr_on;
-        auto kern = !thr ? (d.bloom_mode == 1 ? (fast ? k_fused_ps2_pipe<true, true, false> : k_fused_ps2_pipe<true, false, false>)
-                                              : (fast ? k_fused_ps2_pipe<false, true, false> : k_fused_ps2_pipe<false, false, false>))
-                         : (fast ? k_fused_ps2_pipe<true, true, true> : k_fused_ps2_pipe<true, false, true>);
-        static const bool use_spec = env_int("CRT_SPEC", 1) != 0;
-        if (use_spec && !thr && d.bloom_mode == 1 && fast) {            // feature sets with a compile-time specialisation
-            if (spec_matches(SPEC_DEFAULT, d, f.flicker_on != 0, fast)) kern = k_fused_ps2_pipe<true, true, false, SPEC_DEFAULT>;
-            else if (spec_matches(SPEC_SLANTED, d, f.flicker_on != 0, fast)) kern = k_fused_ps2_pipe<true, true, false, SPEC_SLANTED>;
-        }
+        auto kern = pick_ps2_pipe<false>(d, f, fast, thr);
         // the opt-in shared-memory size is a per-device, per-kernel attribute: set once per context and kernel
         if (env.raise((const void*)kern, P2_PIPE_SMEM) &&
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_PIPE_SMEM) != cudaSuccess) return 2;
         const int resident_pipe = env.sms * (thr ? 3 : 4);
         const int ntiles_th = (int)grid.x * ((d.H + maps->th - 1) / maps->th);      // tiles of maps->th rows
         const cudaError_t e = launch_pdl(kern, dim3(ntiles_th < resident_pipe ? ntiles_th : resident_pipe), dim3(P2_NT), (size_t)P2_PIPE_SMEM, st, pdl,
-                                         d, f, in, out, state, q_out, has_prev, maps->in, maps->st, maps->frame, maps->th);
+                                         d, f, in, out, state, q_out, has_prev, maps->in, maps->st, maps->frame, maps->th, ClipArgs{});
         ++*launches;
         return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 2;
     }

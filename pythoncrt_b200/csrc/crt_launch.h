@@ -39,6 +39,14 @@ struct Scratch;
 
 int launch_fused_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, float* q_out, int has_prev,
                      cudaStream_t st, int* launches, bool pdl, const Ps2Maps* maps);
+// clip mode: frames [maps->frame, maps->frame + nf) in one launch (nf <= clip_max_frames()); in / out = the first of them;
+// fv = their scalars (host); sync = [1 + tiles] ints, zeroed on st before the launch
+int clip_max_frames();
+int launch_fused_ps2_clip(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, cudaStream_t st,
+                          int* launches, const Ps2Maps* maps, int nf, const FrameVar* fv, int* sync);
+bool fused_gauss_ps2_clip_supported(const Dev& d, int K);
+int launch_fused_gauss_ps2_clip(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, cudaStream_t st,
+                                int* launches, const Ps2Maps* maps, const CUtensorMap* gmap_in, int nf, const FrameVar* fv, int* sync);
 int launch_warp_ps2(LaunchEnv& env, const WarpPs2Plan& pl, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state,
                     int has_prev, cudaStream_t st, int* launches, bool pdl);
 int launch_warp_src(LaunchEnv& env, const Dev& d, const FrameDev& f, const uint8_t* in, uint8_t* out, float* state, int has_prev, cudaStream_t st,

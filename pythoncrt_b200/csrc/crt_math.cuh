@@ -169,6 +169,9 @@ struct FrameDev {
     int gy0, gseg, gnseg;
 };
 
+// the per-frame scalars of FrameDev for a run of frames processed by ONE launch (clip mode, crt_fused_ps2.cuh)
+struct FrameVar { float phase32, flicker; double phase; };
+
 // ---- stage 0-4: graded input ----------------------------------------------------
 // u8 -> float32 by true division (crt_filter.py:569)
 CRT_HD float unit(uint8_t v) { return fdiv((float)v, 255.0f); }

@@ -449,3 +449,104 @@ def test_opt_in_single_pass_warp_kernels_at_4k(env, monkeypatch):
     assert res[1][2] < res[0][2]                                     # one kernel per frame instead of two
     assert int((res[0][0].to(torch.int16) - res[1][0].to(torch.int16)).abs().max()) <= 1
     assert float((res[0][1] - res[1][1]).abs().max()) <= 1.0 / 255 + 1e-6
+
+
+# ------------------------------------------------------------------------------------------- clip mode --
+def _clip_params(kind):
+    import host_emu
+    base = host_emu.oracle_to_product_params(CASES_BY_NAME["cfg1_cli_default"].params).but(noise_strength=0.0, glitch_amp_px=0)
+    if kind == "default":
+        return base
+    if kind == "slanted_flicker":      # per-frame scalars: scanline phase and flicker gain differ from frame to frame
+        return base.but(scanline_angle=3.0, scanline_thickness=1.2, flicker_strength=0.08, flicker_hz=50.0)
+    if kind == "gauss_grade":          # BASELINE configs[1]: gaussian bloom (K = 9) + colour grade
+        return host_emu.oracle_to_product_params(CASES_BY_NAME["cfg2_gauss_grade"].params).but(noise_strength=0.0, glitch_amp_px=0)
+    if kind == "gauss_wide":           # K = 7, per-frame scalars
+        return base.but(fast_bloom=False, bloom_sigma=1.0, scanline_angle=2.0, flicker_strength=0.05, flicker_hz=50.0)
+    if kind == "threshold":
+        return base.but(bloom_threshold=0.6)
+    if kind == "no_bloom":
+        return base.but(bloom_strength=0.0)
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize("kind,hw,n", [("default", (1080, 1920), 40), ("default", (720, 1280), 70), ("default", (2160, 3840), 6),
+                                       ("slanted_flicker", (1080, 1920), 24), ("threshold", (1080, 1920), 12), ("no_bloom", (720, 1280), 12),
+                                       ("default", (480, 640), 130), ("gauss_grade", (1080, 1920), 40), ("gauss_grade", (2160, 3840), 5),
+                                       ("gauss_wide", (1080, 1920), 10)])
+def test_clip_mode_is_the_serial_run_bit_for_bit(kind, hw, n, monkeypatch):
+    """Clip mode (csrc/crt_fused_ps2.cuh ClipArgs): a run of frames in ONE launch, chained tile by tile through the persistence
+    state (crt_filter.py:1092).  Same kernel arithmetic in the same order per pixel -> identical bytes and identical state to
+    one launch per frame, for runs longer than a launch holds (64), frames smaller than the resident grid, per-frame scalars,
+    and a second call continuing from the first call's state."""
+    import torch
+    from pythoncrt_b200.engine import CrtEngine
+    h, w = hw
+    p = _clip_params(kind)
+    g = torch.Generator(device="cuda").manual_seed(1234 + n)
+    fr = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+    phases = [0.37 * j for j in range(n)]
+    times = [j / 30.0 for j in range(n)]
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CRT_CLIP", mode)
+        eng = CrtEngine(w, h).configure(p)
+        eng.set_shards(1)
+        cut = n // 3
+        out = torch.empty_like(fr)
+        state = eng.new_state()
+        eng.process(fr[:cut], out[:cut], state=state, state_valid=False, phases=phases[:cut], times=times[:cut])
+        first = int(eng.last_info.reserved[2])
+        eng.process(fr[cut:], out[cut:], state=state, state_valid=True, phases=phases[cut:], times=times[cut:], first_index=cut)
+        res[mode] = (out, state.clone(), first, int(eng.last_info.reserved[2]), int(eng.last_info.kernels_launched))
+        eng.close()
+    assert res["0"][2] == 0 and res["0"][3] == 0
+    if h * w >= 1920 * 1080:            # (smaller frames: fewer tiles than resident CTAs -> one launch per frame, see clip_wanted)
+        assert res["1"][3] == n - n // 3 - ((n - n // 3) % 64 == 1), res["1"][2:]          # the second call went through clip-mode launches
+        assert res["1"][4] <= (n - n // 3 + 63) // 64 + 1
+    else:
+        monkeypatch.setenv("CRT_CLIP_MIN_TILES", "1")         # force clip mode on the small frame too
+        monkeypatch.setenv("CRT_CLIP", "1")
+        eng = CrtEngine(w, h).configure(p)
+        eng.set_shards(1)
+        out2, state2 = eng.process(fr, phases=phases, times=times)
+        assert int(eng.last_info.reserved[2]) == n - 1 - ((n - 1) % 64 == 1)      # runs of <= 64 frames; a single left-over frame goes alone
+        eng.close()
+        assert torch.equal(out2, res["0"][0]) and torch.equal(state2, res["0"][1])
+    assert torch.equal(res["0"][0], res["1"][0])
+    assert torch.equal(res["0"][1], res["1"][1])
+
+
+@pytest.mark.parametrize("env", [{}, {"CRT_CLIP_RELEASE": "1"}, {"CRT_CLIP_RELEASE": "2"}, {"CRT_CLIP_RELEASE": "23"}, {"CRT_CLIP_COOP": "0"},
+                                 {"CRT_CLIP_COOP_GAUSS": "1"}])
+@pytest.mark.parametrize("kind", ["default", "gauss_grade"])
+def test_clip_mode_variants_are_bit_exact_too(kind, env, monkeypatch):
+    """Every publication mode that carries a gpu-scope membar (csrc/crt_fused_ps2.cuh clip_publish; the mode without one is
+    measurably racy and not offered), the atomic item counter where the default is a cooperative launch with a fixed stride, and
+    the reverse: same bytes as one launch per frame, twice in a row (a race would show as a difference between runs)."""
+    import torch
+    from pythoncrt_b200.engine import CrtEngine
+    p = _clip_params(kind)
+    g = torch.Generator(device="cuda").manual_seed(99)
+    fr = torch.randint(0, 256, (30, 1080, 1920, 3), dtype=torch.uint8, device="cuda", generator=g)
+    res = []
+    for clip in ("0", "1", "1"):
+        monkeypatch.setenv("CRT_CLIP", clip)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = CrtEngine(1920, 1080).configure(p)
+        eng.set_shards(1)
+        out, state = eng.process(fr, fps=30.0)
+        res.append((out, state, int(eng.last_info.reserved[2])))
+        eng.close()
+    assert res[0][2] == 0 and res[1][2] == 29 and res[2][2] == 29
+    for k in (1, 2):
+        assert torch.equal(res[0][0], res[k][0]) and torch.equal(res[0][1], res[k][1])
+
+
+def test_clip_mode_matches_the_oracle():
+    """... and against the oracle of the chain, with the reference's own state hand-off."""
+    case = CASES_BY_NAME["cfg1_cli_default"]
+    outs, state, fused = run_case_gpu(case, "export")
+    want, want_state = harness.run_oracle(case, "export", backend="cv2")
+    assert max(int(np.abs(o.astype(np.int16) - w.astype(np.int16)).max()) for o, w in zip(outs, want)) <= 1
