@@ -161,6 +161,14 @@ int crt_set_policy(crt_ctx* ctx, int policy);
  * differs from the strictly serial run by at most persistence^warm-up <= 1/8 LSB before quantisation (identical when
  * persistence == 0).  1 = off (default: every call is strictly serial), 0 = automatic (up to 4 shards, each at least 48 frames
  * and 8 warm-ups long; none for frames of 24 Mpixel and more, which fill the GPU on their own), k = at most k.  Calls shorter than that, and crt_process_static / crt_process_host, stay serial.
+ *
+ * Clip mode.  A strictly serial call of two or more frames whose parameters select a single-pass block kernel (pixel_size 2,
+ * fast / no / gaussian bloom up to 9 taps, persistence on, no noise plane or glitch table per frame, a frame of at least one
+ * tile per resident CTA: 1080p and up) is launched as runs of up to 64 frames per kernel launch, the frames of a tile chained
+ * on the device through per-tile flags: the same bytes and the same state as one launch per frame (the recurrence at :1092
+ * exactly), without the per-frame launch and tail.  In automatic mode (0) the library takes clip mode instead of shards where it
+ * measures faster.  crt_launch_info.reserved[2] reports the frames that went that way.  The caller sees no difference
+ * other than that: the call is asynchronous on `stream` as before.
  */
 int crt_set_shards(crt_ctx* ctx, int shards);
 

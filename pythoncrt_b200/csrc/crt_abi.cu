@@ -782,11 +782,15 @@ int crt_process(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_stat
                 void* stream, crt_launch_info* info) {
     if (!ctx) return CRT_ERR_INVALID;
     int K = (ctx->have_params && d_in && d_out && frames) ? choose_shards(ctx, n_frames) : 1;
-    // Clip mode keeps one stream full on its own and is the serial recurrence exactly: for the fast-bloom / no-bloom kernel shards
-    // only on explicit request.  The gaussian kernel's clip mode is exact too but measures below four shards of per-frame launches
-    // (BASELINE configs[1], run 56: 53.0 k against 56-58 k frames/s) -> automatic mode shards it; crt_set_shards(1) gives clip mode.
-    if (K > 1 && ctx->shards_wanted == 0 && env_int("CRT_SHARDS", -1) < 0 && clip_wanted(ctx, d_out, d_state, nullptr, n_frames) &&
-        (!ctx->plan.gauss_k || env_int("CRT_CLIP_GAUSS_AUTO", 0))) K = 1;
+    // Automatic mode: clip mode (one stream, the serial recurrence exactly) where it measures faster than concurrent shards of
+    // per-frame launches — the fast-bloom / no-bloom kernel below four rounds of tiles per frame (1080p: 80-84 k against 79 k frames/s);
+    // at 4K (6.9 rounds) the shards keep a 3 % edge (21.6 k against 20.9 k), and so they do for the gaussian kernel (BASELINE
+    // configs[1], run 56: 56-58 k against 53 k).  crt_set_shards(1) always gives clip mode where it applies.
+    if (K > 1 && ctx->shards_wanted == 0 && env_int("CRT_SHARDS", -1) < 0 && clip_wanted(ctx, d_out, d_state, nullptr, n_frames)) {
+        const int ntiles = ((ctx->W + P2_TW - 1) / P2_TW) * ((ctx->H + P2_TH - 1) / P2_TH);
+        const int resident = ctx->env.sms * ((ctx->dev.bloom_mode == 1 && ctx->dev.thr_on) ? 3 : 4);
+        if ((!ctx->plan.gauss_k && ntiles < 4 * resident) || env_int("CRT_CLIP_AUTO", 0)) K = 1;
+    }
     if (K > 1 && (d_state || !(ctx->p.persistence > 0.0)))
         return process_sharded(ctx, K, d_in, d_out, d_state, state_valid, frames, n_frames, (cudaStream_t)stream, info);
     if (info) { info->reserved[0] = 1; info->reserved[1] = 0; }
