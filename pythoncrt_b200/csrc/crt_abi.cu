@@ -528,8 +528,9 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
                                                                  &ctx->maps, c.gauss_in, nf, fv.data(), ctx->d_clip_sync)
                                    : launch_fused_ps2_clip(ctx->env, d, f0, d_in + (size_t)i * fb, d_out + (size_t)i * fb, d_state, st, &launches, &ctx->maps,
                                                            nf, fv.data(), ctx->d_clip_sync);
-            prof_mark_clip(ctx, st, true, nf);
-            if (rc) return fail(ctx, rc == 4 ? CRT_ERR_UNSUPPORTED : CRT_ERR_CUDA, std::string("clip-mode launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+            prof_mark_clip(ctx, st, true, rc ? 0 : nf);
+            if (rc == 4) break;          // this parameter set has no clip-mode kernel after all: the frames go one launch each (below)
+            if (rc) return fail(ctx, CRT_ERR_CUDA, std::string("clip-mode launch failed: ") + cudaGetErrorString(cudaGetLastError()));
             i += nf; clip_frames += nf;
         }
     }

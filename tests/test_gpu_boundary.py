@@ -550,3 +550,38 @@ def test_clip_mode_matches_the_oracle():
     outs, state, fused = run_case_gpu(case, "export")
     want, want_state = harness.run_oracle(case, "export", backend="cv2")
     assert max(int(np.abs(o.astype(np.int16) - w.astype(np.int16)).max()) for o, w in zip(outs, want)) <= 1
+
+
+@pytest.mark.parametrize("kind", ["default", "gauss_grade", "threshold"])
+@pytest.mark.parametrize("hw", [(1080, 1920), (1440, 2560), (900, 1600), (1088, 2048)])
+def test_clip_mode_is_deterministic_across_sizes(kind, hw, monkeypatch):
+    """Race hunt in the suite: the flag protocol's margins depend on tiles per resident CTA (1080p: 1.7 rounds for the fast-bloom
+    kernel, 2.3 for the gaussian one).  Three clip-mode runs of 48 frames against one launch per frame, with host <-> device
+    copies running on another stream as in crt_process_host: every byte equal every time."""
+    import torch
+    from pythoncrt_b200.engine import CrtEngine
+    h, w = hw
+    p = _clip_params(kind)
+    g = torch.Generator(device="cuda").manual_seed(h + w)
+    fr = torch.randint(0, 256, (48, h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+    monkeypatch.setenv("CRT_CLIP", "0")
+    eng = CrtEngine(w, h).configure(p)
+    eng.set_shards(1)
+    ref, ref_state = eng.process(fr, fps=30.0)
+    eng.close()
+    monkeypatch.setenv("CRT_CLIP", "1")
+    side = torch.cuda.Stream()
+    hbuf = torch.empty((64 << 20,), dtype=torch.uint8).pin_memory()
+    dbuf = torch.empty((64 << 20,), dtype=torch.uint8, device="cuda")
+    for run in range(3):
+        eng = CrtEngine(w, h).configure(p)
+        eng.set_shards(1)
+        with torch.cuda.stream(side):
+            for _ in range(4):
+                dbuf.copy_(hbuf, non_blocking=True)
+                hbuf.copy_(dbuf, non_blocking=True)
+        out, state = eng.process(fr, fps=30.0)
+        torch.cuda.synchronize()
+        assert int(eng.last_info.reserved[2]) == 47, (kind, hw)
+        eng.close()
+        assert torch.equal(out, ref) and torch.equal(state, ref_state), (kind, hw, run, int((out != ref).sum()))
