@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
     for (int i = 0; i <= R; ++i) { taps[R + i] = d.taps[R + i]; taps[R - i] = taps[R + i]; }
     MaskTabs mt{s_rows, s_cols, s_rows + P2_TH, s_cols + P2_TW};
     __shared__ int s_item[2], s_prev[2], s_hint;    // clip mode: the item of the next iteration; tile and frame of the item being stored;
-    if (CLIP && tid == 0) { s_hint = 0; s_item[0] = ca.static_items ? (int)blockIdx.x : atomicAdd(ca.sync, 1); }      // the item's flag as seen earlier
+    const int rank = (CLIP && ca.per_sm > 0) ? ((int)blockIdx.x % ca.per_sm) * ((int)gridDim.x / ca.per_sm) + (int)blockIdx.x / ca.per_sm : (int)blockIdx.x;
+    if (CLIP && tid == 0) { s_hint = 0; s_item[0] = ca.static_items ? rank : atomicAdd(ca.sync, 1); }      // the item's flag as seen earlier
     __syncthreads();
     const int tiles_x = (d.W + P2_TW - 1) / P2_TW, ntiles = tiles_x * ((d.H + th - 1) / th);
     const int nitems = CLIP ? ntiles * ca.nf : ntiles;
@@ -172,8 +173,19 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
         if (nbx >= tiles_x) { nbx -= tiles_x; ++nby; }
         // clip mode's bookkeeping, split between thread 0 (state traffic) and thread CLIP_B (next item): see k_fused_ps2_pipe
         bool owed = false;                   // thread 0: the previous item's completion is still to be published
-        if (CLIP && tid == CLIP_B) next = ca.static_items ? tile + (int)gridDim.x : atomicAdd(ca.sync, 1);
-        if (CLIP && tid == 0) {
+        const bool own = CLIP && ca.static_items == 2, own_one = own && rank + (int)gridDim.x >= ntiles;      // owned tiles
+        if (CLIP && tid == CLIP_B) {
+            if (own) {
+                const int nt = tby * tiles_x + tbx + (int)gridDim.x;
+                next = nt < ntiles ? fr * ntiles + nt : (fr + 1 < ca.nf ? (fr + 1) * ntiles + rank : nitems);
+            } else next = ca.static_items ? tile + (int)gridDim.x : atomicAdd(ca.sync, 1);
+        }
+        if (own && tid == 0) {
+            if (iter > 0) bulk_wait_read(); else griddep_wait();
+            if (own_one && fr > 0) { bulk_wait_all(); clip_settle(ca.release); }
+            mbar_expect_tx(&bar_st, st_bytes); tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st);
+        }
+        if (CLIP && !own && tid == 0) {
             if (iter > 0) bulk_wait_read(); else griddep_wait();
             if (iter > 0) owed = true;
             if (fr > 0 && (iter == 0 || s_hint < fr || (ca.release & 16))) {
@@ -268,13 +280,16 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
             }
         }
         if (CLIP && tid == 0) {      // (in the slack the rotation above leaves warp 0; the store was issued a phase ago)
-            if (owed) { bulk_wait_all(); clip_publish(ca.sync + 1 + s_prev[0], s_prev[1] + 1, ca.release); }
-            s_prev[0] = tby * tiles_x + tbx; s_prev[1] = fr;
+            if (own) { if (iter > 0 && !own_one) { bulk_wait_all(); clip_settle(ca.release); } }
+            else {
+                if (owed) { bulk_wait_all(); clip_publish(ca.sync + 1 + s_prev[0], s_prev[1] + 1, ca.release); }
+                s_prev[0] = tby * tiles_x + tbx; s_prev[1] = fr;
+            }
         }
         __syncthreads();
         if (CLIP && tid == CLIP_B) {
             s_item[(iter & 1) ^ 1] = next; split(next < nitems ? next : 0, nfr, nby, nbx);
-            if (next < nitems && nfr > 0) hint = clip_peek(ca.sync + 1 + nby * tiles_x + nbx);
+            if (next < nitems && nfr > 0 && !own) hint = clip_peek(ca.sync + 1 + nby * tiles_x + nbx);
         }
         if (TIN && tid == (CLIP ? CLIP_B : 0) && next < nitems) {      // the buffer has been read: fetch the next tile's input bytes
             mbar_expect_tx(&bar_in, RAW_BYTES);
@@ -349,7 +364,7 @@ __global__ void __launch_bounds__(P2_NT, MINB) k_fused_gauss_ps2(Dev d_arg, Fram
     }
     if (tile_out && tid == 0) {
         bulk_wait_all();      // the last tile's store has completed before the CTA exits
-        if (CLIP && iter > 0) clip_publish(ca.sync + 1 + s_prev[0], s_prev[1] + 1, ca.release);
+        if (CLIP && iter > 0 && ca.static_items != 2) clip_publish(ca.sync + 1 + s_prev[0], s_prev[1] + 1, ca.release);
     }
 }
 
@@ -420,17 +435,24 @@ inline int launch_fused_gauss_ps2_clip_t(LaunchEnv& env, const Dev& d, const Fra
     const long long nitems = (long long)((d.W + P2_TW - 1) / P2_TW) * ((d.H + maps->th - 1) / maps->th) * ca.nf;
     ca.frame_bytes = (unsigned long long)d.W * d.H * 3;
     const dim3 grid((unsigned)(nitems < it->second ? nitems : it->second));
-    // items from the atomic counter: with a fixed stride (cooperative launch, as k_fused_ps2_pipe's clip mode) this kernel is 12 %
-    // slower (measured, run 50: 46.5 k against 52.8 k frames/s on BASELINE configs[1]) — its tiles differ in cost and a lagging CTA
-    // then holds up the tiles that wait for its flags
-    const bool use_coop = env_int("CRT_CLIP_COOP_GAUSS", 0) != 0;
+    // items (see run_fused_ps2_clip): the atomic counter by default; it beats the fixed stride of a cooperative
+    // launch by 12 % for this kernel (run 50: 52.8 k against 46.5 k frames/s on BASELINE configs[1] — its tiles differ in cost and a
+    // lagging CTA then holds up the tiles that wait for its flags)
+    const int items = env_int("CRT_CLIP_ITEMS", 0);
     cudaError_t e = cudaErrorNotSupported;
-    if (use_coop) {
+    if (items == 2 || items == 3) {      // 3: ranks permuted for a placement that puts consecutive CTAs on one SM
+        ca.static_items = 2;
+        ca.per_sm = 0;
+        const long long ntl = nitems / ca.nf;
+        if (items == 3 && ntl >= it->second && it->second % env.sms == 0) ca.per_sm = it->second / env.sms;
+        e = launch_pdl(kern, dim3((unsigned)(ntl < it->second ? ntl : it->second)), dim3(P2_NT), smem, st, false, d, f, in, out, state, (float*)nullptr, 1,
+                       maps->st, *gmap_in, maps->frame, maps->th, ca);
+    } else if (items == 1 && env_int("CRT_CLIP_COOP_GAUSS", 0)) {
         ca.static_items = 1;
         e = launch_coop(kern, grid, dim3(P2_NT), smem, st, d, f, in, out, state, (float*)nullptr, 1, maps->st, *gmap_in, maps->frame, maps->th, ca);
         if (e != cudaSuccess) cudaGetLastError();
     }
-    if (e != cudaSuccess) {
+    if (e != cudaSuccess && ca.static_items != 2) {
         ca.static_items = 0;
         e = launch_pdl(kern, grid, dim3(P2_NT), smem, st, false, d, f, in, out, state, (float*)nullptr, 1, maps->st, *gmap_in, maps->frame, maps->th, ca);
     }

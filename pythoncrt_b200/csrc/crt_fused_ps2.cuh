@@ -426,7 +426,9 @@ struct ClipArgs {
     int nf = 1;                          // frames in this launch (1: the per-frame launch, everything below unused)
     int* sync = nullptr;                 // [0]: item counter, [1 + t]: frames of tile t completed — zeroed before the launch
     unsigned long long frame_bytes = 0;  // W * H * 3
-    int static_items = 0;                // 1: item = blockIdx.x + k * gridDim.x (the launch is cooperative: every CTA is resident); 0: atomic counter
+    int static_items = 0;                // 2: owned tiles — CTA i keeps tiles i, i + G, ... through all frames of the run (no flags at all);
+                                         // 1: item = blockIdx.x + k * gridDim.x (the launch is cooperative: every CTA is resident); 0: atomic counter
+    int per_sm = 0;                      // owned tiles: > 0 = CTAs per SM when consecutive CTAs share an SM -> rank = (i % per_sm) * SMs + i / per_sm
     int release = 1;                     // publication / acquisition mode bits (clip_publish; CRT_CLIP_RELEASE)
     FrameVar fv[CLIP_MAX_FRAMES];
 };
@@ -457,6 +459,12 @@ __device__ __forceinline__ void clip_acquire(int mode) {
     else asm volatile("fence.acquire.gpu;" ::: "memory");            // SASS: CCTL.IVALL
     if (mode & 2) asm volatile("fence.proxy.async;" ::: "memory");
     else asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+// owned-tiles mode: this thread's completed TMA stores (cp.async.bulk.wait_group 0) become visible to its later TMA loads —
+// the gpu-scope membar is what the race above showed to be necessary after the bulk group's completion
+__device__ __forceinline__ void clip_settle(int mode) {
+    if (mode & 8) asm volatile("fence.proxy.async.global;" ::: "memory");      // (light form: for the race hunt only)
+    else asm volatile("fence.proxy.async;" ::: "memory");
 }
 __device__ __forceinline__ void clip_wait(const int* flag, int value) {
     int v;
@@ -507,6 +515,8 @@ __global__ void __launch_bounds__(P2_NT, (THR || (CLIP && SPEC == 0)) ? 3 : 4) k
     // clip mode: items = (frame, tile) pairs, frame-major, from the counter; s_item[] hands the item of the next iteration to the CTA
     __shared__ int s_item[2];
     const int nitems = CLIP ? ntiles * ca.nf : ntiles;
+    // owned tiles: which tiles are this CTA's — spread so that the CTAs of one SM own n, n, n, n - 1 tiles whichever way the CTAs were placed
+    const int rank = (CLIP && ca.per_sm > 0) ? ((int)blockIdx.x % ca.per_sm) * ((int)gridDim.x / ca.per_sm) + (int)blockIdx.x / ca.per_sm : (int)blockIdx.x;
     int fr = 0;                                     // frame of the current item within the run
     const unsigned magic_tx = make_magic(tiles_x);
     auto split = [&](int item, int& ifr, int& iby, int& ibx) {      // item -> frame, tile row, tile column (item < 2^31, tile < 2^16)
@@ -519,7 +529,7 @@ __global__ void __launch_bounds__(P2_NT, (THR || (CLIP && SPEC == 0)) ? 3 : 4) k
         mbar_init(&bar_in[0], 1); mbar_init(&bar_in[1], 1); mbar_init(&bar_st, 1);
         fence_mbar_init();
         int first = blockIdx.x;
-        if (CLIP) { first = ca.static_items ? (int)blockIdx.x : atomicAdd(ca.sync, 1); s_item[0] = first; split(first < nitems ? first : 0, fr, tby, tbx); }
+        if (CLIP) { first = ca.static_items ? rank : atomicAdd(ca.sync, 1); s_item[0] = first; split(first < nitems ? first : 0, fr, tby, tbx); }
         // first tile's input: independent of the previous kernel
         if (first < nitems) {
             mbar_expect_tx(&bar_in[0], P2_RAW_BYTES);
@@ -564,9 +574,24 @@ __global__ void __launch_bounds__(P2_NT, (THR || (CLIP && SPEC == 0)) ? 3 : 4) k
         // flag was already set at that look (the normal case: the tile's previous frame is a whole frame of items behind), awaits
         // the previous store's completion after phase 1, when it has long happened, and publishes it.  Blocking on another CTA's
         // flag comes only after our own publication — no CTA waits while it owes one: no deadlock.
+        // OWNED TILES (ca.static_items == 2, opt-in: measured slower, see run_fused_ps2_clip): CTA i keeps tiles i, i + G, ... through every frame of the run, so a tile's
+        // previous frame was stored by this very CTA — no flags, no counter, no waiting for anyone.  Thread 0 settles each store
+        // (completion + membar) in its slack before the phase-1 barrier of the NEXT item, which covers every later fetch of that
+        // tile when the CTA owns two tiles or more; a CTA with a single tile settles at the top (it is the one with time to spare).
         bool owed = false;                   // thread 0: the previous item's completion is still to be published
-        if (CLIP && tid == CLIP_B) next = ca.static_items ? tile + (int)gridDim.x : atomicAdd(ca.sync, 1);
-        if (CLIP && tid == 0 && it > 0) {
+        const bool own = CLIP && ca.static_items == 2, own_one = own && rank + (int)gridDim.x >= ntiles;
+        if (CLIP && tid == CLIP_B) {
+            if (own) {
+                const int nt = tby * tiles_x + tbx + (int)gridDim.x;
+                next = nt < ntiles ? fr * ntiles + nt : (fr + 1 < ca.nf ? (fr + 1) * ntiles + rank : nitems);
+            } else next = ca.static_items ? tile + (int)gridDim.x : atomicAdd(ca.sync, 1);
+        }
+        if (own && tid == 0 && it > 0) {
+            bulk_wait_read();                // the previous tile's TMA store has drained the buffer
+            if (own_one && fr > 0) { bulk_wait_all(); clip_settle(ca.release); }
+            mbar_expect_tx(&bar_st, st_bytes); tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st);
+        }
+        if (CLIP && !own && tid == 0 && it > 0) {
             bulk_wait_read();                // the previous tile's TMA store has drained the buffer
             owed = true;
             if (fr > 0 && (s_hint < fr || (ca.release & 16))) {
@@ -632,8 +657,11 @@ __global__ void __launch_bounds__(P2_NT, (THR || (CLIP && SPEC == 0)) ? 3 : 4) k
             }
         }
         if (CLIP && tid == 0) {      // (in the slack the rotation above leaves warp 0; the store was issued a phase ago)
-            if (owed) { bulk_wait_all(); clip_publish(ca.sync + 1 + s_prev[0], s_prev[1] + 1, ca.release); }
-            s_prev[0] = tby * tiles_x + tbx; s_prev[1] = fr;
+            if (own) { if (it > 0 && !own_one) { bulk_wait_all(); clip_settle(ca.release); } }
+            else {
+                if (owed) { bulk_wait_all(); clip_publish(ca.sync + 1 + s_prev[0], s_prev[1] + 1, ca.release); }
+                s_prev[0] = tby * tiles_x + tbx; s_prev[1] = fr;
+            }
         }
         __syncthreads();
         if (CLIP && tid == CLIP_B) {
@@ -642,13 +670,13 @@ __global__ void __launch_bounds__(P2_NT, (THR || (CLIP && SPEC == 0)) ? 3 : 4) k
                 mbar_expect_tx(&bar_in[buf ^ 1], P2_RAW_BYTES);
                 tma_load_2d_hint(s_raw + (buf ^ 1) * P2_RAW_BYTES, &map_in, (6 * ((nbx * P2_TW >> 1) - 1) - 3 * aa) & ~15,
                                  (frame + nfr) * d.hh + (nby * th >> 1) - 1, &bar_in[buf ^ 1], L2_EVICT_FIRST);
-                if (nfr > 0) hint = clip_peek(ca.sync + 1 + nby * tiles_x + nbx);
+                if (nfr > 0 && !own) hint = clip_peek(ca.sync + 1 + nby * tiles_x + nbx);
             }
         }
         griddep_wait();         // previous kernel of the stream complete: state / pre-warp image / noise may be touched from here on
         if (use_state) {
             if (it == 0 && tid == 0) {           // first tile: the state may only be fetched now
-                if (CLIP && fr > 0) clip_wait(ca.sync + 1 + tby * tiles_x + tbx, fr);
+                if (CLIP && fr > 0 && ca.static_items != 2) clip_wait(ca.sync + 1 + tby * tiles_x + tbx, fr);
                 mbar_expect_tx(&bar_st, st_bytes);
                 tma_load_2d(s_state, &map_st, ox0 * 3, oy0, &bar_st);
             }
@@ -703,7 +731,7 @@ __global__ void __launch_bounds__(P2_NT, (THR || (CLIP && SPEC == 0)) ? 3 : 4) k
     }
     if (tile_out && tid == 0) {
         bulk_wait_all();      // the last tile's store has completed before the CTA exits
-        if (CLIP && it > 0) clip_publish(ca.sync + 1 + s_prev[0], s_prev[1] + 1, ca.release);
+        if (CLIP && it > 0 && ca.static_items != 2) clip_publish(ca.sync + 1 + s_prev[0], s_prev[1] + 1, ca.release);
     }
 }
 
@@ -748,16 +776,27 @@ inline int run_fused_ps2_clip(LaunchEnv& env, const Dev& d, const FrameDev& f, c
         resident = it->second;
     }
     ca.frame_bytes = (unsigned long long)d.W * d.H * 3;
-    // cooperative launch (every CTA resident -> items by a fixed stride, no counter); if the device refuses it, the atomic counter
-    const bool use_coop = env_int("CRT_CLIP_COOP", 1) != 0;
+    // items: CRT_CLIP_ITEMS = 1 fixed stride with per-tile flags (default; cooperative launch: every CTA resident), 0 atomic counter
+    // with per-tile flags (also the fallback of 1), 2 owned tiles (no inter-CTA dependency at all, plain launch; 3: ranks permuted).
+    // Owned tiles measure SLOWER (run 58-59: default chain 4K 50.2 against 48.0 us per frame, 1080p 15.5 against 12.2, configs[1]
+    // 22.8 against 18.7): a CTA works its items off at a latency-bound pace whatever else runs on the SM, so the frame takes
+    // ceil(tiles / CTAs) tile latencies — 2 at 1080p where the flag protocols spread 1.72 per CTA evenly.
+    const int items = env_int("CRT_CLIP_ITEMS", 1);
     const dim3 grid((unsigned)(nitems < resident ? nitems : resident));
     cudaError_t e = cudaErrorNotSupported;
-    if (use_coop) {
+    if (items == 2 || items == 3) {      // 3: ranks permuted for a placement that puts consecutive CTAs on one SM
+        ca.static_items = 2;
+        ca.per_sm = 0;
+        const long long ntl = nitems / ca.nf;      // tiles of a frame: every CTA owns at least one
+        if (items == 3 && ntl >= resident && resident % env.sms == 0) ca.per_sm = resident / env.sms;
+        e = launch_pdl(kern, dim3((unsigned)(ntl < resident ? ntl : resident)), dim3(P2_NT), (size_t)P2_PIPE_SMEM, st, false, d, f, in, out, state,
+                       (float*)nullptr, 1, maps->in, maps->st, maps->frame, maps->th, ca);
+    } else if (items == 1 && env_int("CRT_CLIP_COOP", 1)) {
         ca.static_items = 1;
         e = launch_coop(kern, grid, dim3(P2_NT), (size_t)P2_PIPE_SMEM, st, d, f, in, out, state, (float*)nullptr, 1, maps->in, maps->st, maps->frame, maps->th, ca);
         if (e != cudaSuccess) cudaGetLastError();
     }
-    if (e != cudaSuccess) {
+    if (e != cudaSuccess && ca.static_items != 2) {
         ca.static_items = 0;
         e = launch_pdl(kern, grid, dim3(P2_NT), (size_t)P2_PIPE_SMEM, st, false, d, f, in, out, state, (float*)nullptr, 1, maps->in, maps->st, maps->frame,
                        maps->th, ca);

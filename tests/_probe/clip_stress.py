@@ -17,8 +17,8 @@ for kind, hw in (("default", (1080, 1920)), ("gauss_grade", (1080, 1920)), ("def
     eng = CrtEngine(w, h).configure(p); eng.set_shards(1)
     ref, ref_state = eng.process(fr, fps=30.0); ref = ref.clone(); ref_state = ref_state.clone(); eng.close()
     os.environ["CRT_CLIP"] = "1"
-    for mode in sys.argv[1:] or ["-1", "1", "2", "3"]:
-        os.environ["CRT_CLIP_RELEASE"] = mode
+    for mode in sys.argv[1:] or ["2:1", "2:8", "0:-1", "0:1", "0:2", "1:1"]:      # CRT_CLIP_ITEMS : CRT_CLIP_RELEASE
+        os.environ["CRT_CLIP_ITEMS"], os.environ["CRT_CLIP_RELEASE"] = mode.split(":")
         bad = []
         for r in range(R):
             eng = CrtEngine(w, h).configure(p); eng.set_shards(1)

@@ -517,13 +517,14 @@ def test_clip_mode_is_the_serial_run_bit_for_bit(kind, hw, n, monkeypatch):
     assert torch.equal(res["0"][1], res["1"][1])
 
 
-@pytest.mark.parametrize("env", [{}, {"CRT_CLIP_RELEASE": "1"}, {"CRT_CLIP_RELEASE": "2"}, {"CRT_CLIP_RELEASE": "23"}, {"CRT_CLIP_COOP": "0"},
-                                 {"CRT_CLIP_COOP_GAUSS": "1"}])
+@pytest.mark.parametrize("env", [{}, {"CRT_CLIP_ITEMS": "0"}, {"CRT_CLIP_ITEMS": "1", "CRT_CLIP_COOP_GAUSS": "1"}, {"CRT_CLIP_ITEMS": "2"},
+                                 {"CRT_CLIP_ITEMS": "3"}, {"CRT_CLIP_ITEMS": "0", "CRT_CLIP_RELEASE": "2"}, {"CRT_CLIP_ITEMS": "0", "CRT_CLIP_RELEASE": "23"}])
 @pytest.mark.parametrize("kind", ["default", "gauss_grade"])
 def test_clip_mode_variants_are_bit_exact_too(kind, env, monkeypatch):
-    """Every publication mode that carries a gpu-scope membar (csrc/crt_fused_ps2.cuh clip_publish; the mode without one is
-    measurably racy and not offered), the atomic item counter where the default is a cooperative launch with a fixed stride, and
-    the reverse: same bytes as one launch per frame, twice in a row (a race would show as a difference between runs)."""
+    """The two flag protocols — fixed stride under a cooperative launch (default of the fast-bloom kernel), atomic item counter
+    (default of the gaussian kernel) — with every publication mode that carries a gpu-scope membar, and owned tiles (CTA i keeps
+    tiles i, i + G, ... through the run, no flags; measured slower, opt-in) (csrc/crt_fused_ps2.cuh clip_publish; the mode without one is measurably racy and not offered): same bytes as one
+    launch per frame, twice in a row (a race would show as a difference between runs)."""
     import torch
     from pythoncrt_b200.engine import CrtEngine
     p = _clip_params(kind)
