@@ -414,11 +414,12 @@ struct Ps2Maps {                 // host-encoded tensor maps (crt_abi.cu)
 // One launch per frame leaves a B200 half idle at 1080p: launch latency, table staging and — mostly — the last round of every
 // frame, in which a few CTAs run alone on their SMs (kernel alone 26.8 us per 1080p frame against 17.2 us when concurrent
 // temporal shards fill the gaps, round 2 run 33).  The only cross-frame dependency of these kernels is the persistence state of
-// the SAME tile (crt_filter.py:1092 is per pixel), so a run of frames is one queue of (frame, tile) items, frame-major, handed out
-// by an atomic counter to persistent CTAs; item (f, t) waits for done[t] >= f, published by whoever finished (f - 1, t) once its
-// state tile's TMA store has completed.  Items are handed out in order and only to running CTAs, so the owner of every item an
-// item waits for is resident: no deadlock whatever else shares the GPU.  The result is the serial recurrence exactly — no
-// warm-up halo as with temporal shards.  Per-frame scalars (scanline phase, flicker gain) come from a device array.
+// the SAME tile (crt_filter.py:1092 is per pixel), so a run of frames is one queue of (frame, tile) items, frame-major, worked off
+// by persistent CTAs; item (f, t) may fetch its state once done[t] >= f, published by whoever finished (f - 1, t) after its state
+// tile's TMA store has completed.  Items are taken with a fixed stride under a cooperative launch (every CTA resident), or from
+// an atomic counter — handed out in order and only to running CTAs, so the owner of every item an item waits for is resident:
+// no deadlock whatever else shares the GPU.  The result is the serial recurrence exactly — no warm-up halo as with temporal
+// shards.  Per-frame scalars (scanline phase, flicker gain) travel as kernel parameters.  DESIGN.md 4.8 has the measurements.
 constexpr int P1_ROT = 160;              // phase 1 of the TMA-pipelined kernel: rotation of the thread -> block assignment (see there)
 constexpr int CLIP_B = 224;              // the "next item" thread (warp 7: the lightest in phase 1); thread 0 keeps the state traffic
 constexpr int CLIP_MAX_FRAMES = 64;      // frames per launch: their scalars travel as kernel parameters (no copy to wait for)
