@@ -467,13 +467,20 @@ def _clip_params(kind):
         return base.but(bloom_threshold=0.6)
     if kind == "no_bloom":
         return base.but(bloom_strength=0.0)
+    if kind == "no_triad":             # the general per-pixel tail (FAST = false instantiations)
+        return base.but(triad_strength=0.0, flicker_strength=0.05, flicker_hz=50.0)
+    if kind == "no_triad_no_bloom":
+        return base.but(triad_strength=0.0, bloom_strength=0.0)
+    if kind == "preserve_luma":        # triad with luma preservation: not the composite-LUT tail
+        return base.but(triad_preserve_luma=True)
     raise KeyError(kind)
 
 
 @pytest.mark.parametrize("kind,hw,n", [("default", (1080, 1920), 40), ("default", (720, 1280), 70), ("default", (2160, 3840), 6),
                                        ("slanted_flicker", (1080, 1920), 24), ("threshold", (1080, 1920), 12), ("no_bloom", (720, 1280), 12),
                                        ("default", (480, 640), 130), ("gauss_grade", (1080, 1920), 40), ("gauss_grade", (2160, 3840), 5),
-                                       ("gauss_wide", (1080, 1920), 10)])
+                                       ("gauss_wide", (1080, 1920), 10), ("no_triad", (1080, 1920), 9), ("no_triad_no_bloom", (1080, 1920), 9),
+                                       ("preserve_luma", (1080, 1920), 9)])
 def test_clip_mode_is_the_serial_run_bit_for_bit(kind, hw, n, monkeypatch):
     """Clip mode (csrc/crt_fused_ps2.cuh ClipArgs): a run of frames in ONE launch, chained tile by tile through the persistence
     state (crt_filter.py:1092).  Same kernel arithmetic in the same order per pixel -> identical bytes and identical state to
