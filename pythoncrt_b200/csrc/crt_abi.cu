@@ -314,7 +314,7 @@ struct Call {
 // d_in / n_frames describe the whole clip the frames of this call are taken from (the TMA-pipelined kernels address the
 // clip as ONE tensor: a frame is selected by its index), d_state the state buffer THIS context blends against.
 int prepare_call(crt_ctx* ctx, const uint8_t* d_in, int n_frames, const uint8_t* d_out, float* d_state, const float* d_img, Call* c,
-                 bool concurrent = false) {
+                 bool concurrent = false, int tile_h = 0) {
     if (!ctx->have_params) return fail(ctx, CRT_ERR_INVALID, "crt_set_params has not been called");
     if (!ctx->dev_ok) { int rc = build_dev(ctx); if (rc) return rc; }
     if (n_frames < 0 || (n_frames > 0 && (!d_in || (!d_out && !d_img)))) return fail(ctx, CRT_ERR_INVALID, "null buffer");
@@ -373,7 +373,7 @@ int prepare_call(crt_ctx* ctx, const uint8_t* d_in, int n_frames, const uint8_t*
     }
     // TMA-pipelined block kernels: tensor maps of the clip and of this context's state buffer (or pre-warp image)
     // (single pass, frames one after the other on the GPU: tile height matched to the number of resident CTAs)
-    const int th = (c->want_fused && !concurrent) ? ctx->tile_h : P2_TH;
+    const int th = (c->want_fused && tile_h) ? tile_h : (c->want_fused && !concurrent) ? ctx->tile_h : P2_TH;
     c->pipe = (c->want_fused && ctx->plan.ps2 && c->persist && prepare_ps2_maps(ctx, d, d_in, n_frames, d_state, th)) ||
               (c->want_two_pass && ctx->plan_q.ps2 && prepare_ps2_maps(ctx, ctx->dev_q, d_in, n_frames, ctx->scratch.q));
     // block gaussian kernel: input tile by TMA (a K-specific box over the clip's even rows)
@@ -468,6 +468,23 @@ int launch_frame(crt_ctx* ctx, const Call& c, int index, const uint8_t* in_i, ui
 
 // Clip mode applies to the single-pass block kernel with fast bloom / no bloom whose frames need nothing generated per frame
 // (no noise plane, no glitch table) — the CLI's default chain among them; the caller's state must be blended (persistence > 0).
+int clip_resident(const crt_ctx* ctx) {
+    return ctx->env.sms * ((ctx->plan.gauss_k || (ctx->dev.bloom_mode == 1 && ctx->dev.thr_on)) ? 3 : 4);
+}
+// Tile height of clip-mode launches: the tallest tile that gives the resident CTAs one and a half tiles each (1080p and up: 32
+// rows; 720p: 16), not below 16 rows.  Measured (run 63): a tile costs ~8 us of mostly fixed latency whatever its height (TMA round
+// trips, barriers, the flag protocol), so low tiles only pay as far as they are needed to keep every CTA busy — 720p 9.45 us per
+// frame with 24 rows, 8.63 with 16; VGA in 8-row tiles 8.1 us per frame, slower than one launch per frame with programmatic
+// dependent launch (119 k against 130 k frames/s): frames that small stay out of clip mode.  CRT_CLIP_TH overrides.
+int clip_tile_h(const crt_ctx* ctx) {
+    const int forced = env_int("CRT_CLIP_TH", 0);
+    if (forced >= 8 && forced <= P2_TH && !(forced & 1)) return forced;
+    const int tiles_x = (ctx->W + P2_TW - 1) / P2_TW, resident = clip_resident(ctx);
+    for (int th = P2_TH; th > 16; th -= 2)
+        if (2 * tiles_x * ((ctx->H + th - 1) / th) >= 3 * resident) return th;
+    return 16;
+}
+
 bool clip_wanted(crt_ctx* ctx, const uint8_t* d_out, const float* d_state, const float* d_img, int n_frames) {
     const bool use_clip = env_int("CRT_CLIP", 1) != 0;      // read per call: tests switch it inside one process
     if (!use_clip || !ctx || !ctx->have_params || n_frames < 2 || !d_out || !d_state || d_img || ctx->policy == 1) return false;
@@ -477,11 +494,12 @@ bool clip_wanted(crt_ctx* ctx, const uint8_t* d_out, const float* d_state, const
         return false;
     if (ctx->plan.gauss_k && !fused_gauss_ps2_clip_supported(ctx->dev, ctx->plan.gauss_k)) return false;
     // A tile's frames are a serial chain: a frame takes at least one tile latency, whatever the size.  With fewer tiles than
-    // resident CTAs the chain is the bound (measured, run 43: 720p 11.0 us per frame = one tile latency, 90 k frames/s against
-    // 178 k with four temporal shards; VGA 106 k against 130 k) -> clip mode from one tile per resident CTA upwards.
-    const int ntiles = ((ctx->W + P2_TW - 1) / P2_TW) * ((ctx->H + P2_TH - 1) / P2_TH);
-    const int resident = ctx->env.sms * ((ctx->plan.gauss_k || (ctx->dev.bloom_mode == 1 && ctx->dev.thr_on)) ? 3 : 4);
-    return ntiles >= env_int("CRT_CLIP_MIN_TILES", resident);
+    // resident CTAs the chain is the bound (measured, run 43: 720p in 32-row tiles 11.0 us per frame = one tile latency, 90 k
+    // frames/s against 178 k with four temporal shards; VGA 106 k against 130 k) -> clip mode from one tile per resident CTA
+    // upwards, small frames in LOWER tiles (clip_tile_h: more, shorter chains).
+    const int th = clip_tile_h(ctx);
+    const int ntiles = ((ctx->W + P2_TW - 1) / P2_TW) * ((ctx->H + th - 1) / th);
+    return ntiles >= env_int("CRT_CLIP_MIN_TILES", clip_resident(ctx));
 }
 
 int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_state, int state_valid, float* d_img,
@@ -490,7 +508,7 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
     if (n_frames > 0 && !frames) return fail(ctx, CRT_ERR_INVALID, "null buffer");
     Call c;
     const bool try_clip = clip_wanted(ctx, d_out, d_state, d_img, n_frames);
-    int rc = prepare_call(ctx, d_in, n_frames, d_out, d_state, d_img, &c, try_clip); if (rc) return rc;
+    int rc = prepare_call(ctx, d_in, n_frames, d_out, d_state, d_img, &c, try_clip, try_clip ? clip_tile_h(ctx) : 0); if (rc) return rc;
     static const bool use_pdl = env_int("CRT_PDL", 1) != 0;
     const size_t fb = c.frame_px * 3;
     int launches = 0, i = 0, clip_frames = 0;
@@ -790,7 +808,7 @@ int crt_process(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_stat
     if (K > 1 && ctx->shards_wanted == 0 && env_int("CRT_SHARDS", -1) < 0 && clip_wanted(ctx, d_out, d_state, nullptr, n_frames)) {
         const int ntiles = ((ctx->W + P2_TW - 1) / P2_TW) * ((ctx->H + P2_TH - 1) / P2_TH);
         const int resident = ctx->env.sms * ((ctx->dev.bloom_mode == 1 && ctx->dev.thr_on) ? 3 : 4);
-        if ((!ctx->plan.gauss_k && ntiles < 4 * resident) || env_int("CRT_CLIP_AUTO", 0)) K = 1;
+        if ((!ctx->plan.gauss_k && ntiles >= resident && ntiles < 4 * resident) || env_int("CRT_CLIP_AUTO", 0)) K = 1;      // (720p: shards, 178 k against 115 k)
     }
     if (K > 1 && (d_state || !(ctx->p.persistence > 0.0)))
         return process_sharded(ctx, K, d_in, d_out, d_state, state_valid, frames, n_frames, (cudaStream_t)stream, info);
