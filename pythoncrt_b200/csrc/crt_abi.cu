@@ -274,6 +274,14 @@ int choose_tile_h(int W, int H, int sms, int per_sm, int halo_blocks) {
     if (forced >= 8 && forced <= P2_TH && !(forced & 1)) return forced;
     if (forced < 0 || halo_blocks < 0) return P2_TH;       // halo_blocks < 0: only on request
     const int tiles_x = (W + P2_TW - 1) / P2_TW, slots = sms * per_sm;
+    // frames that do not even half fill the GPU in 32-row tiles (VGA: 150 tiles for 592 CTAs): lower tiles until three fifths of
+    // the CTAs have one — measured (run 66, VGA, TMA-pipelined kernel): 128 k frames/s in 32-row tiles of the plain kernel,
+    // 137 k with 16 rows, 148 k with 12 (400 tiles), 130 k with 8
+    if (2 * tiles_x * ((H + P2_TH - 1) / P2_TH) < slots) {
+        for (int th = P2_TH - 2; th > 12; th -= 2)
+            if (5 * tiles_x * ((H + th - 1) / th) >= 3 * slots) return th;
+        return 12;
+    }
     const double a = 2.0 + 1.2 * halo_blocks;
     auto cost = [&](int th) { return (double)((tiles_x * ((H + th - 1) / th) + slots - 1) / slots) * (th + a); };
     int best = P2_TH;

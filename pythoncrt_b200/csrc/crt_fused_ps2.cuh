@@ -814,7 +814,7 @@ inline int run_fused_ps2(LaunchEnv& env, const Dev& d, const FrameDev& f, const 
     // TMA-pipelined variant (4 CTAs per SM, 3 with the bloom threshold on): pays off when there is a state to fetch and
     // every CTA walks over several tiles
     static const int pipe_min_tiles = env_int("CRT_PIPE_MIN_TILES", 256);      // measured: wins at 720p (460 tiles, +1.5 %), 1080p (+15 %) and 4K, neutral at VGA (150)
-    if (maps && (q_out || has_prev) && ntiles >= pipe_min_tiles) {
+    if (maps && (q_out || has_prev) && (int)grid.x * ((d.H + maps->th - 1) / maps->th) >= pipe_min_tiles) {
         const bool thr = d.bloom_mode == 1 && d.thr_on;
         auto kern = pick_ps2_pipe<false>(d, f, fast, thr);
         // the opt-in shared-memory size is a per-device, per-kernel attribute: set once per context and kernel
