@@ -480,7 +480,7 @@ def _clip_params(kind):
                                        ("slanted_flicker", (1080, 1920), 24), ("threshold", (1080, 1920), 12), ("no_bloom", (720, 1280), 12),
                                        ("default", (480, 640), 130), ("gauss_grade", (1080, 1920), 40), ("gauss_grade", (2160, 3840), 5),
                                        ("gauss_wide", (1080, 1920), 10), ("no_triad", (1080, 1920), 9), ("no_triad_no_bloom", (1080, 1920), 9),
-                                       ("preserve_luma", (1080, 1920), 9)])
+                                       ("preserve_luma", (1080, 1920), 9), ("default", (4320, 7680), 4), ("gauss_grade", (4320, 7680), 4)])
 def test_clip_mode_is_the_serial_run_bit_for_bit(kind, hw, n, monkeypatch):
     """Clip mode (csrc/crt_fused_ps2.cuh ClipArgs): a run of frames in ONE launch, chained tile by tile through the persistence
     state (crt_filter.py:1092).  Same kernel arithmetic in the same order per pixel -> identical bytes and identical state to
