@@ -430,6 +430,7 @@ struct ClipArgs {
     int static_items = 0;                // 2: owned tiles — CTA i keeps tiles i, i + G, ... through all frames of the run (no flags at all);
                                          // 1: item = blockIdx.x + k * gridDim.x (the launch is cooperative: every CTA is resident); 0: atomic counter
     int per_sm = 0;                      // owned tiles: > 0 = CTAs per SM when consecutive CTAs share an SM -> rank = (i % per_sm) * SMs + i / per_sm
+    int w0_idle = 1;                     // fast-bloom kernel: warp 0 does no phase-1 blocks (CRT_CLIP_W0)
     int release = 1;                     // publication / acquisition mode bits (clip_publish; CRT_CLIP_RELEASE)
     FrameVar fv[CLIP_MAX_FRAMES];
 };
@@ -635,7 +636,15 @@ __global__ void __launch_bounds__(P2_NT, (THR || (CLIP && SPEC == 0)) ? 3 : 4) k
             for (int i = 0; i < NIT; ++i) {
                 // blocks are dealt to the threads rotated by P1_ROT: the last, partial round (100 of 612 blocks) then falls to warps 3-6
                 // and the two bookkeeping warps (thread 0, thread CLIP_B) reach the barrier early enough to absorb their waits
-                const int u = ((tid + P1_ROT) & (P2_NT - 1)) + i * P2_NT;
+                // Clip mode: warp 0 — whose thread 0 waits for the previous store, fences and publishes — keeps out of phase 1
+                // altogether (612 blocks are three rounds for 224 threads as for 256) and the partial round skips warp 7 (thread
+                // CLIP_B).  Measured (run 68): default chain 4K 47.6 -> 46.5 us per frame, 1080p 12.27 -> 12.05.
+                int u = ((tid + P1_ROT) & (P2_NT - 1)) + i * P2_NT;
+                if (CLIP && ca.w0_idle) {
+                    int v = tid - 32 + 196;
+                    if (v >= 224) v -= 224;
+                    u = tid < 32 ? (1 << 30) : v + i * 224;
+                }
                 if (u < P2_BW * ((th >> 1) + 2)) {
                     const int bj = u / P2_BW, bi = u - bj * P2_BW;
                     uint32_t r0, r1, r2;
@@ -783,6 +792,7 @@ inline int run_fused_ps2_clip(LaunchEnv& env, const Dev& d, const FrameDev& f, c
     // 22.8 against 18.7): a CTA works its items off at a latency-bound pace whatever else runs on the SM, so the frame takes
     // ceil(tiles / CTAs) tile latencies — 2 at 1080p where the flag protocols spread 1.72 per CTA evenly.
     const int items = env_int("CRT_CLIP_ITEMS", 1);
+    ca.w0_idle = env_int("CRT_CLIP_W0", 1) != 0;
     const dim3 grid((unsigned)(nitems < resident ? nitems : resident));
     cudaError_t e = cudaErrorNotSupported;
     if (items == 2 || items == 3) {      // 3: ranks permuted for a placement that puts consecutive CTAs on one SM
