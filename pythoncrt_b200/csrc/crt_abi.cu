@@ -17,6 +17,7 @@
 #include "crt_fused_gauss_ps2.cuh"
 #include "crt_gather_box.cuh"
 #include "crt_launch.h"
+#include "crt_policy.h"
 
 using namespace crt;
 
@@ -263,31 +264,9 @@ int run_staged(crt_ctx* ctx, const FrameDev& f, const uint8_t* d_in, uint8_t* d_
     return launch_staged(ctx->env, ctx->dev, f, d_in, d_out, d_state, has_prev, d_img, ctx->scratch, st, launches);
 }
 
-// Tile height of the single-pass block kernels for a frame processed ALONE on the GPU.  Their CTAs are persistent and walk the
-// tiles with a fixed stride, so a frame costs ceil(tiles / resident CTAs) tile times: 1080p in 64 x 32 tiles is 1020 tiles for
-// 444 (gaussian bloom, 3 CTAs per SM) or 592 (4 per SM) CTAs = 3 resp. 2 rounds of which the last is 30 % resp. 72 % full.
-// A lower tile (26 rows: 1260 tiles, 2.84 rounds) fills the rounds; the cost model is rounds x (rows + a), a = the rows' worth
-// of halo and per-tile overhead, and 32 rows stay unless the model gains 6 %.  4K: 6.9 rounds, nothing to gain.  Concurrent
-// temporal shards fill each other's partial rounds and keep 32 rows (process_sharded).  CRT_TILE_H overrides.
+// Tile height of the per-frame single-pass block kernels: policy_tile_h (crt_policy.h); CRT_TILE_H overrides.
 int choose_tile_h(int W, int H, int sms, int per_sm, int halo_blocks) {
-    const int forced = env_int("CRT_TILE_H", 0);
-    if (forced >= 8 && forced <= P2_TH && !(forced & 1)) return forced;
-    if (forced < 0 || halo_blocks < 0) return P2_TH;       // halo_blocks < 0: only on request
-    const int tiles_x = (W + P2_TW - 1) / P2_TW, slots = sms * per_sm;
-    // frames that do not even half fill the GPU in 32-row tiles (VGA: 150 tiles for 592 CTAs): lower tiles until three fifths of
-    // the CTAs have one — measured (run 66, VGA, TMA-pipelined kernel): 128 k frames/s in 32-row tiles of the plain kernel,
-    // 137 k with 16 rows, 148 k with 12 (400 tiles), 130 k with 8
-    if (2 * tiles_x * ((H + P2_TH - 1) / P2_TH) < slots) {
-        for (int th = P2_TH - 2; th > 12; th -= 2)
-            if (5 * tiles_x * ((H + th - 1) / th) >= 3 * slots) return th;
-        return 12;
-    }
-    const double a = 2.0 + 1.2 * halo_blocks;
-    auto cost = [&](int th) { return (double)((tiles_x * ((H + th - 1) / th) + slots - 1) / slots) * (th + a); };
-    int best = P2_TH;
-    for (int th = P2_TH - 2; th >= 20; th -= 2)
-        if (cost(th) < cost(best)) best = th;
-    return cost(best) <= 0.94 * cost(P2_TH) ? best : P2_TH;
+    return policy_tile_h(W, H, sms, per_sm, halo_blocks, env_int("CRT_TILE_H", 0));
 }
 
 // Tensor maps for k_fused_ps2_pipe: the clip as uint8 [frames * H/2 even rows][W*3] (box 256 x 18) and the
@@ -479,19 +458,8 @@ int launch_frame(crt_ctx* ctx, const Call& c, int index, const uint8_t* in_i, ui
 int clip_resident(const crt_ctx* ctx) {
     return ctx->env.sms * ((ctx->plan.gauss_k || (ctx->dev.bloom_mode == 1 && ctx->dev.thr_on)) ? 3 : 4);
 }
-// Tile height of clip-mode launches: the tallest tile that gives the resident CTAs one and a half tiles each (1080p and up: 32
-// rows; 720p: 16), not below 16 rows.  Measured (run 63): a tile costs ~8 us of mostly fixed latency whatever its height (TMA round
-// trips, barriers, the flag protocol), so low tiles only pay as far as they are needed to keep every CTA busy — 720p 9.45 us per
-// frame with 24 rows, 8.63 with 16; VGA in 8-row tiles 8.1 us per frame, slower than one launch per frame with programmatic
-// dependent launch (119 k against 130 k frames/s): frames that small stay out of clip mode.  CRT_CLIP_TH overrides.
-int clip_tile_h(const crt_ctx* ctx) {
-    const int forced = env_int("CRT_CLIP_TH", 0);
-    if (forced >= 8 && forced <= P2_TH && !(forced & 1)) return forced;
-    const int tiles_x = (ctx->W + P2_TW - 1) / P2_TW, resident = clip_resident(ctx);
-    for (int th = P2_TH; th > 16; th -= 2)
-        if (2 * tiles_x * ((ctx->H + th - 1) / th) >= 3 * resident) return th;
-    return 16;
-}
+// Tile height of clip-mode launches: policy_clip_tile_h (crt_policy.h); CRT_CLIP_TH overrides.
+int clip_tile_h(const crt_ctx* ctx) { return policy_clip_tile_h(ctx->W, ctx->H, clip_resident(ctx), env_int("CRT_CLIP_TH", 0)); }
 
 bool clip_wanted(crt_ctx* ctx, const uint8_t* d_out, const float* d_state, const float* d_img, int n_frames) {
     const bool use_clip = env_int("CRT_CLIP", 1) != 0;      // read per call: tests switch it inside one process
@@ -501,13 +469,8 @@ bool clip_wanted(crt_ctx* ctx, const uint8_t* d_out, const float* d_state, const
     if (!(ctx->plan.ok && ctx->plan.ps2 && p.persistence > 0.0 && !ctx->dev.noise_on && !glitch_active(p) && !ctx->plan_w.ok && !ctx->plan_s.ok))
         return false;
     if (ctx->plan.gauss_k && !fused_gauss_ps2_clip_supported(ctx->dev, ctx->plan.gauss_k)) return false;
-    // A tile's frames are a serial chain: a frame takes at least one tile latency, whatever the size.  With fewer tiles than
-    // resident CTAs the chain is the bound (measured, run 43: 720p in 32-row tiles 11.0 us per frame = one tile latency, 90 k
-    // frames/s against 178 k with four temporal shards; VGA 106 k against 130 k) -> clip mode from one tile per resident CTA
-    // upwards, small frames in LOWER tiles (clip_tile_h: more, shorter chains).
-    const int th = clip_tile_h(ctx);
-    const int ntiles = ((ctx->W + P2_TW - 1) / P2_TW) * ((ctx->H + th - 1) / th);
-    return ntiles >= env_int("CRT_CLIP_MIN_TILES", clip_resident(ctx));
+    // (a tile's frames are a serial chain: only frames with a tile per resident CTA — policy_clip_size_ok, crt_policy.h)
+    return policy_clip_size_ok(ctx->W, ctx->H, clip_resident(ctx), env_int("CRT_CLIP_TH", 0), env_int("CRT_CLIP_MIN_TILES", 0));
 }
 
 int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_state, int state_valid, float* d_img,
@@ -581,25 +544,11 @@ int process_impl(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_sta
 // run CONCURRENTLY on one GPU, each on its own stream with its own context (scratch buffers, tensor maps), launches
 // interleaved frame by frame.  Measured (round 2, profiles/tools/concurrency_probe.py): default chain at 4K 18.7k -> 21.9k
 // frames/s with 3 shards, 1080p gaussian chain 40.3k -> 55.7k, VGA 113k -> 185k with 4.
-int halo_frames(double persistence) {
-    if (!(persistence > 0.0)) return 0;
-    return (int)ceil(log(1.0 / 2040.0) / log(persistence));
-}
+int halo_frames(double persistence) { return policy_halo_frames(persistence); }
 
 int choose_shards(const crt_ctx* ctx, int n_frames) {
     static const int forced = env_int("CRT_SHARDS", -1);
-    const int wanted = forced >= 0 ? forced : ctx->shards_wanted;
-    if (wanted == 1 || n_frames < 2) return 1;
-    // automatic mode: an 8K frame fills the GPU on its own (16 000+ tiles per kernel); concurrent shards only thrash L2 there
-    // (measured, run 33: BASELINE configs[4] 1 245 frames/s on one stream, 1 203 with three shards)
-    if (wanted == 0 && (size_t)ctx->W * ctx->H >= (size_t)24 << 20) return 1;
-    const int halo = halo_frames(ctx->p.persistence);
-    // a shard must be worth its warm-up: at least 8 halos (<= 12.5 % extra frames) and 48 frames long
-    const int min_chunk = halo * 8 > 48 ? halo * 8 : 48;
-    int k = n_frames / min_chunk;
-    const int cap = wanted == 0 ? 4 : wanted;
-    if (k > cap) k = cap;
-    return k < 1 ? 1 : k;
+    return policy_shards(ctx->shards_wanted, forced, n_frames, ctx->p.persistence, ctx->W, ctx->H);
 }
 
 int sync_shards(crt_ctx* ctx, int K) {
@@ -809,15 +758,10 @@ int crt_process(crt_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, float* d_stat
                 void* stream, crt_launch_info* info) {
     if (!ctx) return CRT_ERR_INVALID;
     int K = (ctx->have_params && d_in && d_out && frames) ? choose_shards(ctx, n_frames) : 1;
-    // Automatic mode: clip mode (one stream, the serial recurrence exactly) where it measures faster than concurrent shards of
-    // per-frame launches — the fast-bloom / no-bloom kernel below four rounds of tiles per frame (1080p: 80-84 k against 79 k frames/s);
-    // at 4K (6.9 rounds) the shards keep a 3 % edge (21.6 k against 20.9 k), and so they do for the gaussian kernel (BASELINE
-    // configs[1], run 56: 56-58 k against 53 k).  crt_set_shards(1) always gives clip mode where it applies.
-    if (K > 1 && ctx->shards_wanted == 0 && env_int("CRT_SHARDS", -1) < 0 && clip_wanted(ctx, d_out, d_state, nullptr, n_frames)) {
-        const int ntiles = ((ctx->W + P2_TW - 1) / P2_TW) * ((ctx->H + P2_TH - 1) / P2_TH);
-        const int resident = ctx->env.sms * ((ctx->dev.bloom_mode == 1 && ctx->dev.thr_on) ? 3 : 4);
-        if ((!ctx->plan.gauss_k && ntiles >= resident && ntiles < 4 * resident) || env_int("CRT_CLIP_AUTO", 0)) K = 1;      // (720p: shards, 178 k against 115 k)
-    }
+    // automatic mode: clip mode instead of shards where it measures faster (policy_auto_prefers_clip, crt_policy.h);
+    // crt_set_shards(1) always gives clip mode where it applies
+    if (K > 1 && ctx->shards_wanted == 0 && env_int("CRT_SHARDS", -1) < 0 && clip_wanted(ctx, d_out, d_state, nullptr, n_frames) &&
+        (policy_auto_prefers_clip(ctx->plan.gauss_k != 0, ctx->W, ctx->H, clip_resident(ctx)) || env_int("CRT_CLIP_AUTO", 0))) K = 1;
     if (K > 1 && (d_state || !(ctx->p.persistence > 0.0)))
         return process_sharded(ctx, K, d_in, d_out, d_state, state_valid, frames, n_frames, (cudaStream_t)stream, info);
     if (info) { info->reserved[0] = 1; info->reserved[1] = 0; }

@@ -31,7 +31,7 @@ def _stale() -> bool:
         return True
     t = os.path.getmtime(SO)
     deps = [SRC] + [os.path.join(CSRC, f) for f in ("crt_math.cuh", "crt_stages.cuh", "crt_derive.h", "crt_fused.cuh", "crt_fused_ps2.cuh",
-                                                   "crt_fused_warp_src.cuh", "crt_launch.h", "crt_tma.cuh")]
+                                                   "crt_fused_warp_src.cuh", "crt_launch.h", "crt_tma.cuh", "crt_policy.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -143,3 +143,11 @@ def check_warp_src(params: CrtParams, W: int, H: int, variant: str = "export"):
     if rc:
         raise RuntimeError(why.value.decode())
     return dict(ok=bool(out[0]), tiles=out[1], violations=out[2], max_quads=out[3], box_px=out[4], why=why.value.decode())
+
+
+def policy(w: int, h: int, *, sms: int = 148, per_sm: int = 4, halo_blocks: int = 1, gaussian: bool = False, shards_wanted: int = 0,
+           n_frames: int = 600, persistence: float = 0.2) -> dict:
+    """csrc/crt_policy.h: the C ABI's scheduling decisions for a frame size / kernel family (pure functions, no GPU)."""
+    out = (C.c_int * 6)()
+    lib().emu_policy(w, h, sms, per_sm, halo_blocks, int(gaussian), shards_wanted, n_frames, C.c_double(persistence), out)
+    return dict(tile_h=out[0], clip_tile_h=out[1], clip_size_ok=bool(out[2]), shards=out[3], auto_prefers_clip=bool(out[4]), halo=out[5])

@@ -14,6 +14,7 @@
 #include "../../pythoncrt_b200/csrc/crt_stages.cuh"
 #include "../../pythoncrt_b200/csrc/crt_fused.cuh"   // host-side tile planner only
 #include "../../pythoncrt_b200/csrc/crt_fused_warp_src.cuh"   // host-side planner of the source-driven warp kernel
+#include "../../pythoncrt_b200/csrc/crt_policy.h"             // scheduling policy of the C ABI (pure functions)
 
 using namespace crt;
 
@@ -182,4 +183,16 @@ extern "C" void emu_pow_unit(const float* x, float* out, int n, double y) {
     alignas(16) static float pow_tab[POW_TAB_FLOATS];
     fill_pow_table(pow_tab);
     for (int i = 0; i < n; ++i) out[i] = pow_unit(x[i], (float)y, pow_tab);
+}
+
+// ---- scheduling policy (crt_policy.h): out = {tile_h per frame, clip tile_h, clip size ok, shards, auto prefers clip, halo} ----
+extern "C" void emu_policy(int W, int H, int sms, int per_sm, int halo_blocks, int gaussian, int shards_wanted, int n_frames, double persistence,
+                           int* out) {
+    const int resident = sms * per_sm;
+    out[0] = policy_tile_h(W, H, sms, per_sm, halo_blocks, 0);
+    out[1] = policy_clip_tile_h(W, H, resident, 0);
+    out[2] = policy_clip_size_ok(W, H, resident, 0, 0) ? 1 : 0;
+    out[3] = policy_shards(shards_wanted, -1, n_frames, persistence, W, H);
+    out[4] = policy_auto_prefers_clip(gaussian != 0, W, H, resident) ? 1 : 0;
+    out[5] = policy_halo_frames(persistence);
 }

@@ -316,3 +316,41 @@ def test_source_driven_warp_planner_partitions_the_output(w, h, warp):
     # glitch / non-monotone maps / odd sizes are left to the two-pass path
     assert not host_emu.check_warp_src(CrtParams(noise_strength=0.0, warp_strength=0.15, glitch_amp_px=8, glitch_height_frac=0.5), 128, 96)["ok"]
     assert not host_emu.check_warp_src(CrtParams(noise_strength=0.0, warp_strength=-0.9), 128, 96)["ok"]
+
+
+# ------------------------------------------------------------------------------------ scheduling policy --
+def test_scheduling_policy_matches_the_measured_choices():
+    """csrc/crt_policy.h (called by crt_abi.cu): tile heights, temporal shards and the choice between clip mode and shards for
+    the frame sizes DESIGN.md 4.8 / 5 quotes, on a 148-SM device."""
+    import host_emu
+    P = host_emu.policy
+    # per-frame launches of the fast-bloom kernel (4 CTAs per SM = 592 resident): 1080p fills two rounds with 28-row tiles, 4K keeps
+    # 32, VGA (150 tiles in 32-row tiles) goes down to 12 rows = 400 tiles
+    assert P(1920, 1080)["tile_h"] == 28
+    assert P(3840, 2160)["tile_h"] == 32
+    assert P(7680, 4320)["tile_h"] == 32
+    assert P(640, 480)["tile_h"] == 12
+    assert P(1280, 720)["tile_h"] in (26, 28)
+    # the gaussian kernel keeps 32 rows (crt_abi.cu passes halo_blocks = -1 for it: lower tiles measured slower)
+    assert P(1920, 1080, per_sm=3, halo_blocks=-1, gaussian=True)["tile_h"] == 32
+    # clip mode: 32 rows from 1080p up, 16 rows at 720p, nothing below (a tile per resident CTA is the minimum)
+    assert P(1920, 1080)["clip_tile_h"] == 32 and P(1920, 1080)["clip_size_ok"]
+    assert P(3840, 2160)["clip_tile_h"] == 32 and P(3840, 2160)["clip_size_ok"]
+    assert P(1280, 720)["clip_tile_h"] == 16 and P(1280, 720)["clip_size_ok"]
+    assert P(640, 480)["clip_tile_h"] == 16 and not P(640, 480)["clip_size_ok"]
+    assert P(1920, 1080, per_sm=3, gaussian=True)["clip_size_ok"]
+    # automatic mode: clip mode instead of shards only for the fast-bloom kernel between one and four rounds of tiles per frame
+    assert P(1920, 1080)["auto_prefers_clip"]
+    assert not P(3840, 2160)["auto_prefers_clip"]          # 6.9 rounds: shards keep a small edge
+    assert not P(1280, 720)["auto_prefers_clip"]           # 0.8 rounds: chain-bound
+    assert not P(1920, 1080, per_sm=3, gaussian=True)["auto_prefers_clip"]
+    # temporal shards: up to 4, each at least 48 frames and 8 warm-ups long; none for 24-Mpixel frames; off on request
+    assert P(1920, 1080, n_frames=600)["shards"] == 4 and P(1920, 1080, n_frames=600)["halo"] == 5
+    assert P(1920, 1080, n_frames=100)["shards"] == 2 and P(1920, 1080, n_frames=64)["shards"] == 1
+    assert P(1920, 1080, n_frames=600, persistence=0.95)["halo"] == 149
+    assert P(1920, 1080, n_frames=600, persistence=0.95)["shards"] == 1       # 8 x 149 warm-up frames do not fit
+    assert P(1920, 1080, n_frames=4000, persistence=0.95)["shards"] == 3
+    assert P(7680, 4320, n_frames=600)["shards"] == 1
+    assert P(1920, 1080, n_frames=600, shards_wanted=1)["shards"] == 1
+    assert P(1920, 1080, n_frames=600, shards_wanted=8)["shards"] == 8
+    assert P(1920, 1080, n_frames=600, persistence=0.0)["halo"] == 0
